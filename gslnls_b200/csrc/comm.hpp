@@ -1,0 +1,13 @@
+// comm.hpp -- multi-GPU exchange of the normal-equation packet (one process per GPU).
+#pragma once
+#include <cuda_runtime.h>
+
+struct gslnls_comm {
+    void *nccl = nullptr; // ncclComm_t
+    int rank = 0, nranks = 1, device = 0;
+};
+
+namespace gslnls {
+// sum `count` doubles in place across ranks on `stream`; every rank receives bitwise the same result
+int comm_allreduce_sum(gslnls_comm *c, double *dev_buf, size_t count, cudaStream_t stream);
+}

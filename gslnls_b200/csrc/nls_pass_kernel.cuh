@@ -1,0 +1,432 @@
+// nls_pass_kernel.cuh -- K1: the fused residual / Jacobian / normal-equation pass, and K4: the
+// final materialisation of residuals and Jacobian.  sm_100a, FP64.
+//
+// This text is compiled at run time by NVRTC, appended to the model source that expr.cpp generates
+// (which defines GSLNLS_P, GSLNLS_NVAR, GSLNLS_JAC_MODE, GSLNLS_FVV_MODE and nls_model_*), so the
+// model is inlined into the loop and a Jacobian row only ever exists in registers.
+//
+// What one launch replaces in the reference (per evaluation at a parameter vector theta):
+//   gsl_f_large   src/nls_large.c:426-472  -> f_i = fn(theta)_i - y_i, non-finite fn -> +Inf
+//   gsl_df_large  src/nls_large.c:474-653  -> J (n x p), NaN scan, transposing copy,
+//                                            cblas_dgemv  g = J^T f   (:629)
+//                                            cblas_dsyrk  J^T J lower (:633)
+//   gsl_blas_ddot f.f (src/nls_fit.c:178)
+//   gsl_fvv_large src/nls_large.c:655-713 + second df call for J^T fvv (mode 2)
+// None of f, J, fvv is written to memory: the kernel reads 8*(nvar+1) (+8 with weights) bytes per
+// observation and writes one packet per CTA.
+//
+// Determinism: fixed grid, fixed per-thread observation sets, fixed-shape shuffle trees, CTA
+// partials summed in CTA order by whichever CTA arrives last.  No floating-point atomics.
+//
+// Tunables (NVRTC -D): NLS_BLOCK threads per CTA, NLS_UNROLL independent loads in flight per
+// thread and array, NLS_MINB CTAs per SM for __launch_bounds__, NLS_VEC 2 = 16-byte loads (needs
+// 16-byte aligned columns) or 1, NLS_HAS_W weights present, NLS_STREAM 1 = L1::no_allocate loads.
+#include "nls_abi.h"
+
+#ifndef NLS_BLOCK
+#define NLS_BLOCK 256
+#endif
+#ifndef NLS_UNROLL
+#define NLS_UNROLL 4
+#endif
+#ifndef NLS_MINB
+#define NLS_MINB 2
+#endif
+#ifndef NLS_VEC
+#define NLS_VEC 2
+#endif
+#ifndef NLS_HAS_W
+#define NLS_HAS_W 0
+#endif
+#ifndef NLS_STREAM
+#define NLS_STREAM 1
+#endif
+
+#define NLS_P GSLNLS_P
+#define NLS_NV (GSLNLS_NVAR > 0 ? GSLNLS_NVAR : 1)
+#define NLS_NPK (NLS_P * (NLS_P + 1) / 2)
+#define NLS_PK (NLS_NPK + NLS_P + 1)
+#define NLS_NW (NLS_BLOCK / 32)
+
+enum { NLS_MODE_IDLE = 0, NLS_MODE_FJ = 1, NLS_MODE_FVV = 2, NLS_MODE_JVP = 3 };
+
+// ------------------------------------------------------------------------------------ loads
+static __device__ __forceinline__ double2 nls_ld2(const double *p)
+{
+    double2 r;
+#if NLS_STREAM
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#else
+    asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#endif
+    return r;
+}
+static __device__ __forceinline__ double nls_ld1(const double *p)
+{
+    double r;
+#if NLS_STREAM
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+#else
+    asm("ld.global.nc.f64 %0, [%1];" : "=d"(r) : "l"(p));
+#endif
+    return r;
+}
+
+static __device__ __forceinline__ bool nls_finite(double v)
+{
+    // exponent field all ones <=> Inf or NaN; integer test keeps the FP64 pipe free
+    return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
+}
+
+// ------------------------------------------------------------------------------------ model glue
+struct NlsThread {
+    double th[NLS_P];  // parameters
+    double vv[NLS_P];  // velocity / direction (modes 2, 3)
+    double dl[NLS_P];  // finite-difference steps  (src/fdjac.c:39-41, :96-98)
+    double idl[NLS_P]; // 1 / step
+    double h_fvv;
+};
+
+static __device__ __forceinline__ void nls_fj(const NlsThread &T, const double *x, double &f, double *J)
+{
+#if GSLNLS_JAC_MODE == 0
+    nls_model_fj(T.th, x, f, J);
+#elif GSLNLS_JAC_MODE == 1
+    // forward differences: (f(theta + delta e_j) - f(theta)) * (1/delta), src/fdjac.c:44-59
+    f = nls_model_f(T.th, x);
+#pragma unroll
+    for (int j = 0; j < NLS_P; ++j) {
+        double tp[NLS_P];
+#pragma unroll
+        for (int k = 0; k < NLS_P; ++k)
+            tp[k] = T.th[k];
+        tp[j] = T.th[j] + T.dl[j];
+        J[j] = (nls_model_f(tp, x) - f) * T.idl[j];
+    }
+#else
+    // centred differences at +-delta/2, src/fdjac.c:101-124
+    f = nls_model_f(T.th, x);
+#pragma unroll
+    for (int j = 0; j < NLS_P; ++j) {
+        double tp[NLS_P];
+#pragma unroll
+        for (int k = 0; k < NLS_P; ++k)
+            tp[k] = T.th[k];
+        tp[j] = T.th[j] + 0.5 * T.dl[j];
+        const double f1 = nls_model_f(tp, x);
+        tp[j] = T.th[j] - 0.5 * T.dl[j];
+        const double f0 = nls_model_f(tp, x);
+        J[j] = (f1 - f0) * T.idl[j];
+    }
+#endif
+}
+
+// one observation, accumulated into the thread-private packet
+template <int MODE>
+static __device__ __forceinline__ void nls_observe(const NlsThread &T, const double *x, double y, double w,
+                                                   double *acc)
+{
+    double f, J[NLS_P];
+    nls_fj(T, x, f, J);
+#if NLS_HAS_W
+    const double sw = sqrt(w); // sqrt_wts_i = sqrt(w_i), src/fdf.c:60-64
+#else
+    (void)w;
+#endif
+    if (MODE == NLS_MODE_FJ) {
+        double r = f - y;
+        if (!nls_finite(f))
+            r = NLS_INF; // src/nls_large.c:464-465
+#if NLS_HAS_W
+        r *= sw;
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            J[j] *= sw;
+#endif
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NLS_P; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j, ++e)
+                acc[e] = fma(J[i], J[j], acc[e]);
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            acc[NLS_NPK + j] = fma(J[j], r, acc[NLS_NPK + j]);
+        acc[NLS_NPK + NLS_P] = fma(r, r, acc[NLS_NPK + NLS_P]);
+    } else if (MODE == NLS_MODE_FVV) {
+        double h;
+#if GSLNLS_FVV_MODE == 1
+        h = nls_model_fvv(T.th, T.vv, x);
+#elif GSLNLS_FVV_MODE == 2
+        {
+            // fvv = (2/h) ((f(x + h v) - f(x)) / h - J v), src/fdfvv.c:47-74
+            double tp[NLS_P];
+#pragma unroll
+            for (int k = 0; k < NLS_P; ++k)
+                tp[k] = T.th[k] + T.h_fvv * T.vv[k];
+            const double fp = nls_model_f(tp, x);
+            const double hinv = 1.0 / T.h_fvv;
+            double u = 0.0;
+#pragma unroll
+            for (int k = 0; k < NLS_P; ++k)
+                u += J[k] * T.vv[k];
+            h = (2.0 * hinv) * ((fp - f) * hinv - u);
+        }
+#else
+        h = 0.0;
+#endif
+#if NLS_HAS_W
+        h *= sw;
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            J[j] *= sw;
+#endif
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            acc[j] = fma(J[j], h, acc[j]);
+        acc[NLS_P] = fma(h, h, acc[NLS_P]);
+    } else { // NLS_MODE_JVP: u = J d ; J^T u ; u^T u   (matrix-free products for Steihaug CG)
+#if NLS_HAS_W
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            J[j] *= sw;
+#endif
+        double u = 0.0;
+#pragma unroll
+        for (int k = 0; k < NLS_P; ++k)
+            u += J[k] * T.vv[k];
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j)
+            acc[j] = fma(J[j], u, acc[j]);
+        acc[NLS_P] = fma(u, u, acc[NLS_P]);
+    }
+}
+
+// stream this CTA's share of the observations through nls_observe<MODE>
+template <int MODE>
+static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, const NlsThread &T, double *acc)
+{
+    const long long n = prm.n;
+    const long long stride = (long long)gridDim.x * NLS_BLOCK;
+    long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
+#if NLS_VEC == 2
+    const long long nv = n >> 1;
+    for (; i + (NLS_UNROLL - 1) * stride < nv; i += NLS_UNROLL * stride) {
+        double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            const long long o = 2 * (i + u * stride);
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k)
+                xv[u][k] = nls_ld2(prm.vars[k] + o);
+            yv[u] = nls_ld2(prm.y + o);
+#if NLS_HAS_W
+            wv[u] = nls_ld2(prm.w + o);
+#else
+            wv[u] = make_double2(1.0, 1.0);
+#endif
+        }
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k) {
+                xa[k] = xv[u][k].x;
+                xb[k] = xv[u][k].y;
+            }
+            nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc);
+            nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc);
+        }
+    }
+    for (; i < nv; i += stride) {
+        const long long o = 2 * i;
+        double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k) {
+            const double2 t = nls_ld2(prm.vars[k] + o);
+            xa[k] = t.x;
+            xb[k] = t.y;
+        }
+        const double2 yy = nls_ld2(prm.y + o);
+#if NLS_HAS_W
+        const double2 ww = nls_ld2(prm.w + o);
+#else
+        const double2 ww = make_double2(1.0, 1.0);
+#endif
+        nls_observe<MODE>(T, xa, yy.x, ww.x, acc);
+        nls_observe<MODE>(T, xb, yy.y, ww.y, acc);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long o = n - 1;
+        double xa[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = nls_ld1(prm.vars[k] + o);
+#if NLS_HAS_W
+        const double ww = nls_ld1(prm.w + o);
+#else
+        const double ww = 1.0;
+#endif
+        nls_observe<MODE>(T, xa, nls_ld1(prm.y + o), ww, acc);
+    }
+#else
+    for (; i + (NLS_UNROLL - 1) * stride < n; i += NLS_UNROLL * stride) {
+        double xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            const long long o = i + u * stride;
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k)
+                xv[u][k] = nls_ld1(prm.vars[k] + o);
+            yv[u] = nls_ld1(prm.y + o);
+#if NLS_HAS_W
+            wv[u] = nls_ld1(prm.w + o);
+#else
+            wv[u] = 1.0;
+#endif
+        }
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u)
+            nls_observe<MODE>(T, xv[u], yv[u], wv[u], acc);
+    }
+    for (; i < n; i += stride) {
+        double xa[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = nls_ld1(prm.vars[k] + i);
+#if NLS_HAS_W
+        const double ww = nls_ld1(prm.w + i);
+#else
+        const double ww = 1.0;
+#endif
+        nls_observe<MODE>(T, xa, nls_ld1(prm.y + i), ww, acc);
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------ K1
+extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const NlsPassParams prm)
+{
+    const int cand = blockIdx.y;
+    const double *req = prm.req + (size_t)cand * prm.req_stride;
+    const int mode = prm.force_mode > 0 ? prm.force_mode : (int)req[0];
+    if (mode == NLS_MODE_IDLE)
+        return; // this candidate has finished; uniform for the whole CTA
+
+    NlsThread T;
+#pragma unroll
+    for (int j = 0; j < NLS_P; ++j) {
+        T.th[j] = req[1 + j];
+        T.vv[j] = req[1 + NLS_P + j];
+        double d = prm.h_df * fabs(T.th[j]);
+        if (d == 0.0)
+            d = prm.h_df;
+        T.dl[j] = d;
+        T.idl[j] = 1.0 / d;
+    }
+    T.h_fvv = prm.h_fvv;
+
+    double acc[NLS_PK];
+#pragma unroll
+    for (int e = 0; e < NLS_PK; ++e)
+        acc[e] = 0.0;
+
+    if (mode == NLS_MODE_FJ)
+        nls_stream<NLS_MODE_FJ>(prm, T, acc);
+    else if (mode == NLS_MODE_FVV)
+        nls_stream<NLS_MODE_FVV>(prm, T, acc);
+    else
+        nls_stream<NLS_MODE_JVP>(prm, T, acc);
+
+    // ---- CTA reduction: fixed shuffle tree, then warps summed in warp order ----
+    __shared__ double sred[NLS_NW][NLS_PK];
+    __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < NLS_PK; ++e) {
+        double v = acc[e];
+        v += __shfl_down_sync(0xffffffffu, v, 16);
+        v += __shfl_down_sync(0xffffffffu, v, 8);
+        v += __shfl_down_sync(0xffffffffu, v, 4);
+        v += __shfl_down_sync(0xffffffffu, v, 2);
+        v += __shfl_down_sync(0xffffffffu, v, 1);
+        if (lane == 0)
+            sred[warp][e] = v;
+    }
+    __syncthreads();
+    double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
+    for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NLS_NW; ++w)
+            s += sred[w][e];
+        part[e] = s;
+    }
+
+    // ---- grid reduction by the last CTA to arrive, CTA order fixed ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(prm.ticket + cand, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    const double *parts = prm.partials + (size_t)cand * gridDim.x * prm.pk_stride;
+    double *out = prm.packet + (size_t)cand * prm.pk_stride;
+    for (int e = warp; e < NLS_PK; e += NLS_NW) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32)
+            s += __ldcg(parts + (size_t)b * prm.pk_stride + e);
+        s += __shfl_down_sync(0xffffffffu, s, 16);
+        s += __shfl_down_sync(0xffffffffu, s, 8);
+        s += __shfl_down_sync(0xffffffffu, s, 4);
+        s += __shfl_down_sync(0xffffffffu, s, 2);
+        s += __shfl_down_sync(0xffffffffu, s, 1);
+        if (lane == 0)
+            out[e] = s;
+    }
+    if (threadIdx.x == 0)
+        prm.ticket[cand] = 0u; // ready for the next launch
+}
+
+// ------------------------------------------------------------------------------------ K4
+// resid_i = sqrt(w_i) (fn_i - y_i) and grad[i + n j] = sqrt(w_i) J_ij at the final parameters:
+// the arrays C_nls_large returns at src/nls_large.c:339-385, produced once, after the fit.
+extern "C" __global__ void __launch_bounds__(256) nls_materialise(const NlsMaterialiseParams prm)
+{
+    NlsThread T;
+#pragma unroll
+    for (int j = 0; j < NLS_P; ++j) {
+        T.th[j] = prm.theta[j];
+        T.vv[j] = 0.0;
+        double d = prm.h_df * fabs(T.th[j]);
+        if (d == 0.0)
+            d = prm.h_df;
+        T.dl[j] = d;
+        T.idl[j] = 1.0 / d;
+    }
+    T.h_fvv = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride) {
+        double xa[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = prm.vars[k][i];
+        double f, J[NLS_P];
+        nls_fj(T, xa, f, J);
+        double r = f - prm.y[i];
+        if (!nls_finite(f))
+            r = NLS_INF;
+        const double sw = prm.w ? sqrt(prm.w[i]) : 1.0;
+        if (prm.resid)
+            prm.resid[i] = r * sw;
+        if (prm.grad) {
+#pragma unroll
+            for (int j = 0; j < NLS_P; ++j)
+                prm.grad[i + prm.n * (long long)j] = J[j] * sw;
+        }
+    }
+}

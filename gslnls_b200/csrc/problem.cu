@@ -1,0 +1,738 @@
+// problem.cu -- host orchestration behind the C ABI (include/gslnls_b200.h).
+//
+// Plays the role of C_nls_large_internal (src/nls_large.c:77-424) and of the driver loop
+// gsl_multilarge_nlinear_driver2 (src/nls_fit.c:153-224), except that the loop body is two kernels
+// per trial step -- K1 fused pass (NVRTC, nls_pass_kernel.cuh) and K3 trust-region step
+// (trs_kernel.cu) -- enqueued in chunks on one stream; the host only reads back a completion
+// counter between chunks.  The p x p state never leaves the device during a fit.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gslnls_b200.h"
+#include "comm.hpp"
+#include "model.hpp"
+#include "nls_abi.h"
+#include "trs_launch.hpp"
+
+namespace gslnls {
+thread_local std::string g_last_error;
+void set_error(const std::string &s) { g_last_error = s; }
+} // namespace gslnls
+using namespace gslnls;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+            return GSLNLS_ECUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+struct gslnls_problem {
+    const gslnls_model *model = nullptr;
+    int p = 0, nvar = 0, has_w = 0, device = 0;
+    int64_t n = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // data
+    std::vector<double *> owned; // buffers we allocated
+    const double *dvars[NLS_MAX_VARS] = {nullptr};
+    const double *dy = nullptr, *dw = nullptr;
+    bool bound = false;
+    // kernels
+    Variant *var = nullptr;
+    VariantKey vkey{};
+    int num_sms = 0, grid_x = 0, occ = 0;
+    // workspace (sized for cap candidates)
+    int cap = 0, cap_grid = 0, cap_trace = 0;
+    int req_stride = 0, pk_stride = 0, state_stride = 0;
+    double *d_req = nullptr, *d_partials = nullptr, *d_packet = nullptr, *d_state = nullptr, *d_starts = nullptr;
+    double *d_partrace = nullptr, *d_ssrtrace = nullptr, *d_condtrace = nullptr, *d_theta = nullptr;
+    unsigned *d_ticket = nullptr;
+    int *d_ndone = nullptr;
+    int *h_ndone = nullptr; // pinned
+    gslnls_comm *comm = nullptr;
+    // active fit
+    trs::Params P{};
+    bool active = false;
+    int ncand = 1;
+    std::vector<double> start;
+    double h_df = 0, h_fvv = 0;
+    int64_t launches = 0, passes = 0;
+    int chunk = 8;
+};
+
+static void free_workspace(gslnls_problem *pb)
+{
+    cudaFree(pb->d_req); cudaFree(pb->d_partials); cudaFree(pb->d_packet); cudaFree(pb->d_state);
+    cudaFree(pb->d_starts); cudaFree(pb->d_ticket); cudaFree(pb->d_ndone);
+    pb->d_req = pb->d_partials = pb->d_packet = pb->d_state = pb->d_starts = nullptr;
+    pb->d_ticket = nullptr; pb->d_ndone = nullptr;
+    pb->cap = 0;
+}
+
+static int ensure_kernels(gslnls_problem *pb, bool batch)
+{
+    int vec = 2;
+    for (int k = 0; k < pb->nvar; ++k)
+        if (reinterpret_cast<uintptr_t>(pb->dvars[k]) & 15u)
+            vec = 1;
+    if ((reinterpret_cast<uintptr_t>(pb->dy) & 15u) || (pb->dw && (reinterpret_cast<uintptr_t>(pb->dw) & 15u)))
+        vec = 1;
+    const KernelTune t = default_tune(pb->p);
+    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb};
+    if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
+        return GSLNLS_SUCCESS;
+    try {
+        pb->var = &const_cast<gslnls_model *>(pb->model)->load(key);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return GSLNLS_ECOMPILE;
+    }
+    pb->vkey = key;
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)pb->var->pass, key.block, 0));
+    pb->occ = std::max(occ, 1);
+    return GSLNLS_SUCCESS;
+}
+
+// grid size along x for one candidate
+static int pick_grid(const gslnls_problem *pb, int ncand)
+{
+    const int64_t nv = pb->vkey.vec == 2 ? pb->n / 2 : pb->n;
+    const int64_t need = std::max<int64_t>(1, (nv + pb->vkey.block - 1) / pb->vkey.block);
+    int64_t full = (int64_t)pb->num_sms * pb->occ;
+    if (ncand > 1) // candidates fill the machine together
+        full = std::max<int64_t>(1, full / std::min<int64_t>(ncand, full));
+    return (int)std::min<int64_t>(need, full);
+}
+
+static int ensure_workspace(gslnls_problem *pb, int ncand, int grid_x, int ntrace)
+{
+    const int p = pb->p;
+    pb->req_stride = trs::request_doubles(p);
+    pb->pk_stride = trs::packet_doubles(p) + 1;
+    pb->state_stride = trs::state_doubles(p);
+    if (ncand > pb->cap || grid_x > pb->cap_grid) {
+        free_workspace(pb);
+        const size_t c = (size_t)ncand;
+        CK(cudaMalloc(&pb->d_req, sizeof(double) * c * pb->req_stride));
+        CK(cudaMalloc(&pb->d_partials, sizeof(double) * c * grid_x * pb->pk_stride));
+        CK(cudaMalloc(&pb->d_packet, sizeof(double) * c * pb->pk_stride));
+        CK(cudaMalloc(&pb->d_state, sizeof(double) * c * pb->state_stride));
+        CK(cudaMalloc(&pb->d_starts, sizeof(double) * c * p));
+        CK(cudaMalloc(&pb->d_ticket, sizeof(unsigned) * c));
+        CK(cudaMalloc(&pb->d_ndone, sizeof(int)));
+        CK(cudaMemsetAsync(pb->d_ticket, 0, sizeof(unsigned) * c, pb->stream));
+        CK(cudaMemsetAsync(pb->d_packet, 0, sizeof(double) * c * pb->pk_stride, pb->stream));
+        CK(cudaMemsetAsync(pb->d_req, 0, sizeof(double) * c * pb->req_stride, pb->stream));
+        pb->cap = ncand;
+        pb->cap_grid = grid_x;
+    }
+    if (ntrace > pb->cap_trace) {
+        cudaFree(pb->d_partrace); cudaFree(pb->d_ssrtrace); cudaFree(pb->d_condtrace);
+        CK(cudaMalloc(&pb->d_partrace, sizeof(double) * (size_t)ntrace * p));
+        CK(cudaMalloc(&pb->d_ssrtrace, sizeof(double) * ntrace));
+        CK(cudaMalloc(&pb->d_condtrace, sizeof(double) * ntrace));
+        pb->cap_trace = ntrace;
+    }
+    if (!pb->d_theta)
+        CK(cudaMalloc(&pb->d_theta, sizeof(double) * 2 * p));
+    return GSLNLS_SUCCESS;
+}
+
+static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
+{
+    NlsPassParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    for (int k = 0; k < pb->nvar; ++k)
+        prm.vars[k] = pb->dvars[k];
+    prm.y = pb->dy;
+    prm.w = pb->dw;
+    prm.n = pb->n;
+    prm.req = pb->d_req;
+    prm.partials = pb->d_partials;
+    prm.packet = pb->d_packet;
+    prm.ticket = pb->d_ticket;
+    prm.h_df = pb->h_df;
+    prm.h_fvv = pb->h_fvv;
+    prm.req_stride = pb->req_stride;
+    prm.pk_stride = pb->pk_stride;
+    prm.force_mode = force_mode;
+    void *args[] = {&prm};
+    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args, 0,
+                        pb->stream));
+    ++pb->launches;
+    ++pb->passes;
+    return GSLNLS_SUCCESS;
+}
+
+static int exchange_packet(gslnls_problem *pb, size_t count)
+{
+    if (!pb->comm || pb->comm->nranks <= 1)
+        return GSLNLS_SUCCESS;
+    return comm_allreduce_sum(pb->comm, pb->d_packet, count, pb->stream);
+}
+
+// ------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+GSLNLS_API int gslnls_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int has_weights, int device,
+                                     gslnls_problem **out)
+{
+    if (!m || !out || n_local < 0)
+        return GSLNLS_EINVAL;
+    *out = nullptr;
+    if (gslnls_device_count() <= device) {
+        set_error("no usable CUDA device (this library has no CPU path)");
+        return GSLNLS_ENODEVICE;
+    }
+    if (m->nvar > NLS_MAX_VARS) {
+        set_error("too many predictor columns");
+        return GSLNLS_EINVAL;
+    }
+    CK(cudaSetDevice(device));
+    gslnls_problem *pb = new gslnls_problem();
+    pb->model = m;
+    pb->p = m->p;
+    pb->nvar = m->nvar;
+    pb->n = n_local;
+    pb->has_w = has_weights ? 1 : 0;
+    pb->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    pb->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&pb->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&pb->ev0));
+    CK(cudaEventCreate(&pb->ev1));
+    CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
+    if (const char *c = std::getenv("GSLNLS_CHUNK"))
+        pb->chunk = std::max(1, std::atoi(c));
+    *out = pb;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
+{
+    if (!pb)
+        return;
+    cudaSetDevice(pb->device);
+    cudaStreamSynchronize(pb->stream);
+    for (double *b : pb->owned)
+        cudaFree(b);
+    free_workspace(pb);
+    cudaFree(pb->d_partrace); cudaFree(pb->d_ssrtrace); cudaFree(pb->d_condtrace); cudaFree(pb->d_theta);
+    cudaFreeHost(pb->h_ndone);
+    cudaEventDestroy(pb->ev0);
+    cudaEventDestroy(pb->ev1);
+    cudaStreamDestroy(pb->stream);
+    delete pb;
+}
+
+GSLNLS_API int gslnls_problem_upload(gslnls_problem *pb, const double *const *vars, const double *y,
+                                     const double *weights)
+{
+    if (!pb || !y || (pb->nvar > 0 && !vars) || (pb->has_w && !weights))
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(pb->n, 1);
+    if (pb->bound || pb->owned.empty()) {
+        for (double *b : pb->owned)
+            cudaFree(b);
+        pb->owned.clear();
+        for (int k = 0; k < pb->nvar + 1 + pb->has_w; ++k) {
+            double *d = nullptr;
+            CK(cudaMalloc(&d, bytes));
+            pb->owned.push_back(d);
+        }
+        pb->bound = false;
+    }
+    for (int k = 0; k < pb->nvar; ++k) {
+        CK(cudaMemcpyAsync(pb->owned[k], vars[k], sizeof(double) * pb->n, cudaMemcpyHostToDevice, pb->stream));
+        pb->dvars[k] = pb->owned[k];
+    }
+    CK(cudaMemcpyAsync(pb->owned[pb->nvar], y, sizeof(double) * pb->n, cudaMemcpyHostToDevice, pb->stream));
+    pb->dy = pb->owned[pb->nvar];
+    pb->dw = nullptr;
+    if (pb->has_w) {
+        CK(cudaMemcpyAsync(pb->owned[pb->nvar + 1], weights, sizeof(double) * pb->n, cudaMemcpyHostToDevice,
+                           pb->stream));
+        pb->dw = pb->owned[pb->nvar + 1];
+    }
+    pb->var = nullptr;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_bind_device(gslnls_problem *pb, const double *const *dev_vars, const double *dev_y,
+                                          const double *dev_weights)
+{
+    if (!pb || !dev_y || (pb->nvar > 0 && !dev_vars) || (pb->has_w && !dev_weights))
+        return GSLNLS_EINVAL;
+    for (int k = 0; k < pb->nvar; ++k)
+        pb->dvars[k] = dev_vars[k];
+    pb->dy = dev_y;
+    pb->dw = pb->has_w ? dev_weights : nullptr;
+    pb->bound = true;
+    pb->var = nullptr;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm)
+{
+    if (!pb)
+        return GSLNLS_EINVAL;
+    pb->comm = comm;
+    return GSLNLS_SUCCESS;
+}
+
+static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch)
+{
+    if (!pb->dy) {
+        set_error("no data: call gslnls_problem_upload or gslnls_problem_bind_device first");
+        return GSLNLS_EINVAL;
+    }
+    CK(cudaSetDevice(pb->device));
+    int rc = ensure_kernels(pb, batch);
+    if (rc)
+        return rc;
+    pb->grid_x = pick_grid(pb, ncand);
+    rc = ensure_workspace(pb, ncand, pb->grid_x, ntrace);
+    return rc;
+}
+
+GSLNLS_API int gslnls_problem_eval_packet(gslnls_problem *pb, const double *theta, double *packet)
+{
+    if (!pb || !theta || !packet)
+        return GSLNLS_EINVAL;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    pb->h_df = pb->h_df > 0 ? pb->h_df : 1.4901161193847656e-08;
+    CK(cudaMemcpyAsync(pb->d_theta, theta, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(trs_launch_set_request(pb->d_req, trs::MODE_FJ, pb->d_theta, nullptr, p, pb->stream));
+    rc = launch_pass(pb, 1, trs::MODE_FJ);
+    if (rc)
+        return rc;
+    rc = exchange_packet(pb, trs::packet_doubles(p));
+    if (rc)
+        return rc;
+    CK(cudaMemcpyAsync(packet, pb->d_packet, sizeof(double) * trs::packet_doubles(p), cudaMemcpyDeviceToHost,
+                       pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_eval_jtfvv(gslnls_problem *pb, const double *theta, const double *v, double *out)
+{
+    if (!pb || !theta || !v || !out)
+        return GSLNLS_EINVAL;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    pb->h_df = pb->h_df > 0 ? pb->h_df : 1.4901161193847656e-08;
+    pb->h_fvv = pb->h_fvv > 0 ? pb->h_fvv : 0.02;
+    CK(cudaMemcpyAsync(pb->d_theta, theta, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(cudaMemcpyAsync(pb->d_theta + p, v, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(trs_launch_set_request(pb->d_req, trs::MODE_FVV, pb->d_theta, pb->d_theta + p, p, pb->stream));
+    rc = launch_pass(pb, 1, trs::MODE_FVV);
+    if (rc)
+        return rc;
+    rc = exchange_packet(pb, p + 1);
+    if (rc)
+        return rc;
+    CK(cudaMemcpyAsync(out, pb->d_packet, sizeof(double) * p, cudaMemcpyDeviceToHost, pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_time_passes(gslnls_problem *pb, const double *theta, int npass, float *ms_per_pass)
+{
+    if (!pb || !theta || npass < 1 || !ms_per_pass)
+        return GSLNLS_EINVAL;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    pb->h_df = pb->h_df > 0 ? pb->h_df : 1.4901161193847656e-08;
+    CK(cudaMemcpyAsync(pb->d_theta, theta, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(trs_launch_set_request(pb->d_req, trs::MODE_FJ, pb->d_theta, nullptr, p, pb->stream));
+    CK(cudaEventRecord(pb->ev0, pb->stream));
+    for (int i = 0; i < npass; ++i) {
+        rc = launch_pass(pb, 1, trs::MODE_FJ);
+        if (rc)
+            return rc;
+    }
+    CK(cudaEventRecord(pb->ev1, pb->stream));
+    CK(cudaEventSynchronize(pb->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, pb->ev0, pb->ev1));
+    *ms_per_pass = ms / (float)npass;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta, double *resid, double *grad)
+{
+    if (!pb || !theta)
+        return GSLNLS_EINVAL;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    double *d_resid = nullptr, *d_grad = nullptr;
+    const size_t n1 = (size_t)std::max<int64_t>(pb->n, 1);
+    if (resid)
+        CK(cudaMalloc(&d_resid, sizeof(double) * n1));
+    if (grad)
+        CK(cudaMalloc(&d_grad, sizeof(double) * n1 * p));
+    CK(cudaMemcpyAsync(pb->d_theta, theta, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    NlsMaterialiseParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    for (int k = 0; k < pb->nvar; ++k)
+        prm.vars[k] = pb->dvars[k];
+    prm.y = pb->dy;
+    prm.w = pb->dw;
+    prm.n = pb->n;
+    prm.theta = pb->d_theta;
+    prm.resid = d_resid;
+    prm.grad = d_grad;
+    prm.h_df = pb->h_df > 0 ? pb->h_df : 1.4901161193847656e-08;
+    void *args[] = {&prm};
+    const int blocks = (int)std::min<int64_t>((pb->n + 255) / 256 > 0 ? (pb->n + 255) / 256 : 1, (int64_t)pb->num_sms * 8);
+    CK(cudaLaunchKernel((const void *)pb->var->materialise, dim3(blocks), dim3(256), args, 0, pb->stream));
+    ++pb->launches;
+    if (resid)
+        CK(cudaMemcpyAsync(resid, d_resid, sizeof(double) * pb->n, cudaMemcpyDeviceToHost, pb->stream));
+    if (grad)
+        CK(cudaMemcpyAsync(grad, d_grad, sizeof(double) * pb->n * p, cudaMemcpyDeviceToHost, pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));
+    cudaFree(d_resid);
+    cudaFree(d_grad);
+    return GSLNLS_SUCCESS;
+}
+
+static int fill_params(gslnls_problem *pb, const int *ci, const double *cd, int batch_iters)
+{
+    trs::Params &P = pb->P;
+    P.p = pb->p;
+    P.maxiter = ci[0];
+    P.trace = ci[1] ? 1 : 0;
+    P.trs = (ci[2] >= 1 && ci[2] <= 5) ? ci[2] : 0;       // src/nls_large.c:97-116
+    P.scale = (ci[3] == 1 || ci[3] == 2) ? ci[3] : 0;     // :119-129
+    P.batch_iters = batch_iters;
+    const int64_t nranks = pb->comm ? pb->comm->nranks : 1;
+    P.cg_maxit = std::max<int64_t>(pb->n * nranks, 1);   // GSL default max_iter = 0 -> n
+    P.factor_up = cd[0]; P.factor_down = cd[1]; P.avmax = cd[2]; P.h_df = cd[3]; P.h_fvv = cd[4]; // :135-139
+    P.xtol = cd[5]; P.ftol = cd[6]; P.gtol = cd[7];
+    P.cg_tol = 1.0e-6;                                     // GSL default tol
+    pb->h_df = cd[3];
+    pb->h_fvv = cd[4];
+    if (P.maxiter < 1) {
+        set_error("maxiter must be >= 1");
+        return GSLNLS_EINVAL;
+    }
+    if (P.p > trs_max_p()) {
+        set_error("p exceeds the dense trust-region kernel limit (100)");
+        return GSLNLS_EINVAL;
+    }
+    if (P.trs == trs::TRS_LMACCEL && pb->model->spec.fvv_mode == GSLNLS_FVV_NONE) {
+        // R/nls_large.R:354-356
+        set_error("analytic second derivative function 'fvv' is required, but none is available");
+        return GSLNLS_EINVAL;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start, const int *control_int,
+                                        const double *control_dbl)
+{
+    if (!pb || !start || !control_int || !control_dbl)
+        return GSLNLS_EINVAL;
+    int rc = fill_params(pb, control_int, control_dbl, 0);
+    if (rc)
+        return rc;
+    const int ntrace = pb->P.trace ? pb->P.maxiter + 1 : 0;
+    rc = prepare(pb, 1, ntrace, false);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    pb->start.assign(start, start + p);
+    pb->ncand = 1;
+    CK(cudaMemcpyAsync(pb->d_starts, start, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    if (ntrace) {
+        CK(cudaMemsetAsync(pb->d_partrace, 0, sizeof(double) * (size_t)ntrace * p, pb->stream));
+        CK(cudaMemsetAsync(pb->d_ssrtrace, 0, sizeof(double) * ntrace, pb->stream));
+        CK(cudaMemsetAsync(pb->d_condtrace, 0, sizeof(double) * ntrace, pb->stream));
+    }
+    CK(trs_launch_reset(pb->d_state, pb->state_stride, pb->d_req, pb->req_stride, pb->d_starts, p, 1, pb->d_ndone,
+                        pb->stream));
+    ++pb->launches;
+    pb->active = true;
+    pb->passes = 0;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *done, int64_t *passes_run,
+                                      float *device_ms)
+{
+    if (!pb || !pb->active)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    const int p = pb->p;
+    const bool tr = pb->P.trace != 0;
+    int64_t run = 0;
+    int fin = 0;
+    CK(cudaEventRecord(pb->ev0, pb->stream));
+    while (!fin && (max_passes <= 0 || run < max_passes)) {
+        int todo = pb->chunk;
+        if (max_passes > 0)
+            todo = (int)std::min<int64_t>(todo, max_passes - run);
+        for (int i = 0; i < todo; ++i) {
+            int rc = launch_pass(pb, 1, 0);
+            if (rc)
+                return rc;
+            rc = exchange_packet(pb, trs::packet_doubles(p));
+            if (rc)
+                return rc;
+            CK(trs_launch_step(pb->P, pb->d_state, pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr,
+                               tr ? pb->d_ssrtrace : nullptr, tr ? pb->d_condtrace : nullptr, pb->d_ndone,
+                               pb->stream));
+            ++pb->launches;
+        }
+        run += todo;
+        CK(cudaMemcpyAsync(pb->h_ndone, pb->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        fin = pb->h_ndone[0] >= 1;
+    }
+    CK(cudaEventRecord(pb->ev1, pb->stream));
+    CK(cudaEventSynchronize(pb->ev1));
+    if (device_ms)
+        CK(cudaEventElapsedTime(device_ms, pb->ev0, pb->ev1));
+    if (done)
+        *done = fin;
+    if (passes_run)
+        *passes_run = run;
+    return GSLNLS_SUCCESS;
+}
+
+static double *dup(const double *src, size_t n)
+{
+    double *d = (double *)std::malloc(sizeof(double) * (n ? n : 1));
+    if (src)
+        std::memcpy(d, src, sizeof(double) * n);
+    return d;
+}
+
+GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, gslnls_result *out)
+{
+    if (!pb || !out || !pb->active)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    const int p = pb->p;
+    std::memset(out, 0, sizeof(*out));
+    std::vector<double> S(pb->state_stride);
+    CK(cudaMemcpyAsync(S.data(), pb->d_state, sizeof(double) * pb->state_stride, cudaMemcpyDeviceToHost, pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));
+    pb->active = false;
+
+    int status = (int)S[trs::S_STATUS];
+    const bool finished = (int)S[trs::S_PHASE] == trs::PH_DONE;
+    if (!finished)
+        status = GSLNLS_CONTINUE; // fit_end before completion (benchmark use)
+    const bool ok = status == GSLNLS_SUCCESS || status == GSLNLS_EMAXITER || !finished;
+    const int64_t nranks = pb->comm ? pb->comm->nranks : 1;
+    out->n = pb->n * nranks;
+    out->n_local = pb->n;
+    out->p = p;
+    const double *v = S.data() + trs::S_COUNT;
+    out->par = dup(ok ? v : pb->start.data(), p);          // src/nls_large.c:293-302
+    out->covar = dup(v + 6 * p + p * p, (size_t)p * p);    // :311-326
+    if (!ok || !finished)
+        for (int i = 0; i < p * p; ++i)
+            out->covar[i] = NAN;
+    out->jtj = dup(v + 6 * p, (size_t)p * p);
+    for (int i = 0; i < p; ++i) // mirror the stored lower triangle
+        for (int j = i + 1; j < p; ++j)
+            out->jtj[i * p + j] = out->jtj[j * p + i];
+    out->grad_vec = dup(v + 2 * p, p);
+    out->ssr = S[trs::S_CHISQ1];
+    out->ssrtol = S[trs::S_CHISQ0] - S[trs::S_CHISQ1];
+    out->chisq_init = S[trs::S_CHISQ_INIT];
+    out->niter = (int)S[trs::S_NITER];
+    out->conv = status;
+    out->info = (int)S[trs::S_INFO];
+    out->status = gslnls_strerror(status);
+    out->algorithm = gslnls_trs_name(pb->P.trs);
+    out->neval[0] = (int64_t)S[trs::S_NEVAL_F];
+    out->neval[1] = (int64_t)S[trs::S_NEVAL_DFU];
+    out->neval[2] = (int64_t)S[trs::S_NEVAL_DF2];
+    out->neval[3] = (int64_t)S[trs::S_NEVAL_FVV];
+    out->npass = (int64_t)S[trs::S_NPASS];
+    if (pb->P.trace) {
+        const int nt = pb->P.maxiter + 1;
+        out->ntrace = nt;
+        out->partrace = dup(nullptr, (size_t)nt * p);
+        out->ssrtrace = dup(nullptr, nt);
+        out->condtrace = dup(nullptr, nt);
+        CK(cudaMemcpy(out->partrace, pb->d_partrace, sizeof(double) * (size_t)nt * p, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->ssrtrace, pb->d_ssrtrace, sizeof(double) * nt, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out->condtrace, pb->d_condtrace, sizeof(double) * nt, cudaMemcpyDeviceToHost));
+    }
+    if (want_resid_grad) {
+        out->resid = dup(nullptr, (size_t)pb->n);
+        out->grad = dup(nullptr, (size_t)pb->n * p);
+        if (ok && finished) {
+            int rc = gslnls_problem_residuals(pb, out->par, out->resid, out->grad); // :339-385
+            if (rc)
+                return rc;
+        } else {
+            for (int64_t i = 0; i < pb->n; ++i)
+                out->resid[i] = NAN;
+            for (int64_t i = 0; i < pb->n * p; ++i)
+                out->grad[i] = NAN;
+        }
+    }
+    return status;
+}
+
+GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const int *control_int,
+                                  const double *control_dbl, int want_resid_grad, gslnls_result *out)
+{
+    int rc = gslnls_problem_fit_begin(pb, start, control_int, control_dbl);
+    if (rc)
+        return rc;
+    int done = 0;
+    // every trial step is one pass (two with geodesic acceleration); maxiter * 17 trials * 2 bounds it
+    const int64_t hard_cap = (int64_t)pb->P.maxiter * 34 + 8;
+    int64_t total = 0;
+    while (!done && total < hard_cap) {
+        int64_t run = 0;
+        rc = gslnls_problem_fit_run(pb, pb->chunk * 4, &done, &run, nullptr);
+        if (rc)
+            return rc;
+        total += run;
+    }
+    return gslnls_problem_fit_end(pb, want_resid_grad, out);
+}
+
+GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb) { return pb ? pb->launches : 0; }
+
+GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars, const double *y,
+                                const double *weights, int64_t n, const double *start, const int *control_int,
+                                const double *control_dbl, int device, int want_resid_grad, gslnls_result *out)
+{
+    if (!m || !y || !start || !control_int || !control_dbl || !out)
+        return GSLNLS_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    if (n < m->p) {
+        // R/nls_large.R:286-288
+        set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
+        return GSLNLS_EINVAL;
+    }
+    gslnls_problem *pb = nullptr;
+    int rc = gslnls_problem_create(m, n, weights != nullptr, device, &pb);
+    if (rc)
+        return rc;
+    rc = gslnls_problem_upload(pb, vars, y, weights);
+    if (rc == GSLNLS_SUCCESS)
+        rc = gslnls_problem_fit(pb, start, control_int, control_dbl, want_resid_grad, out);
+    gslnls_problem_free(pb);
+    return rc;
+}
+
+GSLNLS_API void gslnls_result_free(gslnls_result *r)
+{
+    if (!r)
+        return;
+    std::free(r->par); std::free(r->covar); std::free(r->partrace); std::free(r->ssrtrace);
+    std::free(r->condtrace); std::free(r->resid); std::free(r->grad); std::free(r->jtj); std::free(r->grad_vec);
+    std::memset(r, 0, sizeof(*r));
+}
+
+// ---- batched multi-start inner kernels ------------------------------------------------------
+GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts, int S, const int *control_int,
+                                        const double *control_dbl, double *par_out, double *ssr_out,
+                                        double *logdet_out, int *conv_out, int *niter_out)
+{
+    if (!pb || !starts || S < 1 || !control_int || !control_dbl)
+        return GSLNLS_EINVAL;
+    if (pb->p > 8) {
+        set_error("batched multi-start supports p <= 8");
+        return GSLNLS_EINVAL;
+    }
+    if (S > 65535) {
+        set_error("at most 65535 candidates per batch");
+        return GSLNLS_EINVAL;
+    }
+    int rc = fill_params(pb, control_int, control_dbl, control_int[0]);
+    if (rc)
+        return rc;
+    pb->P.trace = 0;
+    rc = prepare(pb, S, 0, true);
+    if (rc)
+        return rc;
+    const int p = pb->p;
+    CK(cudaMemcpyAsync(pb->d_starts, starts, sizeof(double) * (size_t)S * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(trs_launch_reset(pb->d_state, pb->state_stride, pb->d_req, pb->req_stride, pb->d_starts, p, S, pb->d_ndone,
+                        pb->stream));
+    ++pb->launches;
+    const int64_t hard_cap = (int64_t)pb->P.maxiter * 34 + 8;
+    int64_t total = 0;
+    int fin = 0;
+    while (!fin && total < hard_cap) {
+        for (int i = 0; i < pb->chunk; ++i) {
+            rc = launch_pass(pb, S, 0);
+            if (rc)
+                return rc;
+            rc = exchange_packet(pb, (size_t)S * pb->pk_stride);
+            if (rc)
+                return rc;
+            CK(trs_launch_step_batch(pb->P, pb->d_state, pb->state_stride, pb->d_packet, pb->pk_stride, pb->d_req,
+                                     pb->req_stride, S, pb->d_ndone, pb->stream));
+            ++pb->launches;
+        }
+        total += pb->chunk;
+        CK(cudaMemcpyAsync(pb->h_ndone, pb->d_ndone, sizeof(int), cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        fin = pb->h_ndone[0] >= S;
+    }
+    std::vector<double> St((size_t)S * pb->state_stride);
+    CK(cudaMemcpy(St.data(), pb->d_state, sizeof(double) * St.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < S; ++c) {
+        const double *s = St.data() + (size_t)c * pb->state_stride;
+        if (par_out)
+            std::memcpy(par_out + (size_t)c * p, s + trs::S_COUNT, sizeof(double) * p);
+        if (ssr_out)
+            ssr_out[c] = s[trs::S_CHISQ1];
+        if (logdet_out)
+            logdet_out[c] = s[trs::S_LOGDET0];
+        if (conv_out)
+            conv_out[c] = (int)s[trs::S_PHASE] == trs::PH_DONE ? (int)s[trs::S_STATUS] : GSLNLS_CONTINUE;
+        if (niter_out)
+            niter_out[c] = (int)s[trs::S_NITER];
+    }
+    return GSLNLS_SUCCESS;
+}
+
+} // extern "C"

@@ -1,0 +1,19 @@
+// trs_launch.hpp -- host-callable launchers of the K3 kernels (trs_kernel.cu)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "trs_core.h"
+
+namespace gslnls {
+int trs_max_p();
+cudaError_t trs_launch_step(const trs::Params &P, double *state, const double *packet, double *req,
+                            double *partrace, double *ssrtrace, double *condtrace, int *ndone,
+                            cudaStream_t stream);
+cudaError_t trs_launch_step_batch(const trs::Params &P, double *states, int state_stride, const double *packets,
+                                  int pk_stride, double *reqs, int req_stride, int ncand, int *ndone,
+                                  cudaStream_t stream);
+cudaError_t trs_launch_reset(double *states, int state_stride, double *reqs, int req_stride, const double *starts,
+                             int p, int ncand, int *ndone, cudaStream_t stream);
+cudaError_t trs_launch_set_request(double *req, int mode, const double *theta, const double *v, int p,
+                                   cudaStream_t stream);
+} // namespace gslnls

@@ -1,0 +1,197 @@
+/*
+ * gslnls_b200.h -- C ABI of libgslnls_b200.so: the B200-native gsl_nls_large() hot path.
+ *
+ * This library replaces exactly one reference entry point and what runs under it:
+ *
+ *     SEXP C_nls_large(SEXP fn, SEXP y, SEXP jac, SEXP fvv, SEXP env, SEXP start, SEXP weights,
+ *                      SEXP control_int, SEXP control_dbl)          -- src/nls_large.c:66
+ *     registered at src/init.c:9,16, called from R/nls_large.R:411 and :598,
+ *
+ * i.e. C_nls_large_internal (src/nls_large.c:77-424), its three callbacks gsl_f_large (:426),
+ * gsl_df_large (:474), gsl_fvv_large (:655), callback_large (:715), the driver
+ * gsl_multilarge_nlinear_driver2 (src/nls_fit.c:153-224) and libgsl's multilarge_nlinear trust
+ * solver underneath.  R closures cannot execute on a GPU, so the (fn, jac, fvv, env) quadruple
+ * is replaced by a compiled model (formula text -> symbolic Jacobian / directional second
+ * derivative -> NVRTC device code); every other argument crosses the boundary unchanged:
+ * y, weights (raw, not sqrt), start, control_int[7], control_dbl[8] exactly as packed at
+ * R/nls_large.R:383-407, and the result carries the fields of the list built at
+ * src/nls_large.c:276-416.  Status codes are GSL errno values (0 success, 9 EBADFUNC,
+ * 11 EMAXITER, 27 ENOPROG, ...), strings are gsl_strerror()'s.
+ *
+ * Plain C types only; host pointers unless a name says "device".  The library owns all device
+ * memory it allocates.  One host thread per problem handle.  There is no CPU compute path:
+ * every entry point that needs the GPU fails with GSLNLS_ENODEVICE if none is usable.
+ */
+#ifndef GSLNLS_B200_H
+#define GSLNLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSLNLS_API __attribute__((visibility("default")))
+
+/* return codes beyond GSL's errno range */
+enum {
+    GSLNLS_SUCCESS = 0,
+    GSLNLS_FAILURE = -1,
+    GSLNLS_CONTINUE = -2,
+    GSLNLS_EDOM = 1,
+    GSLNLS_EINVAL = 4,
+    GSLNLS_ENOMEM = 8,
+    GSLNLS_EBADFUNC = 9,
+    GSLNLS_EMAXITER = 11,
+    GSLNLS_EBADLEN = 19,
+    GSLNLS_ENOPROG = 27,
+    GSLNLS_ETOLF = 29,
+    GSLNLS_ETOLX = 30,
+    GSLNLS_ETOLG = 31,
+    GSLNLS_EPARSE = 1001,   /* formula could not be parsed / differentiated */
+    GSLNLS_ECOMPILE = 1002, /* NVRTC rejected the generated kernel */
+    GSLNLS_ECUDA = 1003,    /* CUDA runtime error (message via gslnls_last_error) */
+    GSLNLS_ENODEVICE = 1004,/* no usable CUDA device: there is no CPU fallback */
+    GSLNLS_ECOMM = 1005     /* multi-GPU exchange failed */
+};
+
+/* jac_mode of gslnls_model_compile */
+enum {
+    GSLNLS_JAC_SYMBOLIC = 0, /* deriv()-style symbolic Jacobian (R/nls_large.R:296-306) */
+    GSLNLS_JAC_FORWARD = 1,  /* forward differences, step rule of src/fdjac.c:24-64 */
+    GSLNLS_JAC_CENTER = 2    /* centred differences, src/fdjac.c:81-128 */
+};
+/* fvv_mode */
+enum {
+    GSLNLS_FVV_NONE = 0,
+    GSLNLS_FVV_SYMBOLIC = 1, /* deriv(hessian=TRUE) contracted with v (R/nls_large.R:333-343) */
+    GSLNLS_FVV_FD = 2        /* Transtrum-Sethna Eq. 19, src/fdfvv.c:35-77 */
+};
+
+typedef struct gslnls_model gslnls_model;     /* compiled model: generated CUDA + cubin, opaque */
+typedef struct gslnls_problem gslnls_problem; /* device-resident data + solver workspace, opaque */
+typedef struct gslnls_comm gslnls_comm;       /* multi-GPU exchange context, opaque */
+
+/* The list returned by C_nls_large (src/nls_large.c:279-288), as a C struct.
+ * All pointers are owned by the struct; release with gslnls_result_free. */
+typedef struct gslnls_result {
+    int64_t n;           /* global number of observations */
+    int p;
+    double *par;         /* [p]   final parameters, or start on failure (:293-302) */
+    double *covar;       /* [p*p] column-major (J^T J)^-1, NaN-filled on failure (:311-326) */
+    double ssr;          /* chisq1 (:391) */
+    double ssrtol;       /* chisq0 - chisq1 (:392) */
+    double chisq_init;   /* ssr at start (:230-235, printed by trace) */
+    int niter;           /* gsl_multilarge_nlinear_niter (:248) */
+    int conv;            /* status code (:390); R: isConv = !conv */
+    int info;            /* convergence reason 1 = step, 2 = gradient (src/nls_fit.c:135-144) */
+    const char *status;  /* gsl_strerror(conv) (:389) */
+    const char *algorithm; /* trs name (:393) */
+    int64_t neval[4];    /* f, dfu, df2, fvv (:395-401): logical GSL counts */
+    int64_t npass;       /* physical fused passes over the data that were launched */
+    int ntrace;          /* maxiter + 1 if trace else 0 */
+    double *partrace;    /* [(maxiter+1) * p] column-major, rows 0..niter valid (:177-182,:719-727) */
+    double *ssrtrace;    /* [maxiter+1] */
+    double *condtrace;   /* [maxiter+1] cond(J) per iteration as printed by callback_large (:733-738) */
+    double *resid;       /* [n_local] weighted f - y (:339-343) if requested, else NULL */
+    double *grad;        /* [n_local * p] column-major weighted Jacobian (:354-363) if requested */
+    int64_t n_local;
+    double *jtj;         /* [p*p] column-major J^T J at par (so R = chol(JTJ)^T replaces the O(n p^2) QR) */
+    double *grad_vec;    /* [p] J^T f at par */
+} gslnls_result;
+
+/* ---- model compilation ------------------------------------------------------------------- */
+
+/* Translate the right-hand side of an R model formula into device code.
+ *   rhs_expr     e.g. "A * exp(-lam * x) + b"  (R arithmetic: + - * / ^ ** unary minus, parentheses,
+ *                exp log log2 log10 log1p expm1 sqrt sin cos tan asin acos atan sinh cosh tanh abs
+ *                pnorm dnorm sinpi cospi, the constant pi)
+ *   param_names  p names, in the order of `start`
+ *   var_names    nvar predictor names, in the order the data columns are passed later
+ * Replaces the closures built at R/nls_large.R:273 (.fn), :296-309 (.jac), :333-347 (.fvv). */
+GSLNLS_API int gslnls_model_compile(const char *rhs_expr, const char *const *param_names, int p,
+                                    const char *const *var_names, int nvar, int jac_mode, int fvv_mode,
+                                    gslnls_model **out, char *errbuf, size_t errlen);
+GSLNLS_API void gslnls_model_free(gslnls_model *m);
+GSLNLS_API int gslnls_model_p(const gslnls_model *m);
+GSLNLS_API int gslnls_model_nvar(const gslnls_model *m);
+/* generated model source (the device functions, also valid host C++ for CPU-side codegen tests) */
+GSLNLS_API const char *gslnls_model_source(const gslnls_model *m);
+
+/* ---- one-shot fit: the drop-in for .Call(C_nls_large, ...) ---------------------------------- */
+
+/* vars: nvar host pointers of n doubles each; y: n; weights: n raw weights or NULL;
+ * control_int[7] = {maxiter, trace, algorithm 0..5, scale 0..2, fdtype 0..1, jacclass, jacnz}
+ * control_dbl[8] = {factor_up, factor_down, avmax, h_df, h_fvv, xtol, ftol, gtol}
+ * Host->device copies of the data happen inside this call. Returns the GSL status (== out->conv)
+ * or a GSLNLS_E* library error (out is then zeroed). */
+GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars, const double *y,
+                                const double *weights, int64_t n, const double *start,
+                                const int *control_int, const double *control_dbl, int device,
+                                int want_resid_grad, gslnls_result *out);
+GSLNLS_API void gslnls_result_free(gslnls_result *r);
+
+/* ---- resident-data API (data stays in HBM across fits; used by benchmarks and multi-GPU) ---- */
+
+GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int has_weights, int device,
+                                     gslnls_problem **out);
+GSLNLS_API void gslnls_problem_free(gslnls_problem *pb);
+/* copy host data into library-owned device buffers (pinned staging, async copy engine) */
+GSLNLS_API int gslnls_problem_upload(gslnls_problem *pb, const double *const *vars, const double *y,
+                                     const double *weights);
+/* use caller-owned device buffers (plain device pointers); they must outlive the problem */
+GSLNLS_API int gslnls_problem_bind_device(gslnls_problem *pb, const double *const *dev_vars,
+                                          const double *dev_y, const double *dev_weights);
+/* attach an exchange context: this problem holds one shard of a global problem */
+GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm);
+GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const int *control_int,
+                                  const double *control_dbl, int want_resid_grad, gslnls_result *out);
+/* test / benchmark hooks ------------------------------------------------------------------------ */
+/* one fused pass at theta: packet = [J^T J lower packed row-major | J^T f | f^T f], p(p+1)/2+p+1 doubles
+ * (summed over all shards when a comm is attached) */
+GSLNLS_API int gslnls_problem_eval_packet(gslnls_problem *pb, const double *theta, double *packet);
+/* one geodesic pass at theta with velocity v: out = J^T fvv (p doubles) */
+GSLNLS_API int gslnls_problem_eval_jtfvv(gslnls_problem *pb, const double *theta, const double *v, double *out);
+/* enqueue `npass` fused passes at theta without host synchronisation in between and return the
+ * device time per pass in milliseconds measured with CUDA events on the launch stream */
+GSLNLS_API int gslnls_problem_time_passes(gslnls_problem *pb, const double *theta, int npass, float *ms_per_pass);
+/* weighted residuals f - y and Jacobian at theta (K4); either output may be NULL */
+GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta, double *resid, double *grad_colmajor);
+/* run exactly `ntrial` trust-region trial iterations (pass + step) from the current solver state
+ * created by gslnls_problem_fit_begin, timing them on the device; for bench.py */
+GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start, const int *control_int,
+                                        const double *control_dbl);
+GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *done, int64_t *passes_run,
+                                      float *device_ms);
+GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, gslnls_result *out);
+GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb);
+
+/* ---- batched multi-start inner kernels (src/nls_mstart.c:75-91: det(J^T J) screen + mstart_p LM
+ *      iterations per start point), candidates ride blockIdx.y ----------------------------------- */
+GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts /* S*p row-major */, int S,
+                                        const int *control_int, const double *control_dbl,
+                                        double *par_out /* S*p */, double *ssr_out /* S */,
+                                        double *logdet_out /* S: log det(J^T J) at start, or NULL */,
+                                        int *conv_out /* S */, int *niter_out /* S */);
+
+/* ---- multi-GPU exchange (one process per GPU) ------------------------------------------------ */
+#define GSLNLS_COMM_ID_BYTES 128
+/* rank 0 creates an id and ships it to the other ranks by any means (MPI, files, a process-group broadcast) */
+GSLNLS_API int gslnls_comm_get_unique_id(void *id_bytes /* GSLNLS_COMM_ID_BYTES */);
+GSLNLS_API int gslnls_comm_create(const void *id_bytes, int rank, int nranks, int device, gslnls_comm **out);
+GSLNLS_API void gslnls_comm_free(gslnls_comm *c);
+GSLNLS_API int gslnls_comm_rank(const gslnls_comm *c);
+GSLNLS_API int gslnls_comm_size(const gslnls_comm *c);
+
+/* ---- misc -------------------------------------------------------------------------------------- */
+GSLNLS_API const char *gslnls_strerror(int code);   /* gsl_strerror() strings + library errors */
+GSLNLS_API const char *gslnls_trs_name(int algorithm);
+GSLNLS_API const char *gslnls_last_error(void);     /* thread-local detail of the last GSLNLS_E* */
+GSLNLS_API int gslnls_device_count(void);
+GSLNLS_API const char *gslnls_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSLNLS_B200_H */

@@ -1,0 +1,115 @@
+"""CPU-side checks of the product library: it loads, exports every symbol the header declares,
+compiles models with NVRTC for sm_100a (needs no GPU) and refuses to compute without a device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from gslnls_b200 import Model, _lib, gsl_nls_control, gsl_nls_large, pack_control
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gslnls_b200.h")).read()
+    declared = set(re.findall(r"GSLNLS_API\s+[^;(]*?\b(gslnls_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = set(re.findall(r"\b(gslnls_\w+)\b", out))
+    assert declared <= exported, declared - exported
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    assert b"sm_100a" in L.gslnls_version()
+    assert L.gslnls_strerror(27) == b"iteration is not making progress towards solution"
+    assert L.gslnls_strerror(11) == b"exceeded max number of iterations"
+    assert L.gslnls_trs_name(1) == b"levenberg-marquardt+accel"  # README.md:649
+
+
+def test_no_cuda_symbols_leak_and_no_torch_types():
+    hdr = open(os.path.join(ROOT, "include", "gslnls_b200.h")).read()
+    assert "torch" not in hdr and "at::" not in hdr
+
+
+def test_control_defaults_and_packing():
+    c = gsl_nls_control()
+    assert len(c) == 23  # R/nls.R:1156 "exactly twenty-three components"
+    assert c["maxiter"] == 100 and c["scale"] == "more" and c["solver"] == "qr" and c["fdtype"] == "forward"
+    assert c["factor_up"] == 2 and c["factor_down"] == 3 and c["avmax"] == 0.75 and c["h_fvv"] == 0.02
+    assert c["xtol"] == c["ftol"] == c["gtol"] == c["h_df"] == np.sqrt(np.finfo(float).eps)
+    assert c["mstart_n"] == 30 and c["mstart_q"] == 3 and c["mstart_p"] == 5
+    ci, cd = pack_control(c, "ddogleg", True)
+    assert ci.tolist() == [100, 1, 3, 0, 0, -2, 0]          # R/nls_large.R:383-391
+    assert cd.tolist() == [2, 3, 0.75, c["h_df"], 0.02, c["xtol"], c["ftol"], c["gtol"]]  # :407
+    with pytest.raises(ValueError):
+        gsl_nls_control(scale="nope")
+    with pytest.raises(ValueError):
+        gsl_nls_control(maxiter=0)
+    with pytest.raises(ValueError):
+        gsl_nls_control(xtol=-1)
+
+
+def test_argument_validation_messages():
+    x = np.linspace(0, 1, 8)
+    y = 2 * np.exp(-x)
+    kw = dict(data={"x": x, "y": y}, start={"A": 1.0, "lam": 1.0})
+    with pytest.raises(ValueError, match="analytic Jacobian function 'jac' is required"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", **kw)
+    with pytest.raises(ValueError, match="analytic second derivative function 'fvv' is required"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", algorithm="lmaccel", jac=True, **kw)
+    with pytest.raises(ValueError, match="should be one of"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", algorithm="newton", jac=True, **kw)
+    with pytest.raises(ValueError, match="negative residual degrees of freedom"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", data={"x": x[:1], "y": y[:1]}, start={"A": 1, "lam": 1}, jac=True)
+    with pytest.raises(ValueError, match="parameters without starting value"):
+        gsl_nls_large("y ~ A * exp(-lam * x) + b", jac=True, **kw)   # unit_tests_gslnls.R:118
+    with pytest.raises(ValueError, match="starting values"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", data={"x": x, "y": y}, jac=True)  # :117
+    with pytest.raises(ValueError, match="non-positive weights"):
+        gsl_nls_large("y ~ A * exp(-lam * x)", jac=True, weights=np.zeros(8), **kw)
+    with pytest.raises(TypeError):
+        gsl_nls_large("y ~ A * exp(-lam * x)", data=[1, 2], start={"A": 1}, jac=True)
+
+
+def test_untranslatable_models_fail_loudly():
+    with pytest.raises(_lib.GslnlsError) as ei:
+        Model("A * besselJ(x, 0)", ["A"], ["x"])
+    assert ei.value.code == 1001
+    with pytest.raises(_lib.GslnlsError):
+        Model("A * exp(-lam * x", ["A", "lam"], ["x"])
+    with pytest.raises(_lib.GslnlsError):
+        Model("A * exp(-lam * z)", ["A", "lam"], ["x"])
+
+
+@pytest.mark.skipif(_lib.lib().gslnls_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback_without_a_device():
+    m = Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"])
+    x = np.linspace(0, 3, 25)
+    with pytest.raises(_lib.GslnlsError) as ei:
+        gsl_nls_large("y ~ A * exp(-lam * x) + b", data={"x": x, "y": x}, start={"A": 1, "lam": 1, "b": 0},
+                      jac=True, model=m)
+    assert ei.value.code == 1004  # GSLNLS_ENODEVICE
+
+
+def test_nvrtc_compiles_every_reference_formula_for_sm100a(nist_problems):
+    """all 33 formula problems of R/nls_test.R translate, differentiate and compile (symbolic J + fvv)"""
+    for name, pr in nist_problems.items():
+        rhs = pr["formula"].split("~", 1)[1]
+        lhs = pr["formula"].split("~", 1)[0]
+        vars_ = [k for k in pr["data"] if k not in lhs.replace("log(", "").replace(")", "").split()]
+        m = Model(rhs, pr["param_names"], vars_, jac=True, fvv=True)
+        assert "nls_model_fvv" in m.source, name
+
+
+@pytest.mark.parametrize("jac,fvv", [("forward", "fd"), ("center", None), (True, "fd")])
+def test_nvrtc_compiles_finite_difference_modes(jac, fvv):
+    m = Model("a * exp(-(x - b)^2 / (2 * c^2))", ["a", "b", "c"], ["x"], jac=jac, fvv=fvv)
+    assert ("nls_model_fj" in m.source) == (jac is True)
+
+
+def test_selfstart_shapes_translate():
+    # inst/unit_tests/unit_tests_gslnls.R:272-275 uses SSasymp with gsl_nls_large
+    m = Model("SSasymp(x, Asym, R0, lrc)", ["Asym", "R0", "lrc"], ["x"], jac=True, fvv=True)
+    assert "exp" in m.source

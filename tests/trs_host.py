@@ -1,0 +1,96 @@
+"""ctypes driver of tests/host_harness (host build of the device trust-region state machine)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+S_NAMES = ["phase", "status", "info", "niter", "iter", "bad", "nu", "neval_f", "neval_dfu", "neval_df2",
+           "neval_fvv", "mu", "delta", "avratio", "chisq0", "chisq1", "f2", "chisq_init", "npass", "rho",
+           "logdet0"]
+S_COUNT = 24
+
+
+class HostParams(C.Structure):
+    _fields_ = [("p", C.c_int), ("maxiter", C.c_int), ("trs", C.c_int), ("scale", C.c_int), ("trace", C.c_int),
+                ("batch_iters", C.c_int), ("cg_maxit", C.c_longlong), ("factor_up", C.c_double),
+                ("factor_down", C.c_double), ("avmax", C.c_double), ("h_df", C.c_double), ("h_fvv", C.c_double),
+                ("xtol", C.c_double), ("ftol", C.c_double), ("gtol", C.c_double), ("cg_tol", C.c_double)]
+
+
+_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        d = os.path.join(_HERE, "host_harness")
+        subprocess.check_call(["make", "-C", d, "-s"])
+        _LIB = C.CDLL(os.path.join(d, "_build", "libtrs_host.so"))
+        _LIB.trs_host_fit.restype = C.c_long
+    return _LIB
+
+
+def packet_from_rows(rows, y, weights=None):
+    """packet provider implementing the pass kernel's contract with numpy"""
+    sw = None if weights is None else np.sqrt(np.asarray(weights, dtype=float))
+
+    def provider(mode, theta, v):
+        p = theta.size
+        if mode == 1:
+            f, J, _ = rows(theta, None, True, True, False)
+            r = np.where(np.isfinite(f), f - y, np.inf)
+            if sw is not None:
+                r = r * sw
+                J = J * sw[:, None]
+            with np.errstate(all="ignore"):
+                JTJ = J.T @ J
+                pk = np.concatenate([JTJ[np.tril_indices(p)], J.T @ r, [r @ r]])
+            return pk
+        if mode == 2:
+            _, J, h = rows(theta, v, False, True, True)
+            if sw is not None:
+                J = J * sw[:, None]
+                h = h * sw
+            with np.errstate(all="ignore"):
+                return np.concatenate([J.T @ h, [h @ h]])
+        raise ValueError(mode)
+    return provider
+
+
+def fit(provider, start, algorithm="lm", maxiter=100, scale="more", trace=True, factor_up=2.0, factor_down=3.0,
+        avmax=0.75, h_df=None, h_fvv=0.02, xtol=None, ftol=None, gtol=None, n=1000, batch_iters=0):
+    from oracle.oracle import SCALE, SQRT_EPS, TRS
+    L = lib()
+    start = np.ascontiguousarray(start, dtype=float)
+    p = start.size
+    hp = HostParams(p, maxiter, TRS[algorithm], SCALE[scale], int(trace), batch_iters, n, factor_up, factor_down,
+                    avmax, h_df or SQRT_EPS, h_fvv, xtol or SQRT_EPS, ftol or SQRT_EPS, gtol or SQRT_EPS, 1e-6)
+    state = np.zeros(S_COUNT + 6 * p + 2 * p * p)
+    partrace = np.zeros((maxiter + 1) * p)
+    ssrtrace = np.zeros(maxiter + 1)
+    condtrace = np.zeros(maxiter + 1)
+    npk = p * (p + 1) // 2 + p + 1
+
+    def cb(ctx, mode, th, v, out):
+        theta = np.ctypeslib.as_array(th, shape=(p,)).copy()
+        vel = np.ctypeslib.as_array(v, shape=(p,)).copy()
+        pk = provider(mode, theta, vel)
+        np.ctypeslib.as_array(out, shape=(npk,))[: pk.size] = pk
+        return 0
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    npass = L.trs_host_fit(C.byref(hp), dp(start), _CB(cb), None, dp(state), dp(partrace), dp(ssrtrace),
+                           dp(condtrace), 100000)
+    out = {k: state[i] for i, k in enumerate(S_NAMES)}
+    v = state[S_COUNT:]
+    out.update(par=v[:p].copy(), dx=v[p:2 * p].copy(), g=v[2 * p:3 * p].copy(), diag=v[3 * p:4 * p].copy(),
+               jtj=v[6 * p:6 * p + p * p].reshape(p, p).copy(),
+               covar=v[6 * p + p * p:6 * p + 2 * p * p].reshape(p, p).copy(), npackets=npass)
+    nit = int(out["niter"])
+    out["partrace"] = partrace.reshape(p, maxiter + 1).T[: nit + 1].copy()
+    out["ssrtrace"] = ssrtrace[: nit + 1].copy()
+    out["condtrace"] = condtrace[: nit + 1].copy()
+    return out
