@@ -50,6 +50,10 @@ SIGNATURES = {
     "gslnls_problem_fit_run": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "gslnls_problem_fit_end": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "gslnls_problem_launch_count": (C.c_int64, [C.c_void_p]),
+    "gslnls_problem_timer_start": (C.c_int, [C.c_void_p]),
+    "gslnls_problem_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "gslnls_problem_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "gslnls_problem_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "gslnls_problem_fit_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p,
                                            c_double_p, c_double_p, c_int_p, c_int_p]),
     "gslnls_comm_get_unique_id": (C.c_int, [C.c_void_p]),

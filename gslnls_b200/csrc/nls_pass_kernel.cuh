@@ -45,7 +45,8 @@
 #define NLS_P GSLNLS_P
 #define NLS_NV (GSLNLS_NVAR > 0 ? GSLNLS_NVAR : 1)
 #define NLS_NPK (NLS_P * (NLS_P + 1) / 2)
-#define NLS_PK (NLS_NPK + NLS_P + 1)
+// packet slots: [J^T J lower | J^T f | f^T f | number of non-finite residuals]
+#define NLS_PK (NLS_NPK + NLS_P + 2)
 #define NLS_NW (NLS_BLOCK / 32)
 
 enum { NLS_MODE_IDLE = 0, NLS_MODE_FJ = 1, NLS_MODE_FVV = 2, NLS_MODE_JVP = 3 };
@@ -135,8 +136,12 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
 #endif
     if (MODE == NLS_MODE_FJ) {
         double r = f - y;
-        if (!nls_finite(f))
+        if (!nls_finite(f)) {
             r = NLS_INF; // src/nls_large.c:464-465
+            // counted: gslcblas dnrm2 turns a vector with two or more Inf entries into NaN, which
+            // changes the reference's accept/reject decision (see trs_core.h, norm_of)
+            acc[NLS_NPK + NLS_P + 1] += 1.0;
+        }
 #if NLS_HAS_W
         r *= sw;
 #pragma unroll

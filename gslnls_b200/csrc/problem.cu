@@ -42,7 +42,11 @@ struct gslnls_problem {
     int p = 0, nvar = 0, has_w = 0, device = 0;
     int64_t n = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    // optional per-pass timing (bench.py roofline): event pairs around K1 launches
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
     // data
     std::vector<double *> owned; // buffers we allocated
     const double *dvars[NLS_MAX_VARS] = {nullptr};
@@ -169,8 +173,15 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
     void *args[] = {&prm};
+    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size();
+    if (timed)
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
     CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args, 0,
                         pb->stream));
+    if (timed) {
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
+        pb->prof_used += 2;
+    }
     ++pb->launches;
     ++pb->passes;
     return GSLNLS_SUCCESS;
@@ -225,6 +236,8 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     CK(cudaStreamCreateWithFlags(&pb->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&pb->ev0));
     CK(cudaEventCreate(&pb->ev1));
+    CK(cudaEventCreate(&pb->ev2));
+    CK(cudaEventCreate(&pb->ev3));
     CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
     if (const char *c = std::getenv("GSLNLS_CHUNK"))
         pb->chunk = std::max(1, std::atoi(c));
@@ -245,6 +258,10 @@ GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
     cudaFreeHost(pb->h_ndone);
     cudaEventDestroy(pb->ev0);
     cudaEventDestroy(pb->ev1);
+    cudaEventDestroy(pb->ev2);
+    cudaEventDestroy(pb->ev3);
+    for (cudaEvent_t e : pb->prof_ev)
+        cudaEventDestroy(e);
     cudaStreamDestroy(pb->stream);
     delete pb;
 }
@@ -637,6 +654,57 @@ GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const
 }
 
 GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb) { return pb ? pb->launches : 0; }
+
+GSLNLS_API int gslnls_problem_timer_start(gslnls_problem *pb)
+{
+    if (!pb)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    CK(cudaStreamSynchronize(pb->stream));
+    CK(cudaEventRecord(pb->ev2, pb->stream));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_timer_stop(gslnls_problem *pb, float *ms)
+{
+    if (!pb || !ms)
+        return GSLNLS_EINVAL;
+    CK(cudaEventRecord(pb->ev3, pb->stream));
+    CK(cudaEventSynchronize(pb->ev3));
+    CK(cudaEventElapsedTime(ms, pb->ev2, pb->ev3));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_set_profile(gslnls_problem *pb, int max_passes)
+{
+    if (!pb)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    pb->profile = max_passes > 0;
+    pb->prof_used = 0;
+    while (pb->prof_ev.size() < (size_t)2 * (size_t)std::max(max_passes, 0)) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        pb->prof_ev.push_back(e);
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_profile(gslnls_problem *pb, float *avg_pass_ms, int64_t *npasses_timed)
+{
+    if (!pb || !avg_pass_ms || !npasses_timed)
+        return GSLNLS_EINVAL;
+    CK(cudaStreamSynchronize(pb->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < pb->prof_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pb->prof_ev[i], pb->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *npasses_timed = (int64_t)(pb->prof_used / 2);
+    *avg_pass_ms = *npasses_timed ? (float)(tot / (double)*npasses_timed) : 0.f;
+    return GSLNLS_SUCCESS;
+}
 
 GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars, const double *y,
                                 const double *weights, int64_t n, const double *start, const int *control_int,

@@ -42,7 +42,7 @@ enum { E_SUCCESS = 0, E_FAILURE = -1, E_CONTINUE = -2, E_EDOM = 1, E_EBADFUNC = 
 enum {
     S_PHASE = 0, S_STATUS, S_INFO, S_NITER, S_ITER, S_BAD, S_NU, S_NEVAL_F, S_NEVAL_DFU, S_NEVAL_DF2,
     S_NEVAL_FVV, S_MU, S_DELTA, S_AVRATIO, S_CHISQ0, S_CHISQ1, S_F2, S_CHISQ_INIT, S_NPASS, S_RHO,
-    S_LOGDET0, S_COUNT = 24
+    S_LOGDET0, S_NBAD, S_COUNT = 24
 };
 
 struct Params {
@@ -72,6 +72,12 @@ struct WarpLanes {
 
 TRS_HD inline bool finite_d(double v) { return (v - v) == 0.0; }
 
+// ||f|| as the reference computes it: gslcblas' dnrm2 (scaled sum of squares) returns +Inf for a
+// vector with exactly one Inf entry but NaN as soon as there are two (Inf/Inf in the update), and
+// every comparison in trust_calc_rho (src/trust.c:84-115) is then false -- the step is *accepted*.
+// Reproduced on purpose: results must match the reference on the same inputs.
+TRS_HD inline double norm_of(double sumsq, double nbad) { return nbad >= 2.0 ? NAN : sqrt(sumsq); }
+
 template <int PMAX, class Lanes>
 struct Solver {
     const Params &P;
@@ -87,6 +93,7 @@ struct Solver {
     double nu;
     double nf, ndfu, ndf2, nfvv, npass;
     double mu, delta, avratio, chisq0, chisq1, f2, chisq_init, rho, logdet0;
+    double nbad; // number of non-finite residuals in the current f
     // per-iteration subproblem products (recomputed from g, JTJ, diag on every call)
     double norm_Dgn, norm_Dsd, norm_Dinvg, norm_JDinv2g;
     double trB, detB, normg, term0, term1, tau[2], subg[2], B00, B10, B11;
@@ -267,6 +274,7 @@ struct Solver {
         for (int j = 0; j < p; ++j)
             g[j] = pk[npk + j];
         f2 = pk[npk + p];
+        nbad = pk[npk + p + 1];
         factor_valid = false;
         jtj_dirty = true;
     }
@@ -274,7 +282,7 @@ struct Solver {
     // ---------------------------------------------------------------- predicted reductions
     TRS_HD double pred_quadratic(const double *step)
     {
-        const double normf = sqrt(f2);
+        const double normf = norm_of(f2, nbad);
         double pr = -2.0 * dot(g, step) / (normf * normf);
         symv(step, w3);
         pr -= dot(w3, step) / (normf * normf);
@@ -282,7 +290,7 @@ struct Solver {
     }
     TRS_HD double pred_lm()
     {
-        const double normf = sqrt(f2);
+        const double normf = norm_of(f2, nbad);
         const double norm_Dp = scaled_enorm(diag, vel);
         symv(vel, w3);
         const double norm_Jp = sqrt(dot(w3, vel));
@@ -800,7 +808,7 @@ struct Solver {
             if (tmp > gnorm)
                 gnorm = tmp;
         }
-        const double fnorm = sqrt(f2);
+        const double fnorm = norm_of(f2, nbad);
         const double phi = 0.5 * fnorm * fnorm;
         if (gnorm <= P.gtol * (phi > 1.0 ? phi : 1.0)) {
             info = 2;
@@ -845,7 +853,7 @@ struct Solver {
         nf = S[S_NEVAL_F]; ndfu = S[S_NEVAL_DFU]; ndf2 = S[S_NEVAL_DF2]; nfvv = S[S_NEVAL_FVV];
         mu = S[S_MU]; delta = S[S_DELTA]; avratio = S[S_AVRATIO]; chisq0 = S[S_CHISQ0];
         chisq1 = S[S_CHISQ1]; f2 = S[S_F2]; chisq_init = S[S_CHISQ_INIT]; npass = S[S_NPASS];
-        rho = S[S_RHO]; logdet0 = S[S_LOGDET0];
+        rho = S[S_RHO]; logdet0 = S[S_LOGDET0]; nbad = S[S_NBAD];
         const double *v = S + S_COUNT;
         for (int i = 0; i < p; ++i) {
             x[i] = v[i]; dx[i] = v[p + i]; g[i] = v[2 * p + i]; diag[i] = v[3 * p + i];
@@ -870,7 +878,7 @@ struct Solver {
             S[S_ITER] = iter; S[S_BAD] = bad; S[S_NU] = nu; S[S_NEVAL_F] = nf; S[S_NEVAL_DFU] = ndfu;
             S[S_NEVAL_DF2] = ndf2; S[S_NEVAL_FVV] = nfvv; S[S_MU] = mu; S[S_DELTA] = delta;
             S[S_AVRATIO] = avratio; S[S_CHISQ0] = chisq0; S[S_CHISQ1] = chisq1; S[S_F2] = f2;
-            S[S_CHISQ_INIT] = chisq_init; S[S_NPASS] = npass; S[S_RHO] = rho; S[S_LOGDET0] = logdet0;
+            S[S_CHISQ_INIT] = chisq_init; S[S_NPASS] = npass; S[S_RHO] = rho; S[S_LOGDET0] = logdet0; S[S_NBAD] = nbad;
             double *v = S + S_COUNT;
             for (int i = 0; i < p; ++i) {
                 v[i] = x[i]; v[p + i] = dx[i]; v[2 * p + i] = g[i]; v[3 * p + i] = diag[i];
@@ -1031,9 +1039,9 @@ struct Solver {
             }
         } else { // PH_TRIAL: packet evaluated at xt
             nf += 1.0;
-            const double normf = sqrt(f2);
+            const double normf = norm_of(f2, nbad);
             const double f2t = pk[p * (p + 1) / 2 + p];
-            const double normf_trial = sqrt(f2t);
+            const double normf_trial = norm_of(f2t, pk[p * (p + 1) / 2 + p + 1]);
             bool found = true;
             if (P.trs == TRS_LMACCEL && avratio > P.avmax)
                 found = false;

@@ -187,6 +187,22 @@ class Problem:
                                                        nit.ctypes.data_as(_lib.c_int_p)))
         return {"par": par, "ssr": ssr, "logdet": ld, "conv": conv, "niter": nit}
 
+    def timer_start(self):
+        _lib.check(_lib.lib().gslnls_problem_timer_start(self.handle))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _lib.check(_lib.lib().gslnls_problem_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
+    def set_profile(self, max_passes):
+        _lib.check(_lib.lib().gslnls_problem_set_profile(self.handle, int(max_passes)))
+
+    def profile(self):
+        ms, cnt = C.c_float(), C.c_int64()
+        _lib.check(_lib.lib().gslnls_problem_profile(self.handle, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
     @property
     def launch_count(self):
         return _lib.lib().gslnls_problem_launch_count(self.handle)

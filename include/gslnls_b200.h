@@ -166,6 +166,13 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
                                       float *device_ms);
 GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, gslnls_result *out);
 GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb);
+/* device timers on the solver's own stream (CUDA events): a region timer, and optional event
+ * pairs around each fused-pass launch so a benchmark can report the pass kernel's mean duration
+ * inside its timed region (roofline) */
+GSLNLS_API int gslnls_problem_timer_start(gslnls_problem *pb);
+GSLNLS_API int gslnls_problem_timer_stop(gslnls_problem *pb, float *ms);
+GSLNLS_API int gslnls_problem_set_profile(gslnls_problem *pb, int max_passes);
+GSLNLS_API int gslnls_problem_profile(gslnls_problem *pb, float *avg_pass_ms, int64_t *npasses_timed);
 
 /* ---- batched multi-start inner kernels (src/nls_mstart.c:75-91: det(J^T J) screen + mstart_p LM
  *      iterations per start point), candidates ride blockIdx.y ----------------------------------- */

@@ -90,3 +90,19 @@ def test_maxiter_and_trace_layout(readme_examples):
     assert np.allclose(r["partrace"], o["partrace"], rtol=1e-9)
     assert r["partrace"].shape == (6, 3) and np.allclose(r["partrace"][0], e["start"])
     assert r["condtrace"][1] > 1.0
+
+
+def test_boxbod_reproduces_reference_nan_norm_quirk(nist_problems):
+    """BoxBOD from start 1 with dogleg/ddogleg/cgst: the trial residual vector gets >= 2 +Inf entries,
+    gslcblas dnrm2 returns NaN, every comparison in trust_calc_rho is false, the step is accepted and the
+    following Jacobian evaluation fails with GSL_EBADFUNC.  The device state machine must do the same."""
+    pr = nist_problems["BoxBOD"]
+    data = {k: np.array(v) for k, v in pr["data"].items()}
+    rows = O.sympy_rows(O.split_formula(pr["formula"])[1], pr["param_names"], {"x": data["x"]})
+    prov = T.packet_from_rows(rows, data["y"])
+    for alg in ALGS:
+        r = T.fit(prov, pr["start"], algorithm=alg)
+        o = O.nls_large(rows, data["y"], pr["start"], algorithm=alg)
+        assert int(r["status"]) == o["conv"], alg
+        assert int(r["niter"]) == o["niter"], alg
+    assert O.nls_large(rows, data["y"], pr["start"], algorithm="dogleg")["conv"] == 9

@@ -10,7 +10,7 @@ _LIB = None
 
 S_NAMES = ["phase", "status", "info", "niter", "iter", "bad", "nu", "neval_f", "neval_dfu", "neval_df2",
            "neval_fvv", "mu", "delta", "avratio", "chisq0", "chisq1", "f2", "chisq_init", "npass", "rho",
-           "logdet0"]
+           "logdet0", "nbad"]
 S_COUNT = 24
 
 
@@ -48,7 +48,7 @@ def packet_from_rows(rows, y, weights=None):
                 J = J * sw[:, None]
             with np.errstate(all="ignore"):
                 JTJ = J.T @ J
-                pk = np.concatenate([JTJ[np.tril_indices(p)], J.T @ r, [r @ r]])
+                pk = np.concatenate([JTJ[np.tril_indices(p)], J.T @ r, [r @ r], [np.sum(~np.isfinite(r))]])
             return pk
         if mode == 2:
             _, J, h = rows(theta, v, False, True, True)
@@ -73,12 +73,13 @@ def fit(provider, start, algorithm="lm", maxiter=100, scale="more", trace=True, 
     partrace = np.zeros((maxiter + 1) * p)
     ssrtrace = np.zeros(maxiter + 1)
     condtrace = np.zeros(maxiter + 1)
-    npk = p * (p + 1) // 2 + p + 1
+    npk = p * (p + 1) // 2 + p + 2
 
     def cb(ctx, mode, th, v, out):
         theta = np.ctypeslib.as_array(th, shape=(p,)).copy()
         vel = np.ctypeslib.as_array(v, shape=(p,)).copy()
         pk = provider(mode, theta, vel)
+        np.ctypeslib.as_array(out, shape=(npk,))[:] = 0.0
         np.ctypeslib.as_array(out, shape=(npk,))[: pk.size] = pk
         return 0
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
