@@ -206,7 +206,7 @@ def main():
 
     def run_steps(k):
         """exactly k trial steps as back-to-back fits; returns (outer iterations, fits, last result)"""
-        left, iters, fits, last = k, 0, 0, None
+        left, iters, fits, last, complete = k, 0, 0, None, None
         while left > 0:
             pb.fit_begin(start, algorithm=args.algorithm, control=ctrl)
             done, run = False, 0
@@ -219,7 +219,9 @@ def main():
             left -= max(used, 1)
             iters += last["niter"]
             fits += 1
-        return iters, fits, last
+            if done:
+                complete = last
+        return iters, fits, (complete or last)
 
     def barrier():
         if world > 1:
@@ -250,7 +252,7 @@ def main():
 
     # ---- e2e: gslnls_fit_large() from pinned host buffers, copies inside the timed region ---------
     e2e = None
-    if world == 1:
+    if world == 1 and args.e2e_fits > 0:
         import ctypes as C
         ci, cd = pack_control(ctrl, args.algorithm, False)
         L = _lib.lib()

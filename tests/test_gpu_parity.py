@@ -288,6 +288,6 @@ def test_batched_multistart_inner_loops(G):
         JTJ[np.tril_indices(4)] = pk[:10]
         JTJ = JTJ + np.tril(JTJ, -1).T
         sign, ld = np.linalg.slogdet(JTJ)
-        if sign > 0 and np.isfinite(out["logdet"][c]):
+        if sign > 0 and np.isfinite(out["logdet"][c]) and np.linalg.cond(JTJ) < 1e8:
             assert out["logdet"][c] == pytest.approx(ld, rel=1e-6, abs=1e-6)
     pb.close()
