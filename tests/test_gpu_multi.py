@@ -1,0 +1,49 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): observation shards + packet all-reduce must give
+every rank the single-GPU / oracle answer."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    from gslnls_b200 import _lib
+    return _lib.lib().gslnls_device_count()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_fit_matches_oracle(tmp_path, world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import bench
+    from oracle import oracle as O
+    n = 2_000_003
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, GSLNLS_TEST_OUT=str(tmp_path), GSLNLS_TEST_N=str(n))
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
+                           str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
+                           os.path.join(ROOT, "tests", "dist_gpu_worker.py")], env=env, timeout=600)
+    res = [json.load(open(tmp_path / ("rank%d.json" % r))) for r in range(world)]
+    x, y = bench.synth_rows(0, n, n)
+    full = O.eval_packet("exp3", y, [4.0, 1.3, 0.9], x=x, longdouble=True)
+    for r in res:
+        assert r["packet"] == res[0]["packet"]            # all ranks: bitwise identical reduced packet
+        assert r["fits"] == res[0]["fits"]                # ... and therefore identical trajectories
+    got = np.array(res[0]["packet"])
+    assert np.max(np.abs(got - full) / np.abs(full)) < 1e-12
+    for alg, f in res[0]["fits"].items():
+        ref = O.nls_large("exp3", y, list(bench.START), x=x, algorithm=alg)
+        assert f["conv"] == ref["conv"] == 0 and f["niter"] == ref["niter"], alg
+        assert np.allclose(f["par"], ref["par"], rtol=1e-8), alg
+        assert f["ssr"] == pytest.approx(ref["ssr"], rel=1e-8)
+        assert f["n"] == n
