@@ -19,6 +19,7 @@ typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef int (*fn_GetUniqueId)(ncclUniqueId_t *);
 typedef int (*fn_CommInitRank)(void **, int, ncclUniqueId_t, int);
 typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_AllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*fn_CommDestroy)(void *);
 typedef const char *(*fn_GetErrorString)(int);
 
@@ -27,6 +28,7 @@ struct Nccl {
     fn_GetUniqueId GetUniqueId = nullptr;
     fn_CommInitRank CommInitRank = nullptr;
     fn_AllReduce AllReduce = nullptr;
+    fn_AllGather AllGather = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
     bool ok = false;
@@ -48,9 +50,10 @@ Nccl &nccl()
     N.GetUniqueId = (fn_GetUniqueId)dlsym(N.h, "ncclGetUniqueId");
     N.CommInitRank = (fn_CommInitRank)dlsym(N.h, "ncclCommInitRank");
     N.AllReduce = (fn_AllReduce)dlsym(N.h, "ncclAllReduce");
+    N.AllGather = (fn_AllGather)dlsym(N.h, "ncclAllGather");
     N.CommDestroy = (fn_CommDestroy)dlsym(N.h, "ncclCommDestroy");
     N.GetErrorString = (fn_GetErrorString)dlsym(N.h, "ncclGetErrorString");
-    N.ok = N.GetUniqueId && N.CommInitRank && N.AllReduce && N.CommDestroy;
+    N.ok = N.GetUniqueId && N.CommInitRank && N.AllReduce && N.AllGather && N.CommDestroy;
     return N;
 }
 } // namespace
@@ -64,6 +67,22 @@ int comm_allreduce_sum(gslnls_comm *c, double *dev_buf, size_t count, cudaStream
     const int rc = N.AllReduce(dev_buf, dev_buf, count, ncclFloat64, ncclSum, c->nccl, stream);
     if (rc != 0) {
         set_error(std::string("ncclAllReduce: ") + (N.GetErrorString ? N.GetErrorString(rc) : "error"));
+        return GSLNLS_ECOMM;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+// every rank receives all ranks' `count` doubles, rank-major; the caller sums them in rank order so
+// that all ranks hold bitwise the same packet whatever NCCL's internal reduction order would be
+int comm_allgather(gslnls_comm *c, const double *dev_send, double *dev_recv, size_t count, cudaStream_t stream)
+{
+    if (!c || c->nranks <= 1)
+        return GSLNLS_SUCCESS;
+    Nccl &N = nccl();
+    const int ncclFloat64 = 8;
+    const int rc = N.AllGather(dev_send, dev_recv, count, ncclFloat64, c->nccl, stream);
+    if (rc != 0) {
+        set_error(std::string("ncclAllGather: ") + (N.GetErrorString ? N.GetErrorString(rc) : "error"));
         return GSLNLS_ECOMM;
     }
     return GSLNLS_SUCCESS;

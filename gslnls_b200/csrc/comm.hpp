@@ -10,4 +10,5 @@ struct gslnls_comm {
 namespace gslnls {
 // sum `count` doubles in place across ranks on `stream`; every rank receives bitwise the same result
 int comm_allreduce_sum(gslnls_comm *c, double *dev_buf, size_t count, cudaStream_t stream);
+int comm_allgather(gslnls_comm *c, const double *dev_send, double *dev_recv, size_t count, cudaStream_t stream);
 }

@@ -65,6 +65,9 @@ struct gslnls_problem {
     int *d_ndone = nullptr;
     int *h_ndone = nullptr; // pinned
     gslnls_comm *comm = nullptr;
+    double *d_gather = nullptr;
+    size_t gather_cap = 0;
+    int64_t n_total = 0; // observations over all ranks
     // active fit
     trs::Params P{};
     bool active = false;
@@ -191,7 +194,18 @@ static int exchange_packet(gslnls_problem *pb, size_t count)
 {
     if (!pb->comm || pb->comm->nranks <= 1)
         return GSLNLS_SUCCESS;
-    return comm_allreduce_sum(pb->comm, pb->d_packet, count, pb->stream);
+    const int R = pb->comm->nranks;
+    if (pb->gather_cap < count * R) {
+        cudaFree(pb->d_gather);
+        CK(cudaMalloc(&pb->d_gather, sizeof(double) * count * R));
+        pb->gather_cap = count * R;
+    }
+    int rc = comm_allgather(pb->comm, pb->d_packet, pb->d_gather, count, pb->stream);
+    if (rc)
+        return rc;
+    CK(launch_sum_rank_packets(pb->d_gather, pb->d_packet, (int)count, R, pb->stream));
+    ++pb->launches;
+    return GSLNLS_SUCCESS;
 }
 
 // ------------------------------------------------------------------------------------ C ABI
@@ -255,6 +269,7 @@ GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
         cudaFree(b);
     free_workspace(pb);
     cudaFree(pb->d_partrace); cudaFree(pb->d_ssrtrace); cudaFree(pb->d_condtrace); cudaFree(pb->d_theta);
+    cudaFree(pb->d_gather);
     cudaFreeHost(pb->h_ndone);
     cudaEventDestroy(pb->ev0);
     cudaEventDestroy(pb->ev1);
@@ -319,6 +334,28 @@ GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm)
     if (!pb)
         return GSLNLS_EINVAL;
     pb->comm = comm;
+    pb->n_total = pb->n;
+    if (comm && comm->nranks > 1) {
+        // global number of observations: gather the shard sizes once
+        CK(cudaSetDevice(pb->device));
+        const int R = comm->nranks;
+        double *d = nullptr;
+        CK(cudaMalloc(&d, sizeof(double) * (R + 1)));
+        const double mine = (double)pb->n;
+        CK(cudaMemcpyAsync(d + R, &mine, sizeof(double), cudaMemcpyHostToDevice, pb->stream));
+        int rc = comm_allgather(comm, d + R, d, 1, pb->stream);
+        if (rc) {
+            cudaFree(d);
+            return rc;
+        }
+        std::vector<double> h(R);
+        CK(cudaMemcpyAsync(h.data(), d, sizeof(double) * R, cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        cudaFree(d);
+        pb->n_total = 0;
+        for (double v : h)
+            pb->n_total += (int64_t)v;
+    }
     return GSLNLS_SUCCESS;
 }
 
@@ -351,7 +388,7 @@ GSLNLS_API int gslnls_problem_eval_packet(gslnls_problem *pb, const double *thet
     rc = launch_pass(pb, 1, trs::MODE_FJ);
     if (rc)
         return rc;
-    rc = exchange_packet(pb, trs::packet_doubles(p));
+    rc = exchange_packet(pb, (size_t)pb->pk_stride);
     if (rc)
         return rc;
     CK(cudaMemcpyAsync(packet, pb->d_packet, sizeof(double) * trs::packet_doubles(p), cudaMemcpyDeviceToHost,
@@ -458,8 +495,8 @@ static int fill_params(gslnls_problem *pb, const int *ci, const double *cd, int 
     P.trs = (ci[2] >= 1 && ci[2] <= 5) ? ci[2] : 0;       // src/nls_large.c:97-116
     P.scale = (ci[3] == 1 || ci[3] == 2) ? ci[3] : 0;     // :119-129
     P.batch_iters = batch_iters;
-    const int64_t nranks = pb->comm ? pb->comm->nranks : 1;
-    P.cg_maxit = std::max<int64_t>(pb->n * nranks, 1);   // GSL default max_iter = 0 -> n
+    const int64_t ntot = (pb->comm && pb->comm->nranks > 1) ? pb->n_total : pb->n;
+    P.cg_maxit = std::max<int64_t>(ntot, 1);             // GSL default max_iter = 0 -> n
     P.factor_up = cd[0]; P.factor_down = cd[1]; P.avmax = cd[2]; P.h_df = cd[3]; P.h_fvv = cd[4]; // :135-139
     P.xtol = cd[5]; P.ftol = cd[6]; P.gtol = cd[7];
     P.cg_tol = 1.0e-6;                                     // GSL default tol
@@ -529,7 +566,7 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             int rc = launch_pass(pb, 1, 0);
             if (rc)
                 return rc;
-            rc = exchange_packet(pb, trs::packet_doubles(p));
+            rc = exchange_packet(pb, (size_t)pb->pk_stride);
             if (rc)
                 return rc;
             CK(trs_launch_step(pb->P, pb->d_state, pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr,
@@ -578,8 +615,7 @@ GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, g
     if (!finished)
         status = GSLNLS_CONTINUE; // fit_end before completion (benchmark use)
     const bool ok = status == GSLNLS_SUCCESS || status == GSLNLS_EMAXITER || !finished;
-    const int64_t nranks = pb->comm ? pb->comm->nranks : 1;
-    out->n = pb->n * nranks;
+    out->n = (pb->comm && pb->comm->nranks > 1) ? pb->n_total : pb->n;
     out->n_local = pb->n;
     out->p = p;
     const double *v = S.data() + trs::S_COUNT;

@@ -66,6 +66,25 @@ __global__ void trs_set_request(double *req, int mode, const double *theta, cons
     }
 }
 
+// packet[e] = sum over ranks, in rank order, of gathered[r][e]
+__global__ void sum_rank_packets(const double *gathered, double *packet, int count, int nranks)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count)
+        return;
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r)
+        s += gathered[(size_t)r * count + e];
+    packet[e] = s;
+}
+
+cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int count, int nranks,
+                                    cudaStream_t stream)
+{
+    sum_rank_packets<<<(count + 127) / 128, 128, 0, stream>>>(gathered, packet, count, nranks);
+    return cudaGetLastError();
+}
+
 int trs_max_p() { return 100; }
 
 static size_t warp_smem_bytes(int p) { return sizeof(double) * 2 * (size_t)p * p; }

@@ -16,4 +16,6 @@ cudaError_t trs_launch_reset(double *states, int state_stride, double *reqs, int
                              int p, int ncand, int *ndone, cudaStream_t stream);
 cudaError_t trs_launch_set_request(double *req, int mode, const double *theta, const double *v, int p,
                                    cudaStream_t stream);
+cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int count, int nranks,
+                                    cudaStream_t stream);
 } // namespace gslnls
