@@ -54,11 +54,13 @@ SIGNATURES = {
     "gslnls_problem_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gslnls_problem_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gslnls_problem_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    "gslnls_problem_channel_stats": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.POINTER(C.c_int64)]),
     "gslnls_problem_fit_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p,
                                            c_double_p, c_double_p, c_int_p, c_int_p]),
     "gslnls_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "gslnls_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gslnls_comm_free": (None, [C.c_void_p]),
+    "gslnls_comm_has_peer_memory": (C.c_int, [C.c_void_p]),
     "gslnls_comm_rank": (C.c_int, [C.c_void_p]),
     "gslnls_comm_size": (C.c_int, [C.c_void_p]),
     "gslnls_strerror": (C.c_char_p, [C.c_int]),

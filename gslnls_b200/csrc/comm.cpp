@@ -9,7 +9,11 @@
 #include <cstring>
 #include <string>
 
+#include <cstdlib>
+#include <vector>
+
 #include "../../include/gslnls_b200.h"
+#include "nls_abi.h"
 
 namespace gslnls {
 void set_error(const std::string &s);
@@ -91,6 +95,74 @@ int comm_allgather(gslnls_comm *c, const double *dev_send, double *dev_recv, siz
 
 using namespace gslnls;
 
+// Map every rank's channel block into this process (cudaIpc over NVLink peer access).  The 64-byte
+// handles travel through one NCCL all-gather; all ranks then agree (a second all-gather of an "ok"
+// word) on whether the peer path is usable, so nobody waits on a mailbox nobody writes.
+static void setup_peer_channel(gslnls_comm *c)
+{
+    Nccl &N = nccl();
+    const int R = c->nranks;
+    cudaStream_t st = nullptr;
+    double *d_send = nullptr, *d_recv = nullptr;
+    const size_t words = sizeof(cudaIpcMemHandle_t) / sizeof(double) + 1; // handle + ok word
+    std::vector<double> h_send(words, 0.0), h_recv(words * R, 0.0);
+    bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->channel, NLS_CH_BYTES) == cudaSuccess;
+    ok = ok && cudaMemset(c->channel, 0, NLS_CH_BYTES) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    ok = ok && cudaIpcGetMemHandle(&mine, c->channel) == cudaSuccess;
+    std::memcpy(h_send.data(), &mine, sizeof(mine));
+    h_send[words - 1] = ok ? 1.0 : 0.0;
+    bool xfer = cudaMalloc(&d_send, sizeof(double) * words) == cudaSuccess &&
+                cudaMalloc(&d_recv, sizeof(double) * words * R) == cudaSuccess && st != nullptr;
+    // the collectives below must be entered by every rank, whatever happened locally
+    const int ncclFloat64 = 8;
+    if (xfer) {
+        cudaMemcpyAsync(d_send, h_send.data(), sizeof(double) * words, cudaMemcpyHostToDevice, st);
+        xfer = N.AllGather(d_send, d_recv, words, ncclFloat64, c->nccl, st) == 0;
+        cudaMemcpyAsync(h_recv.data(), d_recv, sizeof(double) * words * R, cudaMemcpyDeviceToHost, st);
+        xfer = cudaStreamSynchronize(st) == cudaSuccess && xfer;
+    }
+    bool all_ok = xfer;
+    for (int r = 0; r < R && all_ok; ++r)
+        all_ok = h_recv[(size_t)r * words + words - 1] == 1.0;
+    if (all_ok) {
+        for (int r = 0; r < R; ++r) {
+            if (r == c->rank) {
+                c->peer_channel[r] = c->channel;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, &h_recv[(size_t)r * words], sizeof(h));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                all_ok = false;
+                break;
+            }
+            c->peer_channel[r] = (char *)ptr;
+        }
+    }
+    // second round: did every rank manage to open every handle?
+    double flag = all_ok ? 1.0 : 0.0;
+    if (xfer) {
+        cudaMemcpyAsync(d_send, &flag, sizeof(double), cudaMemcpyHostToDevice, st);
+        bool g = N.AllGather(d_send, d_recv, 1, ncclFloat64, c->nccl, st) == 0;
+        cudaMemcpyAsync(h_recv.data(), d_recv, sizeof(double) * R, cudaMemcpyDeviceToHost, st);
+        g = cudaStreamSynchronize(st) == cudaSuccess && g;
+        for (int r = 0; r < R && g; ++r)
+            g = h_recv[r] == 1.0;
+        all_ok = all_ok && g;
+    }
+    c->p2p = all_ok;
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    if (st)
+        cudaStreamDestroy(st);
+    cudaGetLastError();
+}
+
 extern "C" {
 
 GSLNLS_API int gslnls_comm_get_unique_id(void *id_bytes)
@@ -142,6 +214,11 @@ GSLNLS_API int gslnls_comm_create(const void *id_bytes, int rank, int nranks, in
             return GSLNLS_ECOMM;
         }
     }
+    if (nranks > 1 && nranks <= NLS_MAX_RANKS) {
+        const char *env = std::getenv("GSLNLS_P2P");
+        if (!env || std::atoi(env) != 0)
+            setup_peer_channel(c); // on failure the NCCL all-gather path remains
+    }
     *out = c;
     return GSLNLS_SUCCESS;
 }
@@ -150,10 +227,18 @@ GSLNLS_API void gslnls_comm_free(gslnls_comm *c)
 {
     if (!c)
         return;
+    cudaSetDevice(c->device);
+    for (int r = 0; r < c->nranks && r < NLS_MAX_RANKS; ++r)
+        if (r != c->rank && c->peer_channel[r])
+            cudaIpcCloseMemHandle(c->peer_channel[r]);
+    if (c->channel)
+        cudaFree(c->channel);
     if (c->nccl)
         nccl().CommDestroy(c->nccl);
     delete c;
 }
+
+GSLNLS_API int gslnls_comm_has_peer_memory(const gslnls_comm *c) { return c && c->p2p ? 1 : 0; }
 
 GSLNLS_API int gslnls_comm_rank(const gslnls_comm *c) { return c ? c->rank : 0; }
 GSLNLS_API int gslnls_comm_size(const gslnls_comm *c) { return c ? c->nranks : 1; }

@@ -3,8 +3,12 @@
 #include <cuda_runtime.h>
 
 struct gslnls_comm {
-    void *nccl = nullptr; // ncclComm_t
+    void *nccl = nullptr; // ncclComm_t (bootstrap, and the exchange when peer memory is unavailable)
     int rank = 0, nranks = 1, device = 0;
+    // peer-memory channel (nls_abi.h NLS_CH_*): this rank's block and every rank's block as mapped here
+    char *channel = nullptr;
+    char *peer_channel[8] = {nullptr};
+    bool p2p = false;
 };
 
 namespace gslnls {

@@ -3,6 +3,22 @@
 #pragma once
 
 #define NLS_MAX_VARS 16
+#define NLS_MAX_RANKS 8
+
+// Device-resident synchronisation channel between the pass kernel (K1), the resident trust-region
+// server (trs_server, trs_kernel.cu) and -- over NVLink peer memory -- the other GPUs' pass kernels.
+// Byte offsets into one cudaMalloc'd block (each word on its own 128-byte line); the block of every
+// rank is mapped into every other rank's address space (cudaIpc), so a pass kernel deposits its
+// packet directly into each peer's mailbox and no collective call sits between pass and step.
+#define NLS_CH_REQ_SEQ 0      /* u64: requests published so far (server -> K1)                  */
+#define NLS_CH_PASS_CTR 128   /* u64: passes completed so far (last CTA of K1 -> next K1)       */
+#define NLS_CH_FIT_SEQ0 256   /* u64: sequence number of the first pass of the current fit      */
+#define NLS_CH_ABORT 384      /* u64: host -> server, leave the fit early                       */
+#define NLS_CH_TIMER 512      /* u64[2]: globaltimer ns, first CTA past the wait / last CTA out  */
+#define NLS_CH_FLAGS 1024     /* u64 x NLS_MAX_RANKS, 128 B apart: latest sequence deposited by rank r */
+#define NLS_CH_DATA 2048      /* double [2 parities][NLS_MAX_RANKS][NLS_CH_MAXPK]               */
+#define NLS_CH_MAXPK 1280
+#define NLS_CH_BYTES (NLS_CH_DATA + 2 * NLS_MAX_RANKS * NLS_CH_MAXPK * 8)
 
 // Parameters of one fused pass (K1).  Passed by value to the kernel.
 struct NlsPassParams {
@@ -17,7 +33,14 @@ struct NlsPassParams {
     double h_df, h_fvv;               // finite-difference steps (control_dbl[3], [4])
     int req_stride, pk_stride;
     int force_mode;                   // >0: ignore req[0] and run this mode (test hooks)
+    int nranks;                       // server mode: ranks depositing into each mailbox (1 = this GPU only)
+    // server mode (channel != nullptr): wait for the request, deposit the packet in every rank's
+    // mailbox; launch-ordered mode (nullptr): the packet goes to `packet` and the host sequences
+    char *channel;                    // this GPU's channel block
+    char *peer_channel[NLS_MAX_RANKS];// every rank's channel block as mapped on this GPU ([rank] == channel)
+    int rank;
     int pad_;
+    int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
 };
 
 struct NlsMaterialiseParams {

@@ -79,6 +79,29 @@ static __device__ __forceinline__ bool nls_finite(double v)
     return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
 }
 
+// ------------------------------------------------------------------------------------ channel words
+static __device__ __forceinline__ unsigned long long nls_ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void nls_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+static __device__ __forceinline__ void nls_st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+static __device__ __forceinline__ unsigned long long nls_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NLS_WATCHDOG_NS 60000000000ull /* a pass never waits a minute for its request */
+
 // ------------------------------------------------------------------------------------ model glue
 struct NlsThread {
     double th[NLS_P];  // parameters
@@ -314,15 +337,45 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
 {
     const int cand = blockIdx.y;
     const double *req = prm.req + (size_t)cand * prm.req_stride;
-    const int mode = prm.force_mode > 0 ? prm.force_mode : (int)req[0];
+    __shared__ unsigned long long s_seq;
+    if (prm.channel) {
+        // server mode: this launch is pass number k = (passes completed so far) + 1; its request is
+        // published by the resident trust-region warp (trs_server) as soon as it has digested
+        // pass k-1, typically while this grid is still being dispatched.
+        if (threadIdx.x == 0) {
+            const unsigned long long k = __ldcg((const unsigned long long *)(prm.channel + NLS_CH_PASS_CTR)) + 1ull;
+            const unsigned long long *rs = (const unsigned long long *)(prm.channel + NLS_CH_REQ_SEQ);
+            unsigned long long t0 = 0ull, spins = 0ull, kk = k;
+            while (nls_ld_acquire_gpu(rs) < k) {
+                if ((++spins & 1023ull) == 0ull) {
+                    const unsigned long long t = nls_globaltimer();
+                    if (t0 == 0ull)
+                        t0 = t;
+                    else if (t - t0 > NLS_WATCHDOG_NS) {
+                        kk = 0ull; // give up: behave like an idle launch
+                        break;
+                    }
+                }
+            }
+            s_seq = kk;
+            if (blockIdx.x == 0 && blockIdx.y == 0)
+                *(unsigned long long *)(prm.channel + NLS_CH_TIMER) = nls_globaltimer();
+        }
+        __syncthreads();
+        if (s_seq == 0ull)
+            return;
+    }
+    const int mode = prm.force_mode > 0 ? prm.force_mode : (int)__ldcg(req);
     if (mode == NLS_MODE_IDLE)
         return; // this candidate has finished; uniform for the whole CTA
+    if (prm.prof_flag && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        *prm.prof_flag = 1;
 
     NlsThread T;
 #pragma unroll
     for (int j = 0; j < NLS_P; ++j) {
-        T.th[j] = req[1 + j];
-        T.vv[j] = req[1 + NLS_P + j];
+        T.th[j] = __ldcg(req + 1 + j);
+        T.vv[j] = __ldcg(req + 1 + NLS_P + j);
         double d = prm.h_df * fabs(T.th[j]);
         if (d == 0.0)
             d = prm.h_df;
@@ -381,6 +434,9 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     __threadfence();
     const double *parts = prm.partials + (size_t)cand * gridDim.x * prm.pk_stride;
     double *out = prm.packet + (size_t)cand * prm.pk_stride;
+    const unsigned long long seq = prm.channel ? s_seq : 0ull;
+    // server mode: slot [seq parity][this rank] of every rank's mailbox (peer memory over NVLink)
+    const size_t slot = ((size_t)(seq & 1ull) * NLS_MAX_RANKS + (size_t)prm.rank) * NLS_CH_MAXPK;
     for (int e = warp; e < NLS_PK; e += NLS_NW) {
         double s = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32)
@@ -390,8 +446,36 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
         s += __shfl_down_sync(0xffffffffu, s, 4);
         s += __shfl_down_sync(0xffffffffu, s, 2);
         s += __shfl_down_sync(0xffffffffu, s, 1);
-        if (lane == 0)
-            out[e] = s;
+        if (lane == 0) {
+            if (prm.channel) {
+                for (int q = 0; q < prm.nranks; ++q)
+                    ((double *)(prm.peer_channel[q] + NLS_CH_DATA))[slot + e] = s;
+            } else {
+                out[e] = s;
+            }
+        }
+    }
+    if (prm.channel) {
+        if (prm.nranks > 1)
+            __threadfence_system();
+        else
+            __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            prm.ticket[cand] = 0u;
+            unsigned long long *tm = (unsigned long long *)(prm.channel + NLS_CH_TIMER);
+            // time from "request seen" (CTA 0) to "packet out", summed over passes
+            tm[1] = __ldcg(tm + 1) + (nls_globaltimer() - __ldcg(tm));
+            tm[2] = __ldcg(tm + 2) + 1ull;
+            *(unsigned long long *)(prm.channel + NLS_CH_PASS_CTR) = seq;
+            if (prm.nranks > 1) {
+                for (int q = 0; q < prm.nranks; ++q)
+                    nls_st_release_sys((unsigned long long *)(prm.peer_channel[q] + NLS_CH_FLAGS + 128 * prm.rank), seq);
+            } else {
+                nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_FLAGS + 128 * prm.rank), seq);
+            }
+        }
+        return;
     }
     if (threadIdx.x == 0)
         prm.ticket[cand] = 0u; // ready for the next launch

@@ -47,6 +47,8 @@ struct gslnls_problem {
     bool profile = false;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
+    int *d_prof_flags = nullptr; // one word per timed launch: did it stream, or was it an idle no-op
+    size_t prof_flags_cap = 0;
     // data
     std::vector<double *> owned; // buffers we allocated
     const double *dvars[NLS_MAX_VARS] = {nullptr};
@@ -76,7 +78,20 @@ struct gslnls_problem {
     double h_df = 0, h_fvv = 0;
     int64_t launches = 0, passes = 0;
     int chunk = 8;
+    // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
+    // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
+    bool allow_server = true, server_on = false;
+    char *own_channel = nullptr; // single-GPU problems own their channel; sharded ones use the comm's
+    cudaStream_t srv_stream = nullptr, ctl_stream = nullptr;
+    cudaEvent_t ev_reset = nullptr, ev_chunk[2] = {nullptr, nullptr};
+    int *h_flags = nullptr, *d_flags = nullptr; // mapped pinned: [0] done (1) / watchdog (2)
+    unsigned long long watchdog_ns = 60000000000ull;
 };
+
+static char *channel_of(const gslnls_problem *pb)
+{
+    return (pb->comm && pb->comm->nranks > 1) ? pb->comm->channel : pb->own_channel;
+}
 
 static void free_workspace(gslnls_problem *pb)
 {
@@ -113,13 +128,15 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
 }
 
 // grid size along x for one candidate
-static int pick_grid(const gslnls_problem *pb, int ncand)
+static int pick_grid(const gslnls_problem *pb, int ncand, bool reserve_slot = false)
 {
     const int64_t nv = pb->vkey.vec == 2 ? pb->n / 2 : pb->n;
     const int64_t need = std::max<int64_t>(1, (nv + pb->vkey.block - 1) / pb->vkey.block);
     int64_t full = (int64_t)pb->num_sms * pb->occ;
     if (ncand > 1) // candidates fill the machine together
         full = std::max<int64_t>(1, full / std::min<int64_t>(ncand, full));
+    if (reserve_slot && full > 1)
+        --full; // one CTA slot stays free for the resident trust-region warp (trs_server)
     return (int)std::min<int64_t>(need, full);
 }
 
@@ -175,8 +192,21 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.req_stride = pb->req_stride;
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
-    void *args[] = {&prm};
+    prm.nranks = 1;
+    if (pb->server_on) {
+        prm.channel = channel_of(pb);
+        prm.peer_channel[0] = prm.channel;
+        if (pb->comm && pb->comm->nranks > 1) {
+            prm.nranks = pb->comm->nranks;
+            prm.rank = pb->comm->rank;
+            for (int r = 0; r < prm.nranks; ++r)
+                prm.peer_channel[r] = pb->comm->peer_channel[r];
+        }
+    }
     const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size();
+    if (timed)
+        prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
+    void *args[] = {&prm};
     if (timed)
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
     CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args, 0,
@@ -205,6 +235,37 @@ static int exchange_packet(gslnls_problem *pb, size_t count)
         return rc;
     CK(launch_sum_rank_packets(pb->d_gather, pb->d_packet, (int)count, R, pb->stream));
     ++pb->launches;
+    return GSLNLS_SUCCESS;
+}
+
+// make the resident trust-region warp leave (no-op when it already has) and wait for it
+static void stop_server(gslnls_problem *pb)
+{
+    if (!pb->server_on)
+        return;
+    char *ch = channel_of(pb);
+    if (pb->h_flags[0] == 0 && ch) {
+        static const unsigned long long one = 1ull;
+        cudaMemcpyAsync(ch + NLS_CH_ABORT, &one, sizeof(one), cudaMemcpyHostToDevice, pb->ctl_stream);
+        cudaStreamSynchronize(pb->ctl_stream);
+    }
+    cudaStreamSynchronize(pb->srv_stream);
+    pb->server_on = false;
+}
+
+// block until the server has published the request that follows the last completed pass (or has
+// finished the fit); the pass launches themselves must already have drained from the main stream
+static int wait_server_caught_up(gslnls_problem *pb)
+{
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(pb->h_ndone); // pinned, 16 bytes
+    char *ch = channel_of(pb);
+    for (long spin = 0; pb->h_flags[0] == 0 && spin < 50000000L; ++spin) {
+        CK(cudaMemcpyAsync(&w[0], ch + NLS_CH_REQ_SEQ, sizeof(w[0]), cudaMemcpyDeviceToHost, pb->ctl_stream));
+        CK(cudaMemcpyAsync(&w[1], ch + NLS_CH_PASS_CTR, sizeof(w[1]), cudaMemcpyDeviceToHost, pb->ctl_stream));
+        CK(cudaStreamSynchronize(pb->ctl_stream));
+        if (w[0] >= w[1] + 1ull)
+            break;
+    }
     return GSLNLS_SUCCESS;
 }
 
@@ -255,6 +316,18 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
     if (const char *c = std::getenv("GSLNLS_CHUNK"))
         pb->chunk = std::max(1, std::atoi(c));
+    if (const char *c = std::getenv("GSLNLS_SERVER"))
+        pb->allow_server = std::atoi(c) != 0;
+    if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
+        pb->watchdog_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000000ull;
+    CK(cudaStreamCreateWithFlags(&pb->srv_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&pb->ctl_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&pb->ev_reset, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pb->ev_chunk[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pb->ev_chunk[1], cudaEventDisableTiming));
+    CK(cudaHostAlloc(&pb->h_flags, sizeof(int) * 4, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&pb->d_flags, pb->h_flags, 0));
+    pb->h_flags[0] = 0;
     *out = pb;
     return GSLNLS_SUCCESS;
 }
@@ -264,7 +337,16 @@ GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
     if (!pb)
         return;
     cudaSetDevice(pb->device);
+    stop_server(pb);
     cudaStreamSynchronize(pb->stream);
+    cudaFree(pb->own_channel);
+    cudaFree(pb->d_prof_flags);
+    cudaFreeHost(pb->h_flags);
+    cudaEventDestroy(pb->ev_reset);
+    cudaEventDestroy(pb->ev_chunk[0]);
+    cudaEventDestroy(pb->ev_chunk[1]);
+    cudaStreamDestroy(pb->srv_stream);
+    cudaStreamDestroy(pb->ctl_stream);
     for (double *b : pb->owned)
         cudaFree(b);
     free_workspace(pb);
@@ -359,7 +441,7 @@ GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm)
     return GSLNLS_SUCCESS;
 }
 
-static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch)
+static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch, bool reserve_slot = false)
 {
     if (!pb->dy) {
         set_error("no data: call gslnls_problem_upload or gslnls_problem_bind_device first");
@@ -369,7 +451,7 @@ static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch)
     int rc = ensure_kernels(pb, batch);
     if (rc)
         return rc;
-    pb->grid_x = pick_grid(pb, ncand);
+    pb->grid_x = pick_grid(pb, ncand, reserve_slot);
     rc = ensure_workspace(pb, ncand, pb->grid_x, ntrace);
     return rc;
 }
@@ -527,9 +609,17 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
     if (rc)
         return rc;
     const int ntrace = pb->P.trace ? pb->P.maxiter + 1 : 0;
-    rc = prepare(pb, 1, ntrace, false);
+    stop_server(pb);
+    const bool sharded = pb->comm && pb->comm->nranks > 1;
+    const bool use_server = pb->allow_server && pb->p <= trs_server_max_p() &&
+                            trs::packet_doubles(pb->p) + 1 <= NLS_CH_MAXPK && (!sharded || pb->comm->p2p);
+    rc = prepare(pb, 1, ntrace, false, use_server);
     if (rc)
         return rc;
+    if (use_server && !sharded && !pb->own_channel) {
+        CK(cudaMalloc(&pb->own_channel, NLS_CH_BYTES));
+        CK(cudaMemsetAsync(pb->own_channel, 0, NLS_CH_BYTES, pb->stream));
+    }
     const int p = pb->p;
     pb->start.assign(start, start + p);
     pb->ncand = 1;
@@ -542,6 +632,21 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
     CK(trs_launch_reset(pb->d_state, pb->state_stride, pb->d_req, pb->req_stride, pb->d_starts, p, 1, pb->d_ndone,
                         pb->stream));
     ++pb->launches;
+    if (use_server) {
+        // the server starts once the records above are in place; the pass launches that follow on
+        // the main stream find their request through the channel, not through stream order
+        const bool tr = pb->P.trace != 0;
+        CK(trs_launch_channel_begin(channel_of(pb), pb->stream));
+        CK(cudaEventRecord(pb->ev_reset, pb->stream));
+        CK(cudaStreamWaitEvent(pb->srv_stream, pb->ev_reset, 0));
+        pb->h_flags[0] = 0;
+        CK(trs_launch_server(pb->P, channel_of(pb), sharded ? pb->comm->nranks : 1, pb->pk_stride, pb->d_state,
+                             pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr, tr ? pb->d_ssrtrace : nullptr,
+                             tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->watchdog_ns,
+                             pb->srv_stream));
+        pb->launches += 2;
+        pb->server_on = true;
+    }
     pb->active = true;
     pb->passes = 0;
     return GSLNLS_SUCCESS;
@@ -558,6 +663,50 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
     int64_t run = 0;
     int fin = 0;
     CK(cudaEventRecord(pb->ev0, pb->stream));
+    if (pb->server_on) {
+        // keep two chunks of pass launches in flight; the only host work per chunk is waiting for the
+        // older chunk's event and looking at the done word the server writes into mapped host memory
+        int slot = 0, inflight = 0;
+        fin = pb->h_flags[0] != 0;
+        while (!fin && (max_passes <= 0 || run < max_passes)) {
+            int todo = pb->chunk;
+            if (max_passes > 0)
+                todo = (int)std::min<int64_t>(todo, max_passes - run);
+            for (int i = 0; i < todo; ++i) {
+                int rc = launch_pass(pb, 1, 0);
+                if (rc)
+                    return rc;
+            }
+            run += todo;
+            CK(cudaEventRecord(pb->ev_chunk[slot], pb->stream));
+            slot ^= 1;
+            if (++inflight == 2) {
+                CK(cudaEventSynchronize(pb->ev_chunk[slot]));
+                --inflight;
+            }
+            fin = pb->h_flags[0] != 0;
+        }
+        CK(cudaEventRecord(pb->ev1, pb->stream));
+        CK(cudaEventSynchronize(pb->ev1));
+        if (!fin) {
+            // the last pass has left the stream; its step may still be running in the server
+            int rc = wait_server_caught_up(pb);
+            if (rc)
+                return rc;
+            fin = pb->h_flags[0] != 0;
+        }
+        if (pb->h_flags[0] == 2) {
+            set_error("trust-region server watchdog: a rank never delivered its packet");
+            return GSLNLS_ECOMM;
+        }
+        if (device_ms)
+            CK(cudaEventElapsedTime(device_ms, pb->ev0, pb->ev1));
+        if (done)
+            *done = fin;
+        if (passes_run)
+            *passes_run = run;
+        return GSLNLS_SUCCESS;
+    }
     while (!fin && (max_passes <= 0 || run < max_passes)) {
         int todo = pb->chunk;
         if (max_passes > 0)
@@ -605,6 +754,15 @@ GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, g
     CK(cudaSetDevice(pb->device));
     const int p = pb->p;
     std::memset(out, 0, sizeof(*out));
+    if (pb->server_on) {
+        // wait until the server has digested every pass that was launched (request seq = passes + 1),
+        // then let it go; an unfinished fit leaves its state record current
+        CK(cudaStreamSynchronize(pb->stream));
+        int rc = wait_server_caught_up(pb);
+        if (rc)
+            return rc;
+        stop_server(pb);
+    }
     std::vector<double> S(pb->state_stride);
     CK(cudaMemcpyAsync(S.data(), pb->d_state, sizeof(double) * pb->state_stride, cudaMemcpyDeviceToHost, pb->stream));
     CK(cudaStreamSynchronize(pb->stream));
@@ -681,7 +839,10 @@ GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const
     int64_t total = 0;
     while (!done && total < hard_cap) {
         int64_t run = 0;
-        rc = gslnls_problem_fit_run(pb, pb->chunk * 4, &done, &run, nullptr);
+        // launch-ordered mode returns to the host every few chunks; with the resident server one call
+        // runs the whole fit
+        const int64_t budget = pb->server_on ? std::min<int64_t>(hard_cap - total, 1 << 30) : pb->chunk * 4;
+        rc = gslnls_problem_fit_run(pb, (int)budget, &done, &run, nullptr);
         if (rc)
             return rc;
         total += run;
@@ -723,6 +884,14 @@ GSLNLS_API int gslnls_problem_set_profile(gslnls_problem *pb, int max_passes)
         CK(cudaEventCreate(&e));
         pb->prof_ev.push_back(e);
     }
+    if (pb->prof_flags_cap < pb->prof_ev.size() / 2) {
+        cudaFree(pb->d_prof_flags);
+        pb->d_prof_flags = nullptr;
+        CK(cudaMalloc(&pb->d_prof_flags, sizeof(int) * (pb->prof_ev.size() / 2)));
+        pb->prof_flags_cap = pb->prof_ev.size() / 2;
+    }
+    if (pb->d_prof_flags)
+        CK(cudaMemsetAsync(pb->d_prof_flags, 0, sizeof(int) * pb->prof_flags_cap, pb->stream));
     return GSLNLS_SUCCESS;
 }
 
@@ -732,13 +901,43 @@ GSLNLS_API int gslnls_problem_profile(gslnls_problem *pb, float *avg_pass_ms, in
         return GSLNLS_EINVAL;
     CK(cudaStreamSynchronize(pb->stream));
     double tot = 0.0;
+    std::vector<int> real(pb->prof_used / 2 + 1, 0);
+    if (pb->prof_used)
+        CK(cudaMemcpy(real.data(), pb->d_prof_flags, sizeof(int) * (pb->prof_used / 2), cudaMemcpyDeviceToHost));
+    int64_t cnt = 0;
     for (size_t i = 0; i + 1 < pb->prof_used; i += 2) {
+        if (!real[i / 2])
+            continue; // an idle launch behind a finished fit: not a pass
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, pb->prof_ev[i], pb->prof_ev[i + 1]));
         tot += ms;
+        ++cnt;
     }
-    *npasses_timed = (int64_t)(pb->prof_used / 2);
+    *npasses_timed = cnt;
     *avg_pass_ms = *npasses_timed ? (float)(tot / (double)*npasses_timed) : 0.f;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_channel_stats(gslnls_problem *pb, int reset, double *avg_stream_us, double *avg_step_us,
+                                            int64_t *npasses)
+{
+    if (!pb)
+        return GSLNLS_EINVAL;
+    char *ch = channel_of(pb);
+    if (avg_stream_us) *avg_stream_us = 0.0;
+    if (avg_step_us) *avg_step_us = 0.0;
+    if (npasses) *npasses = 0;
+    if (!ch)
+        return GSLNLS_SUCCESS;
+    CK(cudaSetDevice(pb->device));
+    CK(cudaStreamSynchronize(pb->stream));
+    unsigned long long tm[5] = {0, 0, 0, 0, 0};
+    CK(cudaMemcpy(tm, ch + NLS_CH_TIMER, sizeof(tm), cudaMemcpyDeviceToHost));
+    if (avg_stream_us && tm[2]) *avg_stream_us = 1e-3 * (double)tm[1] / (double)tm[2];
+    if (avg_step_us && tm[4]) *avg_step_us = 1e-3 * (double)tm[3] / (double)tm[4];
+    if (npasses) *npasses = (int64_t)tm[2];
+    if (reset)
+        CK(cudaMemset(ch + NLS_CH_TIMER, 0, sizeof(tm)));
     return GSLNLS_SUCCESS;
 }
 

@@ -4,6 +4,7 @@
 // Compiled offline for sm_100a into libgslnls_b200.so.
 #include <cuda_runtime.h>
 
+#include "nls_abi.h"
 #include "trs_core.h"
 #include "trs_launch.hpp"
 
@@ -41,6 +42,133 @@ __global__ void __launch_bounds__(128) trs_step_batch(const trs::Params P, doubl
     S.advance(state, packets + (size_t)c * pk_stride, reqs + (size_t)c * req_stride, nullptr, nullptr, nullptr);
     if (S.phase == trs::PH_DONE)
         atomicAdd(ndone, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// trs_server: the trust-region warp stays resident for a whole fit.  It waits until the packet of
+// pass k has been deposited in this GPU's mailbox by every rank's pass kernel (local stores, or
+// NVLink peer stores from the other GPUs), adds the rank packets in rank order -- so all GPUs hold
+// bitwise the same normal equations and take bitwise the same step without any broadcast --,
+// advances the state machine and publishes request k+1, on which the already-dispatched next pass
+// kernel is spinning.  Exchange + step are one resident kernel: no collective call, no launch and
+// no cold instruction cache between two passes.
+static __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+static __device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int PMAX>
+__global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *channel, int nranks, int pk_count,
+                                                 double *state, double *packet, double *req, double *partrace,
+                                                 double *ssrtrace, double *condtrace, int *ndone,
+                                                 volatile int *host_flags, unsigned long long watchdog_ns)
+{
+    extern __shared__ double trs_smem[];
+    const int lane = threadIdx.x & 31;
+    unsigned long long *req_seq = (unsigned long long *)(channel + NLS_CH_REQ_SEQ);
+    const unsigned long long *flags = (const unsigned long long *)(channel + NLS_CH_FLAGS);
+    const unsigned long long *abort_w = (const unsigned long long *)(channel + NLS_CH_ABORT);
+    const double *mbox = (const double *)(channel + NLS_CH_DATA);
+    unsigned long long k = __ldcg((const unsigned long long *)(channel + NLS_CH_FIT_SEQ0));
+    trs::Solver<PMAX, trs::WarpLanes> S(P, trs::WarpLanes(), trs_smem, trs_smem + P.p * P.p);
+    if ((int)__ldcg(state + trs::S_PHASE) == trs::PH_DONE)
+        return;
+    for (;; ++k) {
+        // ---- wait for pass k from every rank (lane r watches rank r) ----
+        unsigned long long t0 = 0ull, spins = 0ull;
+        int why = 0; // 0 packet, 1 abort, 2 watchdog
+        for (;;) {
+            const bool have = lane >= nranks || ld_acquire_sys(flags + 16 * lane) >= k;
+            if (__all_sync(0xffffffffu, have))
+                break;
+            if ((++spins & 255ull) == 0ull) {
+                unsigned long long a = 0ull, t = 0ull;
+                if (lane == 0) {
+                    a = ld_acquire_sys(abort_w);
+                    t = globaltimer_ns();
+                }
+                a = __shfl_sync(0xffffffffu, a, 0);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (a) {
+                    why = 1;
+                    break;
+                }
+                if (t0 == 0ull)
+                    t0 = t;
+                else if (t - t0 > watchdog_ns) {
+                    why = 2;
+                    break;
+                }
+            }
+        }
+        if (why == 1)
+            return; // fit_end before completion: state record is current, request k stays published
+        if (why == 2) {
+            // a peer never delivered: fail the fit instead of hanging the GPU
+            if (lane == 0) {
+                state[trs::S_STATUS] = (double)trs::E_FAILURE;
+                state[trs::S_PHASE] = (double)trs::PH_DONE;
+                req[0] = (double)trs::MODE_IDLE;
+                __threadfence();
+                st_release_gpu(req_seq, k + 1ull);
+                atomicAdd(ndone, 1);
+                __threadfence_system();
+                host_flags[0] = 2;
+            }
+            return;
+        }
+        const unsigned long long t_in = globaltimer_ns();
+        // ---- rank-ordered sum of the deposited packets ----
+        const double *slot = mbox + (size_t)(k & 1ull) * NLS_MAX_RANKS * NLS_CH_MAXPK;
+        for (int e = lane; e < pk_count; e += 32) {
+            double s = __ldcg(slot + e);
+            for (int r = 1; r < nranks; ++r)
+                s += __ldcg(slot + (size_t)r * NLS_CH_MAXPK + e);
+            packet[e] = s;
+        }
+        __syncwarp();
+        S.advance(state, packet, req, partrace, ssrtrace, condtrace);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            st_release_gpu(req_seq, k + 1ull);
+            unsigned long long *tm = (unsigned long long *)(channel + NLS_CH_TIMER);
+            tm[3] += globaltimer_ns() - t_in; // packet complete -> next request published, summed
+            tm[4] += 1ull;
+        }
+        if (S.phase == trs::PH_DONE) {
+            if (lane == 0) {
+                atomicAdd(ndone, 1);
+                __threadfence_system();
+                host_flags[0] = 1;
+            }
+            return;
+        }
+    }
+}
+
+// start-of-fit bookkeeping of the channel (stream-ordered after every earlier pass kernel)
+__global__ void trs_channel_begin(char *channel)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long done = *(unsigned long long *)(channel + NLS_CH_PASS_CTR);
+        *(unsigned long long *)(channel + NLS_CH_FIT_SEQ0) = done + 1ull;
+        *(unsigned long long *)(channel + NLS_CH_ABORT) = 0ull;
+        __threadfence();
+        *(unsigned long long *)(channel + NLS_CH_REQ_SEQ) = done + 1ull; // request 1 of this fit = trs_reset's
+    }
 }
 
 // reset kernels: write the initial state / request records on the device
@@ -86,6 +214,29 @@ cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int 
 }
 
 int trs_max_p() { return 100; }
+int trs_server_max_p() { return 32; }
+
+cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream)
+{
+    trs_channel_begin<<<1, 32, 0, stream>>>(channel);
+    return cudaGetLastError();
+}
+
+cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
+                              double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
+                              int *ndone, int *host_flags_dev, unsigned long long watchdog_ns, cudaStream_t stream)
+{
+    const size_t smem = sizeof(double) * 2 * (size_t)P.p * P.p;
+    if (P.p <= 8)
+        trs_server<8><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace,
+                                               condtrace, ndone, host_flags_dev, watchdog_ns);
+    else if (P.p <= 32)
+        trs_server<32><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace,
+                                                condtrace, ndone, host_flags_dev, watchdog_ns);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 
 static size_t warp_smem_bytes(int p) { return sizeof(double) * 2 * (size_t)p * p; }
 

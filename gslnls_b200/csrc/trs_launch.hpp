@@ -16,6 +16,12 @@ cudaError_t trs_launch_reset(double *states, int state_stride, double *reqs, int
                              int p, int ncand, int *ndone, cudaStream_t stream);
 cudaError_t trs_launch_set_request(double *req, int mode, const double *theta, const double *v, int p,
                                    cudaStream_t stream);
+// resident-server mode (one fit, one candidate): channel bookkeeping + the server kernel itself
+int trs_server_max_p();
+cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream);
+cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
+                              double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
+                              int *ndone, int *host_flags_dev, unsigned long long watchdog_ns, cudaStream_t stream);
 cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int count, int nranks,
                                     cudaStream_t stream);
 } // namespace gslnls

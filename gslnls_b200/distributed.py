@@ -27,6 +27,11 @@ class Comm:
         _lib.check(_lib.lib().gslnls_comm_create(buf, rank, world, device, C.byref(h)))
         self.handle, self.rank, self.world = h, rank, world
 
+    @property
+    def has_peer_memory(self):
+        """True when packets travel through NVLink peer-memory mailboxes (no collective call per pass)"""
+        return bool(_lib.lib().gslnls_comm_has_peer_memory(self.handle))
+
     @staticmethod
     def unique_id():
         buf = C.create_string_buffer(128)

@@ -203,6 +203,12 @@ class Problem:
         _lib.check(_lib.lib().gslnls_problem_profile(self.handle, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
 
+    def channel_stats(self, reset=False):
+        """device clocks of the resident-server mode: (avg pass µs request->packet, avg step µs packet->request, passes)"""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(_lib.lib().gslnls_problem_channel_stats(self.handle, int(reset), C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     @property
     def launch_count(self):
         return _lib.lib().gslnls_problem_launch_count(self.handle)

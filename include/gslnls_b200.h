@@ -174,6 +174,12 @@ GSLNLS_API int gslnls_problem_timer_stop(gslnls_problem *pb, float *ms);
 GSLNLS_API int gslnls_problem_set_profile(gslnls_problem *pb, int max_passes);
 GSLNLS_API int gslnls_problem_profile(gslnls_problem *pb, float *avg_pass_ms, int64_t *npasses_timed);
 
+/* device-side clocks of the resident-server mode (globaltimer, averaged over the passes since the last
+ * reset): time a pass kernel spends between seeing its request and depositing its packet, and time the
+ * trust-region warp spends between a complete packet and the next published request */
+GSLNLS_API int gslnls_problem_channel_stats(gslnls_problem *pb, int reset, double *avg_stream_us,
+                                            double *avg_step_us, int64_t *npasses);
+
 /* ---- batched multi-start inner kernels (src/nls_mstart.c:75-91: det(J^T J) screen + mstart_p LM
  *      iterations per start point), candidates ride blockIdx.y ----------------------------------- */
 GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts /* S*p row-major */, int S,
@@ -188,6 +194,10 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
 GSLNLS_API int gslnls_comm_get_unique_id(void *id_bytes /* GSLNLS_COMM_ID_BYTES */);
 GSLNLS_API int gslnls_comm_create(const void *id_bytes, int rank, int nranks, int device, gslnls_comm **out);
 GSLNLS_API void gslnls_comm_free(gslnls_comm *c);
+/* 1 when the ranks exchange packets through NVLink peer memory (each pass kernel deposits its packet
+ * directly in every GPU's mailbox and a resident trust-region warp consumes it); 0 when the exchange
+ * is an NCCL all-gather between the pass and the step kernel */
+GSLNLS_API int gslnls_comm_has_peer_memory(const gslnls_comm *c);
 GSLNLS_API int gslnls_comm_rank(const gslnls_comm *c);
 GSLNLS_API int gslnls_comm_size(const gslnls_comm *c);
 

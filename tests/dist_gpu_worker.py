@@ -29,7 +29,7 @@ def main():
     pb.set_comm(comm)
     theta = [4.0, 1.3, 0.9]
     pk = pb.eval_packet(theta)
-    out = {"rank": rank, "packet": pk.tolist(), "fits": {}}
+    out = {"rank": rank, "packet": pk.tolist(), "fits": {}, "p2p": int(comm.has_peer_memory)}
     for alg in ("lm", "lmaccel", "dogleg"):
         f = pb.fit(list(bench.START), algorithm=alg)
         out["fits"][alg] = {"par": f["par"].tolist(), "ssr": f["ssr"], "niter": f["niter"], "conv": f["conv"],

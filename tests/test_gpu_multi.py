@@ -18,8 +18,10 @@ def _ngpu():
     return _lib.lib().gslnls_device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_fit_matches_oracle(tmp_path, world):
+@pytest.mark.parametrize("world,p2p", [(2, 1), (2, 0), (4, 1), (8, 1)])
+def test_sharded_fit_matches_oracle(tmp_path, world, p2p):
+    """p2p=1: pass kernels deposit packets in every GPU's mailbox over NVLink peer memory and the resident
+    trust-region warp sums them in rank order; p2p=0: NCCL all-gather + rank-order sum between kernels"""
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     import bench
@@ -29,7 +31,8 @@ def test_sharded_fit_matches_oracle(tmp_path, world):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    env = dict(os.environ, GSLNLS_TEST_OUT=str(tmp_path), GSLNLS_TEST_N=str(n))
+    env = dict(os.environ, GSLNLS_TEST_OUT=str(tmp_path), GSLNLS_TEST_N=str(n), GSLNLS_P2P=str(p2p),
+               GSLNLS_WATCHDOG_S="20")
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node",
                            str(world), "--master-addr", "127.0.0.1", "--master-port", str(port),
                            os.path.join(ROOT, "tests", "dist_gpu_worker.py")], env=env, timeout=600)
@@ -37,6 +40,7 @@ def test_sharded_fit_matches_oracle(tmp_path, world):
     x, y = bench.synth_rows(0, n, n)
     full = O.eval_packet("exp3", y, [4.0, 1.3, 0.9], x=x, longdouble=True)
     for r in res:
+        assert r["p2p"] == p2p
         assert r["packet"] == res[0]["packet"]            # all ranks: bitwise identical reduced packet
         assert r["fits"] == res[0]["fits"]                # ... and therefore identical trajectories
     got = np.array(res[0]["packet"])
