@@ -563,10 +563,40 @@ static const char *fn_name(int fid)
     }
 }
 
-std::string emit_block(const Graph &g, const std::vector<int> &roots, std::vector<std::string> &root_names,
-                       const std::string &indent)
+// one statement computing node e, operands named by `name`
+static std::string node_rhs(const Graph &g, int e, const std::function<std::string(int)> &name)
 {
-    std::vector<char> live(g.size(), 0);
+    const Node &N = g.at(e);
+    switch (N.op) {
+    case Op::Add: return name(N.a) + " + " + name(N.b);
+    case Op::Sub: return name(N.a) + " - " + name(N.b);
+    case Op::Mul: return name(N.a) + " * " + name(N.b);
+    case Op::Div: return name(N.a) + " / " + name(N.b);
+    case Op::Neg: return "-" + name(N.a);
+    case Op::Func: return std::string(fn_name(N.b)) + "(" + name(N.a) + ")";
+    case Op::Pow: {
+        const Node &B = g.at(N.b);
+        if (B.op == Op::Const) {
+            const double c = B.c;
+            if (c == 2.0)
+                return name(N.a) + " * " + name(N.a);
+            if (c == 0.5)
+                return "sqrt(" + name(N.a) + ")";
+            if (c == -0.5)
+                return "1.0 / sqrt(" + name(N.a) + ")";
+            if (c == std::floor(c) && std::fabs(c) <= 64.0)
+                return "nls_powi(" + name(N.a) + ", " + std::to_string(static_cast<int>(c)) + ")";
+            return "pow(" + name(N.a) + ", " + lit(c) + ")";
+        }
+        return "pow(" + name(N.a) + ", " + name(N.b) + ")";
+    }
+    default: return "";
+    }
+}
+
+static void mark_live(const Graph &g, const std::vector<int> &roots, std::vector<char> &live)
+{
+    live.assign(g.size(), 0);
     std::function<void(int)> mark = [&](int e) {
         if (live[e])
             return;
@@ -580,7 +610,19 @@ std::string emit_block(const Graph &g, const std::vector<int> &roots, std::vecto
     };
     for (int r : roots)
         mark(r);
-    auto name = [&](int e) -> std::string {
+}
+
+static bool is_leaf(const Node &N)
+{
+    return N.op == Op::Const || N.op == Op::Param || N.op == Op::Var || N.op == Op::Vel;
+}
+
+std::string emit_block(const Graph &g, const std::vector<int> &roots, std::vector<std::string> &root_names,
+                       const std::string &indent)
+{
+    std::vector<char> live;
+    mark_live(g, roots, live);
+    std::function<std::string(int)> name = [&](int e) -> std::string {
         const Node &N = g.at(e);
         switch (N.op) {
         case Op::Const: return lit(N.c);
@@ -592,44 +634,141 @@ std::string emit_block(const Graph &g, const std::vector<int> &roots, std::vecto
     };
     std::ostringstream os;
     for (int e = 0; e < static_cast<int>(g.size()); ++e) {
-        if (!live[e])
+        if (!live[e] || is_leaf(g.at(e)))
             continue;
-        const Node &N = g.at(e);
-        std::string rhs;
-        switch (N.op) {
-        case Op::Const: case Op::Param: case Op::Var: case Op::Vel: continue;
-        case Op::Add: rhs = name(N.a) + " + " + name(N.b); break;
-        case Op::Sub: rhs = name(N.a) + " - " + name(N.b); break;
-        case Op::Mul: rhs = name(N.a) + " * " + name(N.b); break;
-        case Op::Div: rhs = name(N.a) + " / " + name(N.b); break;
-        case Op::Neg: rhs = "-" + name(N.a); break;
-        case Op::Func: rhs = std::string(fn_name(N.b)) + "(" + name(N.a) + ")"; break;
-        case Op::Pow: {
-            const Node &B = g.at(N.b);
-            if (B.op == Op::Const) {
-                const double c = B.c;
-                if (c == 2.0)
-                    rhs = name(N.a) + " * " + name(N.a);
-                else if (c == 0.5)
-                    rhs = "sqrt(" + name(N.a) + ")";
-                else if (c == -0.5)
-                    rhs = "1.0 / sqrt(" + name(N.a) + ")";
-                else if (c == std::floor(c) && std::fabs(c) <= 64.0)
-                    rhs = "nls_powi(" + name(N.a) + ", " + std::to_string(static_cast<int>(c)) + ")";
-                else
-                    rhs = "pow(" + name(N.a) + ", " + lit(c) + ")";
-            } else {
-                rhs = "pow(" + name(N.a) + ", " + name(N.b) + ")";
-            }
-            break;
-        }
-        }
-        os << indent << "const double t" << e << " = " << rhs << ";\n";
+        os << indent << "const double t" << e << " = " << node_rhs(g, e, name) << ";\n";
     }
     root_names.clear();
     for (int r : roots)
         root_names.push_back(name(r));
     return os.str();
+}
+
+// Two-stage emission for the tiled kernel (p > 8), where neither the parameters nor anything
+// derived from them should occupy registers across the observation loop.  Every subexpression
+// that does not depend on a predictor ("invariant": built from constants, parameters and the
+// velocity only) is computed once per launch by `prep` into c[]; a division of a row quantity by
+// an invariant becomes a multiplication by the invariant's reciprocal.  `body` then evaluates one
+// observation from th[], c[] (both in shared memory) and x[].
+SplitCode emit_split(Graph &g, const std::vector<int> &roots_in, const std::string &indent, bool sink_rows)
+{
+    // ---- pass 1: rewrite a / b (b invariant, a not) -> a * (1 / b) ----
+    std::vector<char> live;
+    mark_live(g, roots_in, live);
+    const int n0 = static_cast<int>(g.size());
+    std::vector<int> re(n0, -1);
+    std::vector<char> inv0(n0, 0);
+    const int one = g.cst(1.0);
+    for (int e = 0; e < n0; ++e) {
+        if (!live[e])
+            continue;
+        const Node N = g.at(e); // by value: g grows below
+        switch (N.op) {
+        case Op::Const: case Op::Param: case Op::Vel: inv0[e] = 1; re[e] = e; break;
+        case Op::Var: inv0[e] = 0; re[e] = e; break;
+        case Op::Neg: inv0[e] = inv0[N.a]; re[e] = re[N.a] == N.a ? e : g.neg(re[N.a]); break;
+        case Op::Func: inv0[e] = inv0[N.a]; re[e] = re[N.a] == N.a ? e : g.func(N.b, re[N.a]); break;
+        default: {
+            inv0[e] = inv0[N.a] && inv0[N.b];
+            const int a = re[N.a], b = re[N.b];
+            if (N.op == Op::Div && inv0[N.b] && !inv0[N.a] && !g.is_const(b)) {
+                re[e] = g.mul(a, g.div(one, b));
+            } else if (a == N.a && b == N.b) {
+                re[e] = e;
+            } else {
+                switch (N.op) {
+                case Op::Add: re[e] = g.add(a, b); break;
+                case Op::Sub: re[e] = g.sub(a, b); break;
+                case Op::Mul: re[e] = g.mul(a, b); break;
+                case Op::Div: re[e] = g.div(a, b); break;
+                default: re[e] = g.pow(a, b); break;
+                }
+            }
+            break;
+        }
+        }
+    }
+    std::vector<int> roots;
+    for (int r : roots_in)
+        roots.push_back(re[r]);
+
+    // ---- pass 2: classify on the rewritten graph ----
+    mark_live(g, roots, live);
+    const int n1 = static_cast<int>(g.size());
+    std::vector<char> inv(n1, 0), used_by_row(n1, 0);
+    for (int e = 0; e < n1; ++e) {
+        if (!live[e])
+            continue;
+        const Node &N = g.at(e);
+        switch (N.op) {
+        case Op::Const: case Op::Param: case Op::Vel: inv[e] = 1; break;
+        case Op::Var: inv[e] = 0; break;
+        case Op::Neg: case Op::Func: inv[e] = inv[N.a]; break;
+        default: inv[e] = inv[N.a] && inv[N.b]; break;
+        }
+        if (!inv[e] && !is_leaf(N)) {
+            used_by_row[N.a] = 1;
+            if (N.op != Op::Neg && N.op != Op::Func)
+                used_by_row[N.b] = 1;
+        }
+    }
+    for (int r : roots)
+        used_by_row[r] = 1;
+    std::vector<int> slot(n1, -1);
+    int nc = 0;
+    for (int e = 0; e < n1; ++e)
+        if (live[e] && inv[e] && !is_leaf(g.at(e)) && used_by_row[e])
+            slot[e] = nc++;
+
+    auto leaf_name = [&](const Node &N) -> std::string {
+        switch (N.op) {
+        case Op::Const: return lit(N.c);
+        case Op::Param: return "th[" + std::to_string(N.a) + "]";
+        case Op::Var: return "x[" + std::to_string(N.a) + "]";
+        default: return "v[" + std::to_string(N.a) + "]";
+        }
+    };
+    std::function<std::string(int)> prep_name = [&](int e) -> std::string {
+        const Node &N = g.at(e);
+        return is_leaf(N) ? leaf_name(N) : "t" + std::to_string(e);
+    };
+    std::function<std::string(int)> body_name = [&](int e) -> std::string {
+        const Node &N = g.at(e);
+        if (is_leaf(N))
+            return leaf_name(N);
+        if (slot[e] >= 0)
+            return "c[" + std::to_string(slot[e]) + "]";
+        return "t" + std::to_string(e);
+    };
+    SplitCode out;
+    std::ostringstream prep, body;
+    for (int e = 0; e < n1; ++e) {
+        if (!live[e] || is_leaf(g.at(e)))
+            continue;
+        if (inv[e]) {
+            prep << indent << "const double t" << e << " = " << node_rhs(g, e, prep_name) << ";\n";
+            if (slot[e] >= 0)
+                prep << indent << "c[" << slot[e] << "] = t" << e << ";\n";
+        } else {
+            body << indent << "const double t" << e << " = " << node_rhs(g, e, body_name) << ";\n";
+            // hand a Jacobian entry to the caller as soon as it exists (roots[0] is f, roots[1+j] is J_j),
+            // so that a long row never has to sit in registers
+            if (sink_rows)
+                for (size_t r = 1; r < roots.size(); ++r)
+                    if (roots[r] == e)
+                        body << indent << "J(" << (r - 1) << ", t" << e << ");\n";
+        }
+    }
+    if (sink_rows)
+        for (size_t r = 1; r < roots.size(); ++r)
+            if (is_leaf(g.at(roots[r])) || inv[roots[r]])
+                body << indent << "J(" << (r - 1) << ", " << body_name(roots[r]) << ");\n";
+    out.prep = prep.str();
+    out.body = body.str();
+    out.nconst = nc;
+    for (int r : roots)
+        out.root_names.push_back(body_name(r));
+    return out;
 }
 
 std::string generate_model_source(const ModelSpec &spec)
@@ -665,6 +804,16 @@ std::string generate_model_source(const ModelSpec &spec)
         for (int j = 0; j < p; ++j)
             os << "    J[" << j << "] = " << names[j + 1] << ";\n";
         os << "}\n\n";
+        // two-stage form for the tiled kernel: invariants once per launch, rows from th[], c[], x[]
+        const SplitCode sc = emit_split(g, roots, "    ", true);
+        os << "#define GSLNLS_NC_FJ " << sc.nconst << "\n";
+        os << "NLS_FN void nls_model_prep_fj(const double *th, double *c)\n{\n"
+           << "    (void)th; (void)c;\n" << sc.prep << "}\n";
+        os << "template <class RowSink>\n"
+           << "NLS_FN void nls_model_fj_c(const double *th, const double *c, const double *x, double &f, RowSink &J)\n{\n"
+           << "    (void)th; (void)x; (void)c;\n"
+           << sc.body << "    f = " << sc.root_names[0] << ";\n";
+        os << "}\n\n";
     }
     if (spec.fvv_mode == 1) {
         const int d1 = g.ddir(f);
@@ -673,6 +822,13 @@ std::string generate_model_source(const ModelSpec &spec)
         os << "NLS_FN double nls_model_fvv(const double *th, const double *v, const double *x)\n{\n"
            << "    (void)th; (void)x; (void)v;\n"
            << body << "    return " << names[0] << ";\n}\n";
+        const SplitCode sc = emit_split(g, {d2}, "    ", false);
+        os << "#define GSLNLS_NC_FVV " << sc.nconst << "\n";
+        os << "NLS_FN void nls_model_prep_fvv(const double *th, const double *v, double *c)\n{\n"
+           << "    (void)th; (void)v; (void)c;\n" << sc.prep << "}\n";
+        os << "NLS_FN double nls_model_fvv_c(const double *th, const double *v, const double *c, const double *x)\n{\n"
+           << "    (void)th; (void)x; (void)v; (void)c;\n"
+           << sc.body << "    return " << sc.root_names[0] << ";\n}\n";
     }
     return os.str();
 }

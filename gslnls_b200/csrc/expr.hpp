@@ -70,6 +70,15 @@ int parse_rhs(Graph &g, const std::string &text, const std::vector<std::string> 
 std::string emit_block(const Graph &g, const std::vector<int> &roots, std::vector<std::string> &root_names,
                        const std::string &indent);
 
+// Two-stage form of the same block: statements that do not depend on a predictor go to `prep`
+// (run once per launch, results in c[0..nconst)), the per-observation rest to `body`.
+struct SplitCode {
+    std::string prep, body;
+    int nconst = 0;
+    std::vector<std::string> root_names;
+};
+SplitCode emit_split(Graph &g, const std::vector<int> &roots, const std::string &indent, bool sink_rows);
+
 struct ModelSpec {
     std::string rhs;
     std::vector<std::string> params, vars;

@@ -13,14 +13,15 @@ namespace gslnls {
 
 struct KernelTune {
     int block = 256, unroll = 4, minb = 2;
+    int tiled = 0; // 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh)
 };
 
 struct VariantKey {
-    int has_w, vec, stream, block, unroll, minb;
+    int has_w, vec, stream, block, unroll, minb, tiled;
     bool operator<(const VariantKey &o) const
     {
-        return std::tie(has_w, vec, stream, block, unroll, minb) <
-               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb);
+        return std::tie(has_w, vec, stream, block, unroll, minb, tiled) <
+               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled);
     }
 };
 
@@ -30,6 +31,7 @@ struct Variant {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t pass = nullptr, materialise = nullptr;
     bool loaded = false;
+    size_t pass_smem = 0; // dynamic shared memory of one nls_pass CTA (tiled variant)
 };
 
 } // namespace gslnls
@@ -50,5 +52,6 @@ struct gslnls_model {
 
 namespace gslnls {
 KernelTune default_tune(int p);
+size_t tiled_smem_bytes(int p, int block, int nconst); // dynamic shared memory of the tiled pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture
 } // namespace gslnls

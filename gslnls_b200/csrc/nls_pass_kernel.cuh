@@ -41,6 +41,9 @@
 #ifndef NLS_STREAM
 #define NLS_STREAM 1
 #endif
+#ifndef NLS_TILED
+#define NLS_TILED 0 /* 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh), for p > 8 */
+#endif
 
 #define NLS_P GSLNLS_P
 #define NLS_NV (GSLNLS_NVAR > 0 ? GSLNLS_NVAR : 1)
@@ -332,12 +335,15 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #endif
 }
 
-// ------------------------------------------------------------------------------------ K1
-extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const NlsPassParams prm)
+// ------------------------------------------------------------------------------------ K1 head / tail
+// Shared by the register-accumulator kernel below and the tiled DMMA kernel (nls_pass_tiled.cuh).
+
+// Start of a launch: in server mode wait for this pass's request; returns the mode to run
+// (NLS_MODE_IDLE: leave) and the pass sequence number.  Uniform across the CTA.
+static __device__ __forceinline__ int nls_begin(const NlsPassParams &prm, const double *req, unsigned long long &seq)
 {
-    const int cand = blockIdx.y;
-    const double *req = prm.req + (size_t)cand * prm.req_stride;
     __shared__ unsigned long long s_seq;
+    seq = 0ull;
     if (prm.channel) {
         // server mode: this launch is pass number k = (passes completed so far) + 1; its request is
         // published by the resident trust-region warp (trs_server) as soon as it has digested
@@ -362,16 +368,18 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
                 *(unsigned long long *)(prm.channel + NLS_CH_TIMER) = nls_globaltimer();
         }
         __syncthreads();
-        if (s_seq == 0ull)
-            return;
+        seq = s_seq;
+        if (seq == 0ull)
+            return NLS_MODE_IDLE;
     }
     const int mode = prm.force_mode > 0 ? prm.force_mode : (int)__ldcg(req);
-    if (mode == NLS_MODE_IDLE)
-        return; // this candidate has finished; uniform for the whole CTA
-    if (prm.prof_flag && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+    if (mode != NLS_MODE_IDLE && prm.prof_flag && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
         *prm.prof_flag = 1;
+    return mode;
+}
 
-    NlsThread T;
+static __device__ __forceinline__ void nls_load_request(const NlsPassParams &prm, const double *req, NlsThread &T)
+{
 #pragma unroll
     for (int j = 0; j < NLS_P; ++j) {
         T.th[j] = __ldcg(req + 1 + j);
@@ -383,45 +391,15 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
         T.idl[j] = 1.0 / d;
     }
     T.h_fvv = prm.h_fvv;
+}
 
-    double acc[NLS_PK];
-#pragma unroll
-    for (int e = 0; e < NLS_PK; ++e)
-        acc[e] = 0.0;
-
-    if (mode == NLS_MODE_FJ)
-        nls_stream<NLS_MODE_FJ>(prm, T, acc);
-    else if (mode == NLS_MODE_FVV)
-        nls_stream<NLS_MODE_FVV>(prm, T, acc);
-    else
-        nls_stream<NLS_MODE_JVP>(prm, T, acc);
-
-    // ---- CTA reduction: fixed shuffle tree, then warps summed in warp order ----
-    __shared__ double sred[NLS_NW][NLS_PK];
+// End of a launch, after this CTA's partial packet (NLS_PK doubles) has been written to
+// prm.partials: the last CTA to arrive sums the CTA partials in CTA order (no FP atomics) and
+// hands the packet on -- to prm.packet (launch-ordered mode) or into every rank's mailbox.
+static __device__ __forceinline__ void nls_grid_finish(const NlsPassParams &prm, int cand, unsigned long long seq)
+{
     __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int e = 0; e < NLS_PK; ++e) {
-        double v = acc[e];
-        v += __shfl_down_sync(0xffffffffu, v, 16);
-        v += __shfl_down_sync(0xffffffffu, v, 8);
-        v += __shfl_down_sync(0xffffffffu, v, 4);
-        v += __shfl_down_sync(0xffffffffu, v, 2);
-        v += __shfl_down_sync(0xffffffffu, v, 1);
-        if (lane == 0)
-            sred[warp][e] = v;
-    }
-    __syncthreads();
-    double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
-    for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NLS_NW; ++w)
-            s += sred[w][e];
-        part[e] = s;
-    }
-
-    // ---- grid reduction by the last CTA to arrive, CTA order fixed ----
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -434,7 +412,6 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     __threadfence();
     const double *parts = prm.partials + (size_t)cand * gridDim.x * prm.pk_stride;
     double *out = prm.packet + (size_t)cand * prm.pk_stride;
-    const unsigned long long seq = prm.channel ? s_seq : 0ull;
     // server mode: slot [seq parity][this rank] of every rank's mailbox (peer memory over NVLink)
     const size_t slot = ((size_t)(seq & 1ull) * NLS_MAX_RANKS + (size_t)prm.rank) * NLS_CH_MAXPK;
     for (int e = warp; e < NLS_PK; e += NLS_NW) {
@@ -480,6 +457,61 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     if (threadIdx.x == 0)
         prm.ticket[cand] = 0u; // ready for the next launch
 }
+
+#if NLS_TILED
+#include "nls_pass_tiled.cuh"
+#else
+// ------------------------------------------------------------------------------------ K1 (register accumulators)
+extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const NlsPassParams prm)
+{
+    const int cand = blockIdx.y;
+    const double *req = prm.req + (size_t)cand * prm.req_stride;
+    unsigned long long seq;
+    const int mode = nls_begin(prm, req, seq);
+    if (mode == NLS_MODE_IDLE)
+        return; // this candidate has finished; uniform for the whole CTA
+
+    NlsThread T;
+    nls_load_request(prm, req, T);
+
+    double acc[NLS_PK];
+#pragma unroll
+    for (int e = 0; e < NLS_PK; ++e)
+        acc[e] = 0.0;
+
+    if (mode == NLS_MODE_FJ)
+        nls_stream<NLS_MODE_FJ>(prm, T, acc);
+    else if (mode == NLS_MODE_FVV)
+        nls_stream<NLS_MODE_FVV>(prm, T, acc);
+    else
+        nls_stream<NLS_MODE_JVP>(prm, T, acc);
+
+    // ---- CTA reduction: fixed shuffle tree, then warps summed in warp order ----
+    __shared__ double sred[NLS_NW][NLS_PK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < NLS_PK; ++e) {
+        double v = acc[e];
+        v += __shfl_down_sync(0xffffffffu, v, 16);
+        v += __shfl_down_sync(0xffffffffu, v, 8);
+        v += __shfl_down_sync(0xffffffffu, v, 4);
+        v += __shfl_down_sync(0xffffffffu, v, 2);
+        v += __shfl_down_sync(0xffffffffu, v, 1);
+        if (lane == 0)
+            sred[warp][e] = v;
+    }
+    __syncthreads();
+    double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
+    for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NLS_NW; ++w)
+            s += sred[w][e];
+        part[e] = s;
+    }
+    nls_grid_finish(prm, cand, seq);
+}
+#endif // NLS_TILED
 
 // ------------------------------------------------------------------------------------ K4
 // resid_i = sqrt(w_i) (fn_i - y_i) and grad[i + n j] = sqrt(w_i) J_ij at the final parameters:

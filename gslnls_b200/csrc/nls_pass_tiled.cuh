@@ -1,0 +1,313 @@
+// nls_pass_tiled.cuh -- K1b: the fused pass for p > 8, J^T J by FP64 tensor-core SYRK.
+//
+// Included by nls_pass_kernel.cuh when NLS_TILED=1 (same entry point name, same packet).  With
+// p(p+1)/2 in the hundreds the normal-equation accumulators no longer fit a thread's registers,
+// so a warp works on slabs of 32 observations:
+//
+//   phase A  lane i evaluates residual and Jacobian row of observation i (the model is inlined,
+//            the row lives in registers) and parks the sqrt(w)-scaled row in the warp's private
+//            shared-memory tile, transposed: tile[column][observation]
+//   phase B  the warp contracts the tile with itself: 8 k-steps of 4 observations, each feeding
+//            one mma.sync.m8n8k4.f64 (DMMA) per 8x8 block pair of the lower triangle.  A- and
+//            B-fragments of a parameter block are the same register, so a k-step costs
+//            ceil(p/8) shared loads for T = PB(PB+1)/2 DMMAs; the T accumulator fragments stay
+//            in registers for the whole launch (42 doubles per lane at p = 48).
+//            J^T r (or J^T fvv, J^T (J d)) is a plain FMA column dot over the same tile.
+//
+// Replaces for large p what nls_pass does for small p: gsl_df_large's dsyrk/dgemv
+// (src/nls_large.c:629,633) without ever forming the n x p matrix J (src/nls_large.c:167).
+// Nothing of size n is written.  On B200 DMMA issues to the same FP64 units as DFMA (measured:
+// 37.1 TFLOP/s either way, no overlap), so the roofline of this kernel is the FP64 pipe; what the
+// tensor-core form buys is one instruction and two operand registers per 256 FMAs.
+//
+// Tunables: NLS_BLOCK threads per CTA (a multiple of 32), NLS_MINB CTAs per SM.
+
+#define NT_PB ((NLS_P + 7) / 8)          /* 8-wide parameter blocks                         */
+#define NT_COLS (NT_PB * 8)              /* J columns incl. zero padding                    */
+#define NT_LDT 36                        /* tile row pitch in doubles: == 4 (mod 8), so both the
+                                            column stores (32 consecutive doubles) and the 4x8
+                                            fragment loads hit 16 distinct 8-byte banks per half-warp */
+#define NT_TILES (NT_PB * (NT_PB + 1) / 2)
+#define NT_GC ((NT_COLS + 31) / 32)      /* column-dot accumulators per lane                */
+
+#if NT_TILES > 28
+#error "nls_pass_tiled: p > 56 needs the tile set split across warps (not built yet)"
+#endif
+
+static __device__ __forceinline__ void nt_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+#if GSLNLS_JAC_MODE == 0
+#define NT_NC_FJ GSLNLS_NC_FJ
+#else
+#define NT_NC_FJ 0
+#endif
+#if GSLNLS_FVV_MODE == 1
+#define NT_NC_FVV GSLNLS_NC_FVV
+#else
+#define NT_NC_FVV 0
+#endif
+// the slow paths (finite-difference Jacobian / fvv) keep parameters and steps in registers
+#define NT_NEED_T (GSLNLS_JAC_MODE != 0 || GSLNLS_FVV_MODE == 2)
+
+// parameters, velocity and the launch invariants of the generated model live in shared memory
+struct NtShared {
+    const double *th, *vv, *c_fj, *c_fvv;
+};
+
+// receives Jacobian entries from the generated row function as they are produced: scaled by
+// sqrt(w) (0 for the padding lanes of the last slab) straight into this lane's tile column; the
+// JVP mode also needs u = row . d, accumulated on the way
+struct NtRowSink {
+    double *col; // &tile[lane]
+    const double *vv;
+    double sw, u;
+    __device__ __forceinline__ void operator()(int j, double v)
+    {
+        const double s = v * sw;
+        col[j * NT_LDT] = s;
+        u = fma(s, vv[j], u);
+    }
+};
+struct NtRowSinkNoDot {
+    double *col;
+    double sw;
+    __device__ __forceinline__ void operator()(int j, double v) { col[j * NT_LDT] = v * sw; }
+};
+
+template <int MODE>
+static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const NlsThread &T, const NtShared &S,
+                                                 double *tile, double *rv, double (&C)[NT_TILES][2],
+                                                 double (&gacc)[NT_GC], double &ss, double &nbad)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n = prm.n;
+    const long long nslab = (n + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * NLS_NW;
+    const int fr = lane >> 2, fc = lane & 3; // fragment coordinates of this lane
+    for (long long slab = (long long)blockIdx.x * NLS_NW + warp; slab < nslab; slab += wstride) {
+        // ---------------- phase A: one observation per lane ----------------
+        const long long i = (slab << 5) + lane;
+        const bool valid = i < n;
+        const long long ii = valid ? i : 0;
+        double xa[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = nls_ld1(prm.vars[k] + ii);
+        const double y = nls_ld1(prm.y + ii);
+#if NLS_HAS_W
+        const double sw = sqrt(nls_ld1(prm.w + ii)); // sqrt_wts_i = sqrt(w_i), src/fdf.c:60-64
+#else
+        const double sw = 1.0;
+#endif
+        // sqrt(w) scaling folded into the tile store; invalid (padding) lanes store zeros
+        const double swv = valid ? sw : 0.0;
+        double f, u = 0.0;
+#if GSLNLS_JAC_MODE == 0
+        if (MODE == NLS_MODE_JVP || (MODE == NLS_MODE_FVV && GSLNLS_FVV_MODE == 2)) {
+            NtRowSink sink{tile + lane, S.vv, swv, 0.0};
+            nls_model_fj_c(S.th, S.c_fj, xa, f, sink);
+            u = sink.u;
+        } else {
+            NtRowSinkNoDot sink{tile + lane, swv};
+            nls_model_fj_c(S.th, S.c_fj, xa, f, sink);
+        }
+#else
+        double J[NLS_P];
+        nls_fj(T, xa, f, J);
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j) {
+            tile[j * NT_LDT + lane] = J[j] * swv;
+            u = fma(J[j] * swv, S.vv[j], u);
+        }
+#endif
+        double r;
+        if (MODE == NLS_MODE_FJ) {
+            r = f - y;
+            if (!nls_finite(f)) {
+                r = NLS_INF; // src/nls_large.c:464-465
+                if (valid)
+                    nbad += 1.0;
+            }
+            r *= sw;
+        } else if (MODE == NLS_MODE_FVV) {
+#if GSLNLS_FVV_MODE == 1
+            r = nls_model_fvv_c(S.th, S.vv, S.c_fvv, xa) * sw;
+#elif GSLNLS_FVV_MODE == 2
+            {
+                // fvv = (2/h) ((f(x + h v) - f(x)) / h - J v), src/fdfvv.c:47-74  (u = sqrt(w) J v here)
+                double tp[NLS_P];
+#pragma unroll
+                for (int k = 0; k < NLS_P; ++k)
+                    tp[k] = T.th[k] + T.h_fvv * T.vv[k];
+                const double fp = nls_model_f(tp, xa);
+                const double hinv = 1.0 / T.h_fvv;
+                r = (2.0 * hinv) * (((fp - f) * hinv) * sw - u);
+            }
+#else
+            r = 0.0;
+#endif
+        } else { // JVP: u = (sqrt(w) J) d
+            r = u;
+        }
+        if (!valid)
+            r = 0.0;
+        rv[lane] = r;
+        ss = fma(r, r, ss);
+        __syncwarp();
+
+        // ---------------- phase B: tile^T tile on the FP64 tensor path ----------------
+        if (MODE == NLS_MODE_FJ) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                double frag[NT_PB];
+#pragma unroll
+                for (int b = 0; b < NT_PB; ++b)
+                    frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+                int t = 0;
+#pragma unroll
+                for (int bi = 0; bi < NT_PB; ++bi)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj, ++t)
+                        nt_dmma(C[t][0], C[t][1], frag[bi], frag[bj]);
+            }
+        }
+        // column dot with r: lane owns columns lane, lane+32, ...; the observation index is rotated by
+        // the lane so that the 32 lanes read 32 different banks
+#pragma unroll 8
+        for (int o = 0; o < 32; ++o) {
+            const int oo = (o + lane) & 31;
+            const double rr = rv[oo];
+#pragma unroll
+            for (int g = 0; g < NT_GC; ++g) {
+                const int c = lane + 32 * g;
+                if (c < NT_COLS)
+                    gacc[g] = fma(tile[c * NT_LDT + oo], rr, gacc[g]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const NlsPassParams prm)
+{
+    extern __shared__ double nt_smem[];
+    const int cand = blockIdx.y;
+    const double *req = prm.req + (size_t)cand * prm.req_stride;
+    unsigned long long seq;
+    const int mode = nls_begin(prm, req, seq);
+    if (mode == NLS_MODE_IDLE)
+        return;
+
+    NlsThread T;
+#if NT_NEED_T
+    nls_load_request(prm, req, T);
+#endif
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // shared memory: per-warp tile [NT_COLS][NT_LDT] + rv[32]; the CTA packet [NLS_PK]; theta, v and
+    // the model's launch invariants
+    double *tile = nt_smem + (size_t)warp * (NT_COLS * NT_LDT + 32);
+    double *rv = tile + NT_COLS * NT_LDT;
+    double *pk = nt_smem + (size_t)NLS_NW * (NT_COLS * NT_LDT + 32);
+    double *s_th = pk + NLS_PK, *s_vv = s_th + NLS_P, *s_cfj = s_vv + NLS_P, *s_cfvv = s_cfj + NT_NC_FJ;
+    for (int e = lane; e < NT_COLS * NT_LDT; e += 32)
+        tile[e] = 0.0; // padding columns stay zero for the whole launch
+    for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK)
+        pk[e] = 0.0;
+    for (int j = threadIdx.x; j < NLS_P; j += NLS_BLOCK) {
+        s_th[j] = __ldcg(req + 1 + j);
+        s_vv[j] = __ldcg(req + 1 + NLS_P + j);
+    }
+    __syncthreads();
+#if GSLNLS_JAC_MODE == 0
+    if (threadIdx.x == 0)
+        nls_model_prep_fj(s_th, s_cfj);
+#endif
+#if GSLNLS_FVV_MODE == 1
+    if (threadIdx.x == NLS_BLOCK - 1 && mode == NLS_MODE_FVV)
+        nls_model_prep_fvv(s_th, s_vv, s_cfvv);
+#endif
+    __syncthreads();
+    NtShared S;
+    S.th = s_th; S.vv = s_vv; S.c_fj = s_cfj; S.c_fvv = s_cfvv;
+
+    double C[NT_TILES][2];
+#pragma unroll
+    for (int t = 0; t < NT_TILES; ++t)
+        C[t][0] = C[t][1] = 0.0;
+    double gacc[NT_GC];
+#pragma unroll
+    for (int g = 0; g < NT_GC; ++g)
+        gacc[g] = 0.0;
+    double ss = 0.0, nbad = 0.0;
+
+    if (mode == NLS_MODE_FJ)
+        nt_stream<NLS_MODE_FJ>(prm, T, S, tile, rv, C, gacc, ss, nbad);
+    else if (mode == NLS_MODE_FVV)
+        nt_stream<NLS_MODE_FVV>(prm, T, S, tile, rv, C, gacc, ss, nbad);
+    else
+        nt_stream<NLS_MODE_JVP>(prm, T, S, tile, rv, C, gacc, ss, nbad);
+
+    // ---- CTA reduction: warps add their fragments into the shared packet in warp order ----
+    ss += __shfl_down_sync(0xffffffffu, ss, 16);
+    ss += __shfl_down_sync(0xffffffffu, ss, 8);
+    ss += __shfl_down_sync(0xffffffffu, ss, 4);
+    ss += __shfl_down_sync(0xffffffffu, ss, 2);
+    ss += __shfl_down_sync(0xffffffffu, ss, 1);
+    nbad += __shfl_down_sync(0xffffffffu, nbad, 16);
+    nbad += __shfl_down_sync(0xffffffffu, nbad, 8);
+    nbad += __shfl_down_sync(0xffffffffu, nbad, 4);
+    nbad += __shfl_down_sync(0xffffffffu, nbad, 2);
+    nbad += __shfl_down_sync(0xffffffffu, nbad, 1);
+    const int fr = lane >> 2, fc2 = (lane & 3) * 2;
+    for (int w = 0; w < NLS_NW; ++w) {
+        if (warp == w) {
+            if (mode == NLS_MODE_FJ) {
+                // packet: [J^T J lower packed row-major | J^T f | f^T f | #non-finite]
+                int t = 0;
+#pragma unroll
+                for (int bi = 0; bi < NT_PB; ++bi)
+#pragma unroll
+                    for (int bj = 0; bj <= bi; ++bj, ++t) {
+                        const int row = bi * 8 + fr;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int col = bj * 8 + fc2 + h;
+                            if (row < NLS_P && col <= row)
+                                pk[row * (row + 1) / 2 + col] += C[t][h];
+                        }
+                    }
+#pragma unroll
+                for (int g = 0; g < NT_GC; ++g) {
+                    const int c = lane + 32 * g;
+                    if (c < NLS_P)
+                        pk[NLS_NPK + c] += gacc[g];
+                }
+                if (lane == 0) {
+                    pk[NLS_NPK + NLS_P] += ss;
+                    pk[NLS_NPK + NLS_P + 1] += nbad;
+                }
+            } else {
+                // FVV / JVP packet: [J^T h (p) | h^T h]
+#pragma unroll
+                for (int g = 0; g < NT_GC; ++g) {
+                    const int c = lane + 32 * g;
+                    if (c < NLS_P)
+                        pk[c] += gacc[g];
+                }
+                if (lane == 0)
+                    pk[NLS_P] += ss;
+            }
+        }
+        __syncthreads();
+    }
+    double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
+    for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK)
+        part[e] = pk[e];
+    nls_grid_finish(prm, cand, seq);
+}

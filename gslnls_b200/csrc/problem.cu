@@ -111,7 +111,7 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
     if ((reinterpret_cast<uintptr_t>(pb->dy) & 15u) || (pb->dw && (reinterpret_cast<uintptr_t>(pb->dw) & 15u)))
         vec = 1;
     const KernelTune t = default_tune(pb->p);
-    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb};
+    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb, batch ? 0 : t.tiled};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;
     try {
@@ -122,7 +122,7 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
     }
     pb->vkey = key;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)pb->var->pass, key.block, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)pb->var->pass, key.block, pb->var->pass_smem));
     pb->occ = std::max(occ, 1);
     return GSLNLS_SUCCESS;
 }
@@ -130,8 +130,14 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
 // grid size along x for one candidate
 static int pick_grid(const gslnls_problem *pb, int ncand, bool reserve_slot = false)
 {
-    const int64_t nv = pb->vkey.vec == 2 ? pb->n / 2 : pb->n;
-    const int64_t need = std::max<int64_t>(1, (nv + pb->vkey.block - 1) / pb->vkey.block);
+    int64_t need;
+    if (pb->vkey.tiled) { // a warp takes slabs of 32 observations
+        const int64_t nslab = (pb->n + 31) / 32, nw = pb->vkey.block / 32;
+        need = std::max<int64_t>(1, (nslab + nw - 1) / nw);
+    } else {
+        const int64_t nv = pb->vkey.vec == 2 ? pb->n / 2 : pb->n;
+        need = std::max<int64_t>(1, (nv + pb->vkey.block - 1) / pb->vkey.block);
+    }
     int64_t full = (int64_t)pb->num_sms * pb->occ;
     if (ncand > 1) // candidates fill the machine together
         full = std::max<int64_t>(1, full / std::min<int64_t>(ncand, full));
@@ -209,8 +215,8 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     void *args[] = {&prm};
     if (timed)
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
-    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args, 0,
-                        pb->stream));
+    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
+                        pb->var->pass_smem, pb->stream));
     if (timed) {
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
         pb->prof_used += 2;
