@@ -537,7 +537,7 @@ static std::string lit(double v)
 static const char *fn_name(int fid)
 {
     switch (fid) {
-    case F_EXP: return "exp";
+    case F_EXP: return "NLS_EXP";
     case F_LOG: return "log";
     case F_LOG2: return "log2";
     case F_LOG10: return "log10";

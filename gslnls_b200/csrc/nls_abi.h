@@ -41,7 +41,12 @@ struct NlsPassParams {
     int rank;
     int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
+    // two-level grid reduction (single-candidate launches): CTAs in groups of NLS_RED_GROUP, the last
+    // arriver of a group sums the group's partials, the last group sums the group sums
+    double *group_partials;           // [ceil(gridDim.x / NLS_RED_GROUP)][pk_stride] or nullptr (flat reduction)
+    unsigned int *group_ticket;       // [ceil(gridDim.x / NLS_RED_GROUP)] arrival counters (zero between launches)
 };
+#define NLS_RED_GROUP 32
 
 struct NlsMaterialiseParams {
     const double *vars[NLS_MAX_VARS];

@@ -16,6 +16,79 @@ using std::erfc;
 #define NLS_NAN (NAN)
 #endif
 
+// exp() of the generated models.  The pass kernels are co-limited by the FP64 pipe (DMMA included: on
+// B200 the tensor-core FP64 path issues to the same units), and CUDA's exp() is 16 of the 33 FP64
+// instructions per observation of the 3-parameter exponential model.  nls_exp() spends 10: k =
+// rint(x 64/ln2), r = x - k ln2/64 (two FMAs), a degree-5 polynomial on |r| <= ln2/128 and one
+// table entry 2^(j/64) from shared memory, the power of two added to the exponent field by the
+// integer pipe.  Maximum error 1.24 ulp over |x| <= 700 (checked against mpmath); larger |x|,
+// infinities and NaN take the library exp().
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__device__ const unsigned long long nls_exp_tab_bits[64] = {
+    0x3ff0000000000000ULL, 0x3ff02c9a3e778061ULL, 0x3ff059b0d3158574ULL, 0x3ff0874518759bc8ULL,
+    0x3ff0b5586cf9890fULL, 0x3ff0e3ec32d3d1a2ULL, 0x3ff11301d0125b51ULL, 0x3ff1429aaea92de0ULL,
+    0x3ff172b83c7d517bULL, 0x3ff1a35beb6fcb75ULL, 0x3ff1d4873168b9aaULL, 0x3ff2063b88628cd6ULL,
+    0x3ff2387a6e756238ULL, 0x3ff26b4565e27cddULL, 0x3ff29e9df51fdee1ULL, 0x3ff2d285a6e4030bULL,
+    0x3ff306fe0a31b715ULL, 0x3ff33c08b26416ffULL, 0x3ff371a7373aa9cbULL, 0x3ff3a7db34e59ff7ULL,
+    0x3ff3dea64c123422ULL, 0x3ff4160a21f72e2aULL, 0x3ff44e086061892dULL, 0x3ff486a2b5c13cd0ULL,
+    0x3ff4bfdad5362a27ULL, 0x3ff4f9b2769d2ca7ULL, 0x3ff5342b569d4f82ULL, 0x3ff56f4736b527daULL,
+    0x3ff5ab07dd485429ULL, 0x3ff5e76f15ad2148ULL, 0x3ff6247eb03a5585ULL, 0x3ff6623882552225ULL,
+    0x3ff6a09e667f3bcdULL, 0x3ff6dfb23c651a2fULL, 0x3ff71f75e8ec5f74ULL, 0x3ff75feb564267c9ULL,
+    0x3ff7a11473eb0187ULL, 0x3ff7e2f336cf4e62ULL, 0x3ff82589994cce13ULL, 0x3ff868d99b4492edULL,
+    0x3ff8ace5422aa0dbULL, 0x3ff8f1ae99157736ULL, 0x3ff93737b0cdc5e5ULL, 0x3ff97d829fde4e50ULL,
+    0x3ff9c49182a3f090ULL, 0x3ffa0c667b5de565ULL, 0x3ffa5503b23e255dULL, 0x3ffa9e6b5579fdbfULL,
+    0x3ffae89f995ad3adULL, 0x3ffb33a2b84f15fbULL, 0x3ffb7f76f2fb5e47ULL, 0x3ffbcc1e904bc1d2ULL,
+    0x3ffc199bdd85529cULL, 0x3ffc67f12e57d14bULL, 0x3ffcb720dcef9069ULL, 0x3ffd072d4a07897cULL,
+    0x3ffd5818dcfba487ULL, 0x3ffda9e603db3285ULL, 0x3ffdfc97337b9b5fULL, 0x3ffe502ee78b3ff6ULL,
+    0x3ffea4afa2a490daULL, 0x3ffefa1bee615a27ULL, 0x3fff50765b6e4540ULL, 0x3fffa7c1819e90d8ULL,
+};
+static __device__ __forceinline__ double *nls_exp_tab()
+{
+    __shared__ double tab[64];
+    return tab;
+}
+// every kernel that evaluates a model calls this once, with all threads of the CTA
+static __device__ __forceinline__ void nls_exp_init()
+{
+#if defined(NLS_FAST_EXP) && NLS_FAST_EXP
+    for (int i = threadIdx.x; i < 64; i += blockDim.x)
+        nls_exp_tab()[i] = __longlong_as_double((long long)nls_exp_tab_bits[i]);
+    __syncthreads();
+#endif
+}
+NLS_FN double nls_exp(double x)
+{
+    if (!(fabs(x) <= 700.0))
+        return exp(x);
+    const double t = fma(x, 92.33248261689366, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -0.010830424696249145, x);
+    r = fma(kf, -3.623510646634843e-19, r);
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    const double r2 = r * r;
+    const double pr = fma(q, r2, r);
+    const double T = nls_exp_tab()[k & 63];
+    const double res = fma(T, pr, T);
+    return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+}
+#else
+NLS_FN double nls_exp(double x) { return exp(x); }
+#endif
+// Measured on B200 (round 1): the branch to the library path splits the 8-observation basic block of
+// the pass kernel and costs more than the six FP64 instructions save (n = 1e8 pass 319 us vs 288 us),
+// so the generated code uses the library exp() unless NLS_FAST_EXP=1 is passed to NVRTC.
+#ifndef NLS_FAST_EXP
+#define NLS_FAST_EXP 0
+#endif
+#if NLS_FAST_EXP
+#define NLS_EXP(x) nls_exp(x)
+#else
+#define NLS_EXP(x) exp(x)
+#endif
+
 // x^n for a literal integer n: repeated squaring, unrolled at compile time once n is known
 NLS_FN double nls_powi(double a, int n)
 {

@@ -340,10 +340,16 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 
 // Start of a launch: in server mode wait for this pass's request; returns the mode to run
 // (NLS_MODE_IDLE: leave) and the pass sequence number.  Uniform across the CTA.
-static __device__ __forceinline__ int nls_begin(const NlsPassParams &prm, const double *req, unsigned long long &seq)
+// the pass sequence number lives in shared memory, not in a register across the streaming loop
+static __device__ __forceinline__ unsigned long long *nls_seq_slot()
 {
     __shared__ unsigned long long s_seq;
-    seq = 0ull;
+    return &s_seq;
+}
+
+static __device__ __forceinline__ int nls_begin(const NlsPassParams &prm, const double *req)
+{
+    unsigned long long &s_seq = *nls_seq_slot();
     if (prm.channel) {
         // server mode: this launch is pass number k = (passes completed so far) + 1; its request is
         // published by the resident trust-region warp (trs_server) as soon as it has digested
@@ -368,8 +374,7 @@ static __device__ __forceinline__ int nls_begin(const NlsPassParams &prm, const 
                 *(unsigned long long *)(prm.channel + NLS_CH_TIMER) = nls_globaltimer();
         }
         __syncthreads();
-        seq = s_seq;
-        if (seq == 0ull)
+        if (s_seq == 0ull)
             return NLS_MODE_IDLE;
     }
     const int mode = prm.force_mode > 0 ? prm.force_mode : (int)__ldcg(req);
@@ -393,45 +398,21 @@ static __device__ __forceinline__ void nls_load_request(const NlsPassParams &prm
     T.h_fvv = prm.h_fvv;
 }
 
-// End of a launch, after this CTA's partial packet (NLS_PK doubles) has been written to
-// prm.partials: the last CTA to arrive sums the CTA partials in CTA order (no FP atomics) and
-// hands the packet on -- to prm.packet (launch-ordered mode) or into every rank's mailbox.
-static __device__ __forceinline__ void nls_grid_finish(const NlsPassParams &prm, int cand, unsigned long long seq)
+// hand the reduced packet on: prm.packet (launch-ordered mode) or slot [seq parity][this rank] of
+// every rank's mailbox (server mode; peer memory over NVLink), then publish
+static __device__ __forceinline__ void nls_packet_out(const NlsPassParams &prm, int cand, unsigned long long seq,
+                                                      int e, double s)
 {
-    __shared__ int s_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(prm.ticket + cand, 1u);
-        s_last = (t == gridDim.x - 1);
+    if (prm.channel) {
+        const size_t slot = ((size_t)(seq & 1ull) * NLS_MAX_RANKS + (size_t)prm.rank) * NLS_CH_MAXPK;
+        for (int q = 0; q < prm.nranks; ++q)
+            ((double *)(prm.peer_channel[q] + NLS_CH_DATA))[slot + e] = s;
+    } else {
+        prm.packet[(size_t)cand * prm.pk_stride + e] = s;
     }
-    __syncthreads();
-    if (!s_last)
-        return;
-    __threadfence();
-    const double *parts = prm.partials + (size_t)cand * gridDim.x * prm.pk_stride;
-    double *out = prm.packet + (size_t)cand * prm.pk_stride;
-    // server mode: slot [seq parity][this rank] of every rank's mailbox (peer memory over NVLink)
-    const size_t slot = ((size_t)(seq & 1ull) * NLS_MAX_RANKS + (size_t)prm.rank) * NLS_CH_MAXPK;
-    for (int e = warp; e < NLS_PK; e += NLS_NW) {
-        double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32)
-            s += __ldcg(parts + (size_t)b * prm.pk_stride + e);
-        s += __shfl_down_sync(0xffffffffu, s, 16);
-        s += __shfl_down_sync(0xffffffffu, s, 8);
-        s += __shfl_down_sync(0xffffffffu, s, 4);
-        s += __shfl_down_sync(0xffffffffu, s, 2);
-        s += __shfl_down_sync(0xffffffffu, s, 1);
-        if (lane == 0) {
-            if (prm.channel) {
-                for (int q = 0; q < prm.nranks; ++q)
-                    ((double *)(prm.peer_channel[q] + NLS_CH_DATA))[slot + e] = s;
-            } else {
-                out[e] = s;
-            }
-        }
-    }
+}
+static __device__ __forceinline__ void nls_packet_publish(const NlsPassParams &prm, int cand, unsigned long long seq)
+{
     if (prm.channel) {
         if (prm.nranks > 1)
             __threadfence_system();
@@ -458,6 +439,84 @@ static __device__ __forceinline__ void nls_grid_finish(const NlsPassParams &prm,
         prm.ticket[cand] = 0u; // ready for the next launch
 }
 
+// End of a launch, after this CTA's partial packet (NLS_PK doubles) has been written to
+// prm.partials.  No floating-point atomics anywhere: partials are summed in CTA order, by whichever
+// CTA happens to arrive last, so the packet is bit-identical from run to run.
+//   flat (multi-candidate launches): the last CTA of a candidate sums all its CTA partials
+//   two-level (single candidate):    the last CTA of each group of NLS_RED_GROUP sums the group,
+//                                    the last group to finish sums the group sums; every thread
+//                                    owns packet entries, so a 1226-entry packet (p = 48) over
+//                                    444 CTAs costs two short, fully parallel rounds
+static __device__ __forceinline__ void nls_grid_finish(const NlsPassParams &prm, int cand)
+{
+    __shared__ int s_last;
+    const unsigned long long seq = prm.channel ? *nls_seq_slot() : 0ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __threadfence();
+    __syncthreads();
+    if (prm.group_partials) {
+        const int grp = blockIdx.x / NLS_RED_GROUP, ngrp = (gridDim.x + NLS_RED_GROUP - 1) / NLS_RED_GROUP;
+        const int b0 = grp * NLS_RED_GROUP;
+        const int gsize = min(NLS_RED_GROUP, (int)gridDim.x - b0);
+        if (threadIdx.x == 0)
+            s_last = (atomicAdd(prm.group_ticket + grp, 1u) == (unsigned)(gsize - 1));
+        __syncthreads();
+        if (!s_last)
+            return;
+        __threadfence();
+        const double *parts = prm.partials + (size_t)b0 * prm.pk_stride;
+        double *gp = prm.group_partials + (size_t)grp * prm.pk_stride;
+        for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
+            double s = 0.0;
+#pragma unroll 8
+            for (int b = 0; b < gsize; ++b)
+                s += __ldcg(parts + (size_t)b * prm.pk_stride + e);
+            gp[e] = s;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            prm.group_ticket[grp] = 0u;
+            s_last = (atomicAdd(prm.ticket + cand, 1u) == (unsigned)(ngrp - 1));
+        }
+        __syncthreads();
+        if (!s_last)
+            return;
+        __threadfence();
+        for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
+            double s = 0.0;
+#pragma unroll 4
+            for (int g = 0; g < ngrp; ++g)
+                s += __ldcg(prm.group_partials + (size_t)g * prm.pk_stride + e);
+            nls_packet_out(prm, cand, seq, e, s);
+        }
+        nls_packet_publish(prm, cand, seq);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(prm.ticket + cand, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    const double *parts = prm.partials + (size_t)cand * gridDim.x * prm.pk_stride;
+    for (int e = warp; e < NLS_PK; e += NLS_NW) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32)
+            s += __ldcg(parts + (size_t)b * prm.pk_stride + e);
+        s += __shfl_down_sync(0xffffffffu, s, 16);
+        s += __shfl_down_sync(0xffffffffu, s, 8);
+        s += __shfl_down_sync(0xffffffffu, s, 4);
+        s += __shfl_down_sync(0xffffffffu, s, 2);
+        s += __shfl_down_sync(0xffffffffu, s, 1);
+        if (lane == 0)
+            nls_packet_out(prm, cand, seq, e, s);
+    }
+    nls_packet_publish(prm, cand, seq);
+}
+
 #if NLS_TILED
 #include "nls_pass_tiled.cuh"
 #else
@@ -466,10 +525,10 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
 {
     const int cand = blockIdx.y;
     const double *req = prm.req + (size_t)cand * prm.req_stride;
-    unsigned long long seq;
-    const int mode = nls_begin(prm, req, seq);
+    const int mode = nls_begin(prm, req);
     if (mode == NLS_MODE_IDLE)
         return; // this candidate has finished; uniform for the whole CTA
+    nls_exp_init();
 
     NlsThread T;
     nls_load_request(prm, req, T);
@@ -509,7 +568,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
             s += sred[w][e];
         part[e] = s;
     }
-    nls_grid_finish(prm, cand, seq);
+    nls_grid_finish(prm, cand);
 }
 #endif // NLS_TILED
 
@@ -518,6 +577,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
 // the arrays C_nls_large returns at src/nls_large.c:339-385, produced once, after the fit.
 extern "C" __global__ void __launch_bounds__(256) nls_materialise(const NlsMaterialiseParams prm)
 {
+    nls_exp_init();
     NlsThread T;
 #pragma unroll
     for (int j = 0; j < NLS_P; ++j) {

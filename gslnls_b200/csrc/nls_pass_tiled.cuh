@@ -12,7 +12,8 @@
 //            B-fragments of a parameter block are the same register, so a k-step costs
 //            ceil(p/8) shared loads for T = PB(PB+1)/2 DMMAs; the T accumulator fragments stay
 //            in registers for the whole launch (42 doubles per lane at p = 48).
-//            J^T r (or J^T fvv, J^T (J d)) is a plain FMA column dot over the same tile.
+//            J^T r (or J^T fvv, J^T (J d)) reuses the fragment registers: one FMA per block and
+//            k-step into per-lane partial sums, folded across the four fragment columns at the end.
 //
 // Replaces for large p what nls_pass does for small p: gsl_df_large's dsyrk/dgemv
 // (src/nls_large.c:629,633) without ever forming the n x p matrix J (src/nls_large.c:167).
@@ -28,7 +29,7 @@
                                             column stores (32 consecutive doubles) and the 4x8
                                             fragment loads hit 16 distinct 8-byte banks per half-warp */
 #define NT_TILES (NT_PB * (NT_PB + 1) / 2)
-#define NT_GC ((NT_COLS + 31) / 32)      /* column-dot accumulators per lane                */
+#define NT_GC NT_PB                      /* column-dot partial sums per lane (one per block)  */
 
 #if NT_TILES > 28
 #error "nls_pass_tiled: p > 56 needs the tile set split across warps (not built yet)"
@@ -89,25 +90,52 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
     const long long nslab = (n + 31) >> 5;
     const long long wstride = (long long)gridDim.x * NLS_NW;
     const int fr = lane >> 2, fc = lane & 3; // fragment coordinates of this lane
-    for (long long slab = (long long)blockIdx.x * NLS_NW + warp; slab < nslab; slab += wstride) {
+    // software prefetch: the predictor / response / weight of the next slab are requested before this
+    // slab's arithmetic starts, so their DRAM latency hides behind ~4000 FP64-pipe cycles
+    long long slab = (long long)blockIdx.x * NLS_NW + warp;
+    double nx[NLS_NV], ny = 0.0, nw = 1.0;
+    {
+        const long long i0 = (slab << 5) + lane;
+        const long long ii0 = (slab < nslab && i0 < n) ? i0 : 0;
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            nx[k] = nls_ld1(prm.vars[k] + ii0);
+        ny = nls_ld1(prm.y + ii0);
+#if NLS_HAS_W
+        nw = nls_ld1(prm.w + ii0);
+#endif
+    }
+    for (; slab < nslab; slab += wstride) {
         // ---------------- phase A: one observation per lane ----------------
         const long long i = (slab << 5) + lane;
         const bool valid = i < n;
-        const long long ii = valid ? i : 0;
         double xa[NLS_NV];
 #pragma unroll
         for (int k = 0; k < GSLNLS_NVAR; ++k)
-            xa[k] = nls_ld1(prm.vars[k] + ii);
-        const double y = nls_ld1(prm.y + ii);
+            xa[k] = nx[k];
+        const double y = ny;
 #if NLS_HAS_W
-        const double sw = sqrt(nls_ld1(prm.w + ii)); // sqrt_wts_i = sqrt(w_i), src/fdf.c:60-64
+        const double sw = sqrt(nw); // sqrt_wts_i = sqrt(w_i), src/fdf.c:60-64
 #else
         const double sw = 1.0;
 #endif
+        {
+            const long long in = ((slab + wstride) << 5) + lane;
+            const long long iin = (slab + wstride < nslab && in < n) ? in : 0;
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k)
+                nx[k] = nls_ld1(prm.vars[k] + iin);
+            ny = nls_ld1(prm.y + iin);
+#if NLS_HAS_W
+            nw = nls_ld1(prm.w + iin);
+#endif
+        }
         // sqrt(w) scaling folded into the tile store; invalid (padding) lanes store zeros
         const double swv = valid ? sw : 0.0;
         double f, u = 0.0;
-#if GSLNLS_JAC_MODE == 0
+#if defined(NT_DEBUG_SKIP_A)
+        f = xa[0]; // timing experiment: no model evaluation, tile keeps its initial contents
+#elif GSLNLS_JAC_MODE == 0
         if (MODE == NLS_MODE_JVP || (MODE == NLS_MODE_FVV && GSLNLS_FVV_MODE == 2)) {
             NtRowSink sink{tile + lane, S.vv, swv, 0.0};
             nls_model_fj_c(S.th, S.c_fj, xa, f, sink);
@@ -161,13 +189,18 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
         __syncwarp();
 
         // ---------------- phase B: tile^T tile on the FP64 tensor path ----------------
-        if (MODE == NLS_MODE_FJ) {
+        // k-step ks covers observations 4 ks .. 4 ks + 3; this lane's fragment element of block b is
+        // J[observation 4 ks + fc][column 8 b + fr].  The same registers feed the column dot with r
+        // (J^T r, or J^T fvv / J^T (J d)): a partial sum per lane, folded over fc once per launch.
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                double frag[NT_PB];
+        for (int ks = 0; ks < 8; ++ks) {
+            double frag[NT_PB];
 #pragma unroll
-                for (int b = 0; b < NT_PB; ++b)
-                    frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+            for (int b = 0; b < NT_PB; ++b)
+                frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+            const double rk = rv[ks * 4 + fc];
+#if !defined(NT_DEBUG_SKIP_B)
+            if (MODE == NLS_MODE_FJ) {
                 int t = 0;
 #pragma unroll
                 for (int bi = 0; bi < NT_PB; ++bi)
@@ -175,19 +208,10 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
                     for (int bj = 0; bj <= bi; ++bj, ++t)
                         nt_dmma(C[t][0], C[t][1], frag[bi], frag[bj]);
             }
-        }
-        // column dot with r: lane owns columns lane, lane+32, ...; the observation index is rotated by
-        // the lane so that the 32 lanes read 32 different banks
-#pragma unroll 8
-        for (int o = 0; o < 32; ++o) {
-            const int oo = (o + lane) & 31;
-            const double rr = rv[oo];
+#endif
 #pragma unroll
-            for (int g = 0; g < NT_GC; ++g) {
-                const int c = lane + 32 * g;
-                if (c < NT_COLS)
-                    gacc[g] = fma(tile[c * NT_LDT + oo], rr, gacc[g]);
-            }
+            for (int b = 0; b < NT_PB; ++b)
+                gacc[b] = fma(frag[b], rk, gacc[b]);
         }
         __syncwarp();
     }
@@ -198,10 +222,10 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     extern __shared__ double nt_smem[];
     const int cand = blockIdx.y;
     const double *req = prm.req + (size_t)cand * prm.req_stride;
-    unsigned long long seq;
-    const int mode = nls_begin(prm, req, seq);
+    const int mode = nls_begin(prm, req);
     if (mode == NLS_MODE_IDLE)
         return;
+    nls_exp_init();
 
     NlsThread T;
 #if NT_NEED_T
@@ -265,6 +289,13 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     nbad += __shfl_down_sync(0xffffffffu, nbad, 2);
     nbad += __shfl_down_sync(0xffffffffu, nbad, 1);
     const int fr = lane >> 2, fc2 = (lane & 3) * 2;
+    // column dots: fold the four fc-lanes of each fragment row (fixed xor tree); lanes with fc == 0 own
+    // column 8 b + fr afterwards
+#pragma unroll
+    for (int b = 0; b < NT_PB; ++b) {
+        gacc[b] += __shfl_xor_sync(0xffffffffu, gacc[b], 1);
+        gacc[b] += __shfl_xor_sync(0xffffffffu, gacc[b], 2);
+    }
     for (int w = 0; w < NLS_NW; ++w) {
         if (warp == w) {
             if (mode == NLS_MODE_FJ) {
@@ -283,10 +314,10 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
                         }
                     }
 #pragma unroll
-                for (int g = 0; g < NT_GC; ++g) {
-                    const int c = lane + 32 * g;
-                    if (c < NLS_P)
-                        pk[NLS_NPK + c] += gacc[g];
+                for (int b = 0; b < NT_PB; ++b) {
+                    const int c = b * 8 + fr;
+                    if ((lane & 3) == 0 && c < NLS_P)
+                        pk[NLS_NPK + c] += gacc[b];
                 }
                 if (lane == 0) {
                     pk[NLS_NPK + NLS_P] += ss;
@@ -295,10 +326,10 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
             } else {
                 // FVV / JVP packet: [J^T h (p) | h^T h]
 #pragma unroll
-                for (int g = 0; g < NT_GC; ++g) {
-                    const int c = lane + 32 * g;
-                    if (c < NLS_P)
-                        pk[c] += gacc[g];
+                for (int b = 0; b < NT_PB; ++b) {
+                    const int c = b * 8 + fr;
+                    if ((lane & 3) == 0 && c < NLS_P)
+                        pk[c] += gacc[b];
                 }
                 if (lane == 0)
                     pk[NLS_P] += ss;
@@ -309,5 +340,5 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
     for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK)
         part[e] = pk[e];
-    nls_grid_finish(prm, cand, seq);
+    nls_grid_finish(prm, cand);
 }

@@ -61,6 +61,8 @@ struct gslnls_problem {
     // workspace (sized for cap candidates)
     int cap = 0, cap_grid = 0, cap_trace = 0;
     int req_stride = 0, pk_stride = 0, state_stride = 0;
+    double *d_gparts = nullptr;
+    unsigned *d_gticket = nullptr;
     double *d_req = nullptr, *d_partials = nullptr, *d_packet = nullptr, *d_state = nullptr, *d_starts = nullptr;
     double *d_partrace = nullptr, *d_ssrtrace = nullptr, *d_condtrace = nullptr, *d_theta = nullptr;
     unsigned *d_ticket = nullptr;
@@ -97,6 +99,8 @@ static void free_workspace(gslnls_problem *pb)
 {
     cudaFree(pb->d_req); cudaFree(pb->d_partials); cudaFree(pb->d_packet); cudaFree(pb->d_state);
     cudaFree(pb->d_starts); cudaFree(pb->d_ticket); cudaFree(pb->d_ndone);
+    cudaFree(pb->d_gparts); cudaFree(pb->d_gticket);
+    pb->d_gparts = nullptr; pb->d_gticket = nullptr;
     pb->d_req = pb->d_partials = pb->d_packet = pb->d_state = pb->d_starts = nullptr;
     pb->d_ticket = nullptr; pb->d_ndone = nullptr;
     pb->cap = 0;
@@ -162,6 +166,10 @@ static int ensure_workspace(gslnls_problem *pb, int ncand, int grid_x, int ntrac
         CK(cudaMalloc(&pb->d_starts, sizeof(double) * c * p));
         CK(cudaMalloc(&pb->d_ticket, sizeof(unsigned) * c));
         CK(cudaMalloc(&pb->d_ndone, sizeof(int)));
+        const size_t ngrp = ((size_t)grid_x + NLS_RED_GROUP - 1) / NLS_RED_GROUP;
+        CK(cudaMalloc(&pb->d_gparts, sizeof(double) * ngrp * pb->pk_stride));
+        CK(cudaMalloc(&pb->d_gticket, sizeof(unsigned) * ngrp));
+        CK(cudaMemsetAsync(pb->d_gticket, 0, sizeof(unsigned) * ngrp, pb->stream));
         CK(cudaMemsetAsync(pb->d_ticket, 0, sizeof(unsigned) * c, pb->stream));
         CK(cudaMemsetAsync(pb->d_packet, 0, sizeof(double) * c * pb->pk_stride, pb->stream));
         CK(cudaMemsetAsync(pb->d_req, 0, sizeof(double) * c * pb->req_stride, pb->stream));
@@ -198,6 +206,12 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.req_stride = pb->req_stride;
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
+    static const bool flat_red = std::getenv("GSLNLS_FLAT_RED") != nullptr; // developer aid
+    // two-level grid reduction for long packets (p > 8); a short packet is summed faster by one CTA
+    if (ncand == 1 && pb->grid_x > NLS_RED_GROUP && pb->pk_stride >= 48 && !flat_red) {
+        prm.group_partials = pb->d_gparts;
+        prm.group_ticket = pb->d_gticket;
+    }
     prm.nranks = 1;
     if (pb->server_on) {
         prm.channel = channel_of(pb);

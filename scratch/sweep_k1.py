@@ -1,7 +1,7 @@
 """scratch: K1 pass time vs n and tune (launch-ordered back-to-back passes)"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.environ.get("PYTHONPATH", os.path.dirname(os.path.dirname(os.path.abspath(__file__)))).split(":")[0])
 import torch
 from gslnls_b200 import Model, Problem
 
