@@ -52,6 +52,6 @@ struct gslnls_model {
 
 namespace gslnls {
 KernelTune default_tune(int p);
-size_t tiled_smem_bytes(int p, int block, int nconst); // dynamic shared memory of the tiled pass kernel
+size_t tiled_smem_bytes(int p, int block, int nprod, int nconst); // dynamic shared memory of the tiled pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture
 } // namespace gslnls

@@ -23,6 +23,9 @@ using std::erfc;
 // table entry 2^(j/64) from shared memory, the power of two added to the exponent field by the
 // integer pipe.  Maximum error 1.24 ulp over |x| <= 700 (checked against mpmath); larger |x|,
 // infinities and NaN take the library exp().
+#ifndef NLS_FAST_EXP
+#define NLS_FAST_EXP 0
+#endif
 #if defined(__CUDACC__) || defined(__CUDACC_RTC__)
 __device__ const unsigned long long nls_exp_tab_bits[64] = {
     0x3ff0000000000000ULL, 0x3ff02c9a3e778061ULL, 0x3ff059b0d3158574ULL, 0x3ff0874518759bc8ULL,
@@ -50,16 +53,53 @@ static __device__ __forceinline__ double *nls_exp_tab()
 // every kernel that evaluates a model calls this once, with all threads of the CTA
 static __device__ __forceinline__ void nls_exp_init()
 {
-#if defined(NLS_FAST_EXP) && NLS_FAST_EXP
+#if NLS_FAST_EXP == 1
     for (int i = threadIdx.x; i < 64; i += blockDim.x)
         nls_exp_tab()[i] = __longlong_as_double((long long)nls_exp_tab_bits[i]);
     __syncthreads();
 #endif
 }
+static __device__ __forceinline__ int nls_selp(int a, int b, bool c)
+{
+    int r;
+    asm("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\nselp.b32 %0, %1, %2, p;\n}" : "=r"(r) : "r"(a), "r"(b), "r"((int)c));
+    return r;
+}
+// Branch-free: a branch inside exp() ends the basic block, and the instruction scheduler can then no
+// longer interleave the independent exp() chains of neighbouring observations (or of the 16 terms of
+// a Gaussian mixture), which leaves them latency-bound.  |x| >= 708, infinities and NaN are resolved
+// by integer selects on the result words: exp(x >= 708) = +Inf (the true value is finite up to
+// 709.78, but such a model value overflows the sum of squares anyway), exp(x <= -708) = 0 (true value
+// below 3.4e-308), NaN -> +Inf or NaN bit pattern with the sign cleared (non-finite either way, which
+// is all the residual rule of src/nls_large.c:464-465 looks at).
 NLS_FN double nls_exp(double x)
 {
-    if (!(fabs(x) <= 700.0))
-        return exp(x);
+    const int hi = __double2hiint(x);
+    const int ahi = hi & 0x7fffffff;
+    const bool special = ahi >= 0x40862000;                     // |x| >= 708, Inf, NaN
+    const bool to_zero = (hi < 0) && (ahi <= 0x7ff00000);       // large negative, -Inf
+#if NLS_FAST_EXP == 2
+    // polynomial only: k = rint(x / ln 2), degree-11 near-minimax polynomial on |r| <= ln2 / 2 (0.91 ulp)
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double kf = t - 6755399441055744.0;
+    double r = fma(kf, -0.6931471805599453, x);
+    r = fma(kf, -2.3190468138462996e-17, r);
+    double q = fma(2.5110049204818658e-08, r, 2.763265472252779e-07);
+    q = fma(q, r, 2.755724088722987e-06);
+    q = fma(q, r, 2.4801485441561313e-05);
+    q = fma(q, r, 0.00019841269890076403);
+    q = fma(q, r, 0.0013888888952352863);
+    q = fma(q, r, 0.008333333333319589);
+    q = fma(q, r, 0.04166666666648795);
+    q = fma(q, r, 0.1666666666666668);
+    q = fma(q, r, 0.5000000000000019);
+    q = fma(q, r, 1.0);
+    const double res = fma(q, r, 1.0);
+    const int m = k;
+#else
+    // table: k = rint(x 64 / ln 2), degree-5 polynomial on |r| <= ln2 / 128, 2^(j/64) from shared memory
+    // (1.24 ulp)
     const double t = fma(x, 92.33248261689366, 6755399441055744.0);
     const int k = __double2loint(t);
     const double kf = t - 6755399441055744.0;
@@ -72,14 +112,18 @@ NLS_FN double nls_exp(double x)
     const double pr = fma(q, r2, r);
     const double T = nls_exp_tab()[k & 63];
     const double res = fma(T, pr, T);
-    return __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+    const int m = k >> 6;
+#endif
+    // opaque selects: written as a C conditional the compiler would branch around the arithmetic above
+    const int shi = to_zero ? 0 : (ahi > 0x7ff00000 ? ahi : 0x7ff00000);
+    const int ohi = nls_selp(shi, __double2hiint(res) + (m << 20), special);
+    const int olo = nls_selp(0, __double2loint(res), special);
+    return __hiloint2double(ohi, olo);
 }
 #else
 NLS_FN double nls_exp(double x) { return exp(x); }
 #endif
-// Measured on B200 (round 1): the branch to the library path splits the 8-observation basic block of
-// the pass kernel and costs more than the six FP64 instructions save (n = 1e8 pass 319 us vs 288 us),
-// so the generated code uses the library exp() unless NLS_FAST_EXP=1 is passed to NVRTC.
+// NLS_FAST_EXP: 0 library exp(), 1 table variant, 2 polynomial variant of nls_exp()
 #ifndef NLS_FAST_EXP
 #define NLS_FAST_EXP 0
 #endif

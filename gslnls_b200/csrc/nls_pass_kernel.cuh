@@ -151,7 +151,7 @@ static __device__ __forceinline__ void nls_fj(const NlsThread &T, const double *
 // one observation, accumulated into the thread-private packet
 template <int MODE>
 static __device__ __forceinline__ void nls_observe(const NlsThread &T, const double *x, double y, double w,
-                                                   double *acc)
+                                                   double *acc, int &nbad)
 {
     double f, J[NLS_P];
     nls_fj(T, x, f, J);
@@ -161,13 +161,13 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
     (void)w;
 #endif
     if (MODE == NLS_MODE_FJ) {
-        double r = f - y;
-        if (!nls_finite(f)) {
-            r = NLS_INF; // src/nls_large.c:464-465
-            // counted: gslcblas dnrm2 turns a vector with two or more Inf entries into NaN, which
-            // changes the reference's accept/reject decision (see trs_core.h, norm_of)
-            acc[NLS_NPK + NLS_P + 1] += 1.0;
-        }
+        // non-finite model value -> residual +Inf (src/nls_large.c:464-465), and counted: gslcblas
+        // dnrm2 turns a vector with two or more Inf entries into NaN, which changes the reference's
+        // accept/reject decision (see trs_core.h, norm_of).  Selects and an integer counter, no
+        // branch: the observations of one loop trip stay in one basic block.
+        const bool bad = !nls_finite(f);
+        double r = bad ? NLS_INF : f - y;
+        nbad += bad ? 1 : 0;
 #if NLS_HAS_W
         r *= sw;
 #pragma unroll
@@ -240,6 +240,7 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     const long long n = prm.n;
     const long long stride = (long long)gridDim.x * NLS_BLOCK;
     long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
+    int nbad = 0;
 #if NLS_VEC == 2
     const long long nv = n >> 1;
     for (; i + (NLS_UNROLL - 1) * stride < nv; i += NLS_UNROLL * stride) {
@@ -265,8 +266,8 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
                 xa[k] = xv[u][k].x;
                 xb[k] = xv[u][k].y;
             }
-            nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc);
-            nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc);
+            nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc, nbad);
+            nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc, nbad);
         }
     }
     for (; i < nv; i += stride) {
@@ -284,8 +285,8 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #else
         const double2 ww = make_double2(1.0, 1.0);
 #endif
-        nls_observe<MODE>(T, xa, yy.x, ww.x, acc);
-        nls_observe<MODE>(T, xb, yy.y, ww.y, acc);
+        nls_observe<MODE>(T, xa, yy.x, ww.x, acc, nbad);
+        nls_observe<MODE>(T, xb, yy.y, ww.y, acc, nbad);
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long o = n - 1;
@@ -298,7 +299,7 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #else
         const double ww = 1.0;
 #endif
-        nls_observe<MODE>(T, xa, nls_ld1(prm.y + o), ww, acc);
+        nls_observe<MODE>(T, xa, nls_ld1(prm.y + o), ww, acc, nbad);
     }
 #else
     for (; i + (NLS_UNROLL - 1) * stride < n; i += NLS_UNROLL * stride) {
@@ -318,7 +319,7 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
         }
 #pragma unroll
         for (int u = 0; u < NLS_UNROLL; ++u)
-            nls_observe<MODE>(T, xv[u], yv[u], wv[u], acc);
+            nls_observe<MODE>(T, xv[u], yv[u], wv[u], acc, nbad);
     }
     for (; i < n; i += stride) {
         double xa[NLS_NV];
@@ -330,9 +331,11 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #else
         const double ww = 1.0;
 #endif
-        nls_observe<MODE>(T, xa, nls_ld1(prm.y + i), ww, acc);
+        nls_observe<MODE>(T, xa, nls_ld1(prm.y + i), ww, acc, nbad);
     }
 #endif
+    if (MODE == NLS_MODE_FJ)
+        acc[NLS_NPK + NLS_P + 1] = (double)nbad;
 }
 
 // ------------------------------------------------------------------------------------ K1 head / tail

@@ -2,12 +2,18 @@
 //
 // Included by nls_pass_kernel.cuh when NLS_TILED=1 (same entry point name, same packet).  With
 // p(p+1)/2 in the hundreds the normal-equation accumulators no longer fit a thread's registers,
-// so a warp works on slabs of 32 observations:
+// so the work moves in slabs of 32 observations through shared-memory tiles, between two kinds of
+// warps of the same CTA (warp specialisation; hand-off through mbarriers, no CTA-wide barrier in
+// the streaming loop):
 //
-//   phase A  lane i evaluates residual and Jacobian row of observation i (the model is inlined,
-//            the row lives in registers) and parks the sqrt(w)-scaled row in the warp's private
-//            shared-memory tile, transposed: tile[column][observation]
-//   phase B  the warp contracts the tile with itself: 8 k-steps of 4 observations, each feeding
+//   producer warps (phase A)  lane i evaluates residual and Jacobian row of observation i (the model
+//            is inlined) and parks the sqrt(w)-scaled row in the warp's tile, transposed:
+//            tile[column][observation].  They never hold accumulators, so the row code has the
+//            registers it needs.
+//   consumer warps (phase B)  one per SM sub-partition, serving NT_NPROD producers in a fixed
+//            round-robin; they hold the T accumulator fragments for the whole launch and never
+//            evaluate the model, so nothing spills.  A consumer contracts a tile with itself: 8
+//            k-steps of 4 observations, each feeding
 //            one mma.sync.m8n8k4.f64 (DMMA) per 8x8 block pair of the lower triangle.  A- and
 //            B-fragments of a parameter block are the same register, so a k-step costs
 //            ceil(p/8) shared loads for T = PB(PB+1)/2 DMMAs; the T accumulator fragments stay
@@ -21,7 +27,11 @@
 // 37.1 TFLOP/s either way, no overlap), so the roofline of this kernel is the FP64 pipe; what the
 // tensor-core form buys is one instruction and two operand registers per 256 FMAs.
 //
-// Tunables: NLS_BLOCK threads per CTA (a multiple of 32), NLS_MINB CTAs per SM.
+// Both kinds of warp issue to the same FP64 pipe; the consumers always have independent DMMAs ready,
+// which fills the latency bubbles of the producers' dependent chains.
+//
+// Tunables: NLS_UNROLL = NT_NPROD producer warps per consumer warp, NLS_BLOCK = 32 * NT_NCONS *
+// (1 + NT_NPROD) threads per CTA, NLS_MINB CTAs per SM.
 
 #define NT_PB ((NLS_P + 7) / 8)          /* 8-wide parameter blocks                         */
 #define NT_COLS (NT_PB * 8)              /* J columns incl. zero padding                    */
@@ -31,9 +41,36 @@
 #define NT_TILES (NT_PB * (NT_PB + 1) / 2)
 #define NT_GC NT_PB                      /* column-dot partial sums per lane (one per block)  */
 
+#define NT_NPROD NLS_UNROLL
+#define NT_NCONS (NLS_NW / (1 + NT_NPROD))
+#define NT_NP (NT_NCONS * NT_NPROD)      /* producer warps (= tile buffers) per CTA           */
+#define NT_TILE_DOUBLES (NT_COLS * NT_LDT + 32)
+
 #if NT_TILES > 28
 #error "nls_pass_tiled: p > 56 needs the tile set split across warps (not built yet)"
 #endif
+
+// ---- mbarrier hand-off (shared::cta): 32 arrivals per phase, parity waits ----
+static __device__ __forceinline__ unsigned nt_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void nt_bar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nt_saddr(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void nt_bar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nt_saddr(bar)) : "memory");
+}
+static __device__ __forceinline__ void nt_bar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "NT_WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra NT_DONE_%=;\n"
+                 "bra NT_WAIT_%=;\n"
+                 "NT_DONE_%=:\n"
+                 "}" ::"r"(nt_saddr(bar)), "r"(parity) : "memory");
+}
 
 static __device__ __forceinline__ void nt_dmma(double &c0, double &c1, double a, double b)
 {
@@ -80,19 +117,19 @@ struct NtRowSinkNoDot {
     __device__ __forceinline__ void operator()(int j, double v) { col[j * NT_LDT] = v * sw; }
 };
 
+// ---------------------------------------------------------------- producer: phase A
 template <int MODE>
-static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const NlsThread &T, const NtShared &S,
-                                                 double *tile, double *rv, double (&C)[NT_TILES][2],
-                                                 double (&gacc)[NT_GC], double &ss, double &nbad)
+static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, const NlsThread &T, const NtShared &S,
+                                                  int q, double *tile, double *rv, unsigned long long *full,
+                                                  unsigned long long *empty, double &ss, double &nbad)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const long long n = prm.n;
     const long long nslab = (n + 31) >> 5;
-    const long long wstride = (long long)gridDim.x * NLS_NW;
-    const int fr = lane >> 2, fc = lane & 3; // fragment coordinates of this lane
+    const long long wstride = (long long)gridDim.x * NT_NP;
     // software prefetch: the predictor / response / weight of the next slab are requested before this
-    // slab's arithmetic starts, so their DRAM latency hides behind ~4000 FP64-pipe cycles
-    long long slab = (long long)blockIdx.x * NLS_NW + warp;
+    // slab's arithmetic starts
+    long long slab = (long long)blockIdx.x * NT_NP + q;
     double nx[NLS_NV], ny = 0.0, nw = 1.0;
     {
         const long long i0 = (slab << 5) + lane;
@@ -105,8 +142,8 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
         nw = nls_ld1(prm.w + ii0);
 #endif
     }
-    for (; slab < nslab; slab += wstride) {
-        // ---------------- phase A: one observation per lane ----------------
+    int nbad_i = 0;
+    for (unsigned r = 0; slab < nslab; slab += wstride, ++r) {
         const long long i = (slab << 5) + lane;
         const bool valid = i < n;
         double xa[NLS_NV];
@@ -130,6 +167,7 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
             nw = nls_ld1(prm.w + iin);
 #endif
         }
+        nt_bar_wait(empty, (r & 1u) ^ 1u); // the consumer is done with this tile's previous contents
         // sqrt(w) scaling folded into the tile store; invalid (padding) lanes store zeros
         const double swv = valid ? sw : 0.0;
         double f, u = 0.0;
@@ -153,18 +191,14 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
             u = fma(J[j] * swv, S.vv[j], u);
         }
 #endif
-        double r;
+        double rr;
         if (MODE == NLS_MODE_FJ) {
-            r = f - y;
-            if (!nls_finite(f)) {
-                r = NLS_INF; // src/nls_large.c:464-465
-                if (valid)
-                    nbad += 1.0;
-            }
-            r *= sw;
+            const bool bad = !nls_finite(f); // -> residual +Inf, src/nls_large.c:464-465 (selects, no branch)
+            rr = (bad ? NLS_INF : f - y) * sw;
+            nbad_i += (bad && valid) ? 1 : 0;
         } else if (MODE == NLS_MODE_FVV) {
 #if GSLNLS_FVV_MODE == 1
-            r = nls_model_fvv_c(S.th, S.vv, S.c_fvv, xa) * sw;
+            rr = nls_model_fvv_c(S.th, S.vv, S.c_fvv, xa) * sw;
 #elif GSLNLS_FVV_MODE == 2
             {
                 // fvv = (2/h) ((f(x + h v) - f(x)) / h - J v), src/fdfvv.c:47-74  (u = sqrt(w) J v here)
@@ -174,46 +208,76 @@ static __device__ __forceinline__ void nt_stream(const NlsPassParams &prm, const
                     tp[k] = T.th[k] + T.h_fvv * T.vv[k];
                 const double fp = nls_model_f(tp, xa);
                 const double hinv = 1.0 / T.h_fvv;
-                r = (2.0 * hinv) * (((fp - f) * hinv) * sw - u);
+                rr = (2.0 * hinv) * (((fp - f) * hinv) * sw - u);
             }
 #else
-            r = 0.0;
+            rr = 0.0;
 #endif
         } else { // JVP: u = (sqrt(w) J) d
-            r = u;
+            rr = u;
         }
         if (!valid)
-            r = 0.0;
-        rv[lane] = r;
-        ss = fma(r, r, ss);
-        __syncwarp();
+            rr = 0.0;
+        rv[lane] = rr;
+        ss = fma(rr, rr, ss);
+        nt_bar_arrive(full); // 32 arrivals (release): the tile and rv are complete
+    }
+    nbad = (double)nbad_i;
+}
 
-        // ---------------- phase B: tile^T tile on the FP64 tensor path ----------------
-        // k-step ks covers observations 4 ks .. 4 ks + 3; this lane's fragment element of block b is
-        // J[observation 4 ks + fc][column 8 b + fr].  The same registers feed the column dot with r
-        // (J^T r, or J^T fvv / J^T (J d)): a partial sum per lane, folded over fc once per launch.
+// ---------------------------------------------------------------- consumer: phase B
+template <int MODE>
+static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int c, double *tiles,
+                                                  unsigned long long *full, unsigned long long *empty,
+                                                  double (&C)[NT_TILES][2], double (&gacc)[NT_GC])
+{
+    const int lane = threadIdx.x & 31;
+    const long long nslab = (prm.n + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * NT_NP;
+    const int fr = lane >> 2, fc = lane & 3; // fragment coordinates of this lane
+    // producers q = c NT_NPROD + j, j = 0..NT_NPROD-1, each in its own slab sequence; the consumer
+    // takes their tiles in the fixed order (round 0: j = 0, 1, ..; round 1: ..) -- deterministic sums
+    for (unsigned r = 0;; ++r) {
+        bool any = false;
+#pragma unroll 1
+        for (int j = 0; j < NT_NPROD; ++j) {
+            const int q = c * NT_NPROD + j;
+            const long long slab = (long long)blockIdx.x * NT_NP + q + (long long)r * wstride;
+            if (slab >= nslab)
+                continue;
+            any = true;
+            const double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
+            const double *rv = tile + NT_COLS * NT_LDT;
+            nt_bar_wait(full + q, r & 1u);
+            // k-step ks covers observations 4 ks .. 4 ks + 3; this lane's fragment element of block b is
+            // J[observation 4 ks + fc][column 8 b + fr].  The same registers feed the column dot with r
+            // (J^T r, or J^T fvv / J^T (J d)): a partial sum per lane, folded over fc once per launch.
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            double frag[NT_PB];
+            for (int ks = 0; ks < 8; ++ks) {
+                double frag[NT_PB];
 #pragma unroll
-            for (int b = 0; b < NT_PB; ++b)
-                frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
-            const double rk = rv[ks * 4 + fc];
+                for (int b = 0; b < NT_PB; ++b)
+                    frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+                const double rk = rv[ks * 4 + fc];
+                if (ks == 7)
+                    nt_bar_arrive(empty + q); // every load of this tile has been issued before (release)
 #if !defined(NT_DEBUG_SKIP_B)
-            if (MODE == NLS_MODE_FJ) {
-                int t = 0;
+                if (MODE == NLS_MODE_FJ) {
+                    int t = 0;
 #pragma unroll
-                for (int bi = 0; bi < NT_PB; ++bi)
+                    for (int bi = 0; bi < NT_PB; ++bi)
 #pragma unroll
-                    for (int bj = 0; bj <= bi; ++bj, ++t)
-                        nt_dmma(C[t][0], C[t][1], frag[bi], frag[bj]);
-            }
+                        for (int bj = 0; bj <= bi; ++bj, ++t)
+                            nt_dmma(C[t][0], C[t][1], frag[bi], frag[bj]);
+                }
 #endif
 #pragma unroll
-            for (int b = 0; b < NT_PB; ++b)
-                gacc[b] = fma(frag[b], rk, gacc[b]);
+                for (int b = 0; b < NT_PB; ++b)
+                    gacc[b] = fma(frag[b], rk, gacc[b]);
+            }
         }
-        __syncwarp();
+        if (!any)
+            break;
     }
 }
 
@@ -233,19 +297,23 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
 #endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // shared memory: per-warp tile [NT_COLS][NT_LDT] + rv[32]; the CTA packet [NLS_PK]; theta, v and
-    // the model's launch invariants
-    double *tile = nt_smem + (size_t)warp * (NT_COLS * NT_LDT + 32);
-    double *rv = tile + NT_COLS * NT_LDT;
-    double *pk = nt_smem + (size_t)NLS_NW * (NT_COLS * NT_LDT + 32);
+    // shared memory: NT_NP tiles [NT_COLS][NT_LDT] + rv[32]; the CTA packet [NLS_PK]; theta, v and the
+    // model's launch invariants; the full / empty barriers of every tile
+    double *tiles = nt_smem;
+    double *pk = nt_smem + (size_t)NT_NP * NT_TILE_DOUBLES;
     double *s_th = pk + NLS_PK, *s_vv = s_th + NLS_P, *s_cfj = s_vv + NLS_P, *s_cfvv = s_cfj + NT_NC_FJ;
-    for (int e = lane; e < NT_COLS * NT_LDT; e += 32)
-        tile[e] = 0.0; // padding columns stay zero for the whole launch
+    unsigned long long *full = (unsigned long long *)(s_cfvv + NT_NC_FVV), *empty = full + NT_NP;
+    for (int e = threadIdx.x; e < NT_NP * NT_TILE_DOUBLES; e += NLS_BLOCK)
+        tiles[e] = 0.0; // padding columns stay zero for the whole launch
     for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK)
         pk[e] = 0.0;
     for (int j = threadIdx.x; j < NLS_P; j += NLS_BLOCK) {
         s_th[j] = __ldcg(req + 1 + j);
         s_vv[j] = __ldcg(req + 1 + NLS_P + j);
+    }
+    if (threadIdx.x < NT_NP) {
+        nt_bar_init(full + threadIdx.x, 32);
+        nt_bar_init(empty + threadIdx.x, 32);
     }
     __syncthreads();
 #if GSLNLS_JAC_MODE == 0
@@ -270,14 +338,25 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
         gacc[g] = 0.0;
     double ss = 0.0, nbad = 0.0;
 
-    if (mode == NLS_MODE_FJ)
-        nt_stream<NLS_MODE_FJ>(prm, T, S, tile, rv, C, gacc, ss, nbad);
-    else if (mode == NLS_MODE_FVV)
-        nt_stream<NLS_MODE_FVV>(prm, T, S, tile, rv, C, gacc, ss, nbad);
-    else
-        nt_stream<NLS_MODE_JVP>(prm, T, S, tile, rv, C, gacc, ss, nbad);
+    const bool consumer = warp < NT_NCONS;
+    if (consumer) {
+        if (mode == NLS_MODE_FJ)
+            nt_consume<NLS_MODE_FJ>(prm, warp, tiles, full, empty, C, gacc);
+        else
+            nt_consume<NLS_MODE_FVV>(prm, warp, tiles, full, empty, C, gacc); // FVV and JVP: column dots only
+    } else {
+        const int q = warp - NT_NCONS;
+        double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
+        double *rv = tile + NT_COLS * NT_LDT;
+        if (mode == NLS_MODE_FJ)
+            nt_produce<NLS_MODE_FJ>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+        else if (mode == NLS_MODE_FVV)
+            nt_produce<NLS_MODE_FVV>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+        else
+            nt_produce<NLS_MODE_JVP>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+    }
 
-    // ---- CTA reduction: warps add their fragments into the shared packet in warp order ----
+    // ---- CTA reduction: warps add their sums into the shared packet in warp order ----
     ss += __shfl_down_sync(0xffffffffu, ss, 16);
     ss += __shfl_down_sync(0xffffffffu, ss, 8);
     ss += __shfl_down_sync(0xffffffffu, ss, 4);
@@ -296,43 +375,37 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
         gacc[b] += __shfl_xor_sync(0xffffffffu, gacc[b], 1);
         gacc[b] += __shfl_xor_sync(0xffffffffu, gacc[b], 2);
     }
+    const int goff = mode == NLS_MODE_FJ ? NLS_NPK : 0; // FVV / JVP packet: [J^T h (p) | h^T h]
+    __syncthreads();
     for (int w = 0; w < NLS_NW; ++w) {
         if (warp == w) {
-            if (mode == NLS_MODE_FJ) {
-                // packet: [J^T J lower packed row-major | J^T f | f^T f | #non-finite]
-                int t = 0;
+            if (consumer) {
+                if (mode == NLS_MODE_FJ) {
+                    // packet: [J^T J lower packed row-major | J^T f | f^T f | #non-finite]
+                    int t = 0;
 #pragma unroll
-                for (int bi = 0; bi < NT_PB; ++bi)
+                    for (int bi = 0; bi < NT_PB; ++bi)
 #pragma unroll
-                    for (int bj = 0; bj <= bi; ++bj, ++t) {
-                        const int row = bi * 8 + fr;
+                        for (int bj = 0; bj <= bi; ++bj, ++t) {
+                            const int row = bi * 8 + fr;
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int col = bj * 8 + fc2 + h;
-                            if (row < NLS_P && col <= row)
-                                pk[row * (row + 1) / 2 + col] += C[t][h];
+                            for (int h = 0; h < 2; ++h) {
+                                const int col = bj * 8 + fc2 + h;
+                                if (row < NLS_P && col <= row)
+                                    pk[row * (row + 1) / 2 + col] += C[t][h];
+                            }
                         }
-                    }
+                }
 #pragma unroll
                 for (int b = 0; b < NT_PB; ++b) {
                     const int c = b * 8 + fr;
                     if ((lane & 3) == 0 && c < NLS_P)
-                        pk[NLS_NPK + c] += gacc[b];
+                        pk[goff + c] += gacc[b];
                 }
-                if (lane == 0) {
-                    pk[NLS_NPK + NLS_P] += ss;
-                    pk[NLS_NPK + NLS_P + 1] += nbad;
-                }
-            } else {
-                // FVV / JVP packet: [J^T h (p) | h^T h]
-#pragma unroll
-                for (int b = 0; b < NT_PB; ++b) {
-                    const int c = b * 8 + fr;
-                    if ((lane & 3) == 0 && c < NLS_P)
-                        pk[c] += gacc[b];
-                }
-                if (lane == 0)
-                    pk[NLS_P] += ss;
+            } else if (lane == 0) {
+                pk[goff + NLS_P] += ss;
+                if (mode == NLS_MODE_FJ)
+                    pk[goff + NLS_P + 1] += nbad;
             }
         }
         __syncthreads();

@@ -135,9 +135,10 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
 static int pick_grid(const gslnls_problem *pb, int ncand, bool reserve_slot = false)
 {
     int64_t need;
-    if (pb->vkey.tiled) { // a warp takes slabs of 32 observations
+    if (pb->vkey.tiled) { // a producer warp takes slabs of 32 observations
         const int64_t nslab = (pb->n + 31) / 32, nw = pb->vkey.block / 32;
-        need = std::max<int64_t>(1, (nslab + nw - 1) / nw);
+        const int64_t np = nw / (1 + pb->vkey.unroll) * pb->vkey.unroll;
+        need = std::max<int64_t>(1, (nslab + np - 1) / np);
     } else {
         const int64_t nv = pb->vkey.vec == 2 ? pb->n / 2 : pb->n;
         need = std::max<int64_t>(1, (nv + pb->vkey.block - 1) / pb->vkey.block);

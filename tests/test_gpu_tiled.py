@@ -123,3 +123,22 @@ def test_gaussmix48_fit_matches_oracle(G, alg):
     assert np.allclose(fit["par"], ref["par"], rtol=1e-8)
     assert fit["ssr"] == pytest.approx(ref["ssr"], rel=1e-8)
     pb.close()
+
+
+def test_tiled_exp_accuracy(G):
+    """the tiled kernels evaluate exp() with the table-based branch-free nls_exp() (nls_model_prelude.h):
+    K4 materialises f = exp(c x) for a p = 9 model whose other terms vanish; compare with numpy's exp"""
+    n = 200_001
+    x = np.concatenate([np.linspace(-745.0, 709.0, n - 7), [0.0, -0.0, 1e-300, -1e-300, 800.0, -800.0, 708.5]])
+    names = ["c"] + ["z%d" % k for k in range(8)]
+    rhs = "exp(c * x)" + "".join(" + z%d * x" % k for k in range(8))
+    m = G.Model(rhs, names, ["x"], jac=True)
+    pb = G.Problem(m, n).upload([x], np.zeros(n))
+    f = pb.residuals([1.0] + [0.0] * 8)
+    with np.errstate(over="ignore"):
+        ref = np.exp(x)
+    ok = (np.abs(x) < 708.0)
+    rel = np.abs(f[ok] - ref[ok]) / ref[ok]
+    assert rel.max() < 4 * np.finfo(float).eps, rel.max()   # <= 1.24 ulp by construction
+    assert np.all(f[x >= 708.0] == np.inf) and np.all(f[x <= -708.0] == 0.0)
+    pb.close()
