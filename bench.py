@@ -235,12 +235,14 @@ def main():
         sampler.start()
     launches0 = pb.launch_count
     pb.set_profile(args.steps + 64)
+    pb.channel_stats(reset=True)
     barrier()
     pb.timer_start()
     iters, fits, last = run_steps(args.steps)
     ms = pb.timer_stop()
     barrier()
     pass_ms, pass_cnt = pb.profile()
+    stream_us, step_us, stream_cnt = pb.channel_stats()
     pb.set_profile(0)
     launches = pb.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
@@ -298,14 +300,25 @@ def main():
                    "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
                    "final": {"par": [float(v) for v in last["par"]], "ssr": float(last["ssr"]),
                              "niter": int(last["niter"]), "status": last["status"]},
-                   "parallelism": "observation-sharded x%d, one packet all-reduce per pass" % world},
+                   "parallelism": "observation-sharded x%d; per pass one %d-double packet per rank, %s" % (
+                       world, 3 * 4 // 2 + 3 + 2,
+                       "deposited by the pass kernel in every GPU's mailbox over NVLink peer memory and summed in "
+                       "rank order by the resident trust-region warp (no collective call)"
+                       if (comm is not None and comm.has_peer_memory) else
+                       ("NCCL all-gather + rank-order sum" if world > 1 else "single GPU, resident trust-region warp"))},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                      "kernel": "nls_pass (K1)", "algorithmic_bytes_per_launch": alg_bytes,
-                     "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt), "peak_source": peak_src},
+                     "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt), "peak_source": peak_src,
+                     "note": "avg_launch_ms = CUDA-event time of the nls_pass launches inside the timed region; in "
+                             "resident-server mode a launch starts by waiting (in-kernel) for the trust-region warp's "
+                             "request, so it spans wait + stream + grid reduction; stream_us / step_us are the device "
+                             "globaltimer splits (request seen -> packet out, packet complete -> next request)",
+                     "stream_us": stream_us, "step_us": step_us,
+                     "frac_stream": (alg_bytes / (stream_us * 1e-6) / 1e9 / peak) if stream_us > 0 else None},
     }
     if e2e:
         line["e2e"] = e2e

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -974,14 +975,28 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
         set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
         return GSLNLS_EINVAL;
     }
+    static const bool trace = std::getenv("GSLNLS_TRACE_E2E") != nullptr; // developer aid: phase times on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     gslnls_problem *pb = nullptr;
     int rc = gslnls_problem_create(m, n, weights != nullptr, device, &pb);
     if (rc)
         return rc;
+    const double t1 = now();
     rc = gslnls_problem_upload(pb, vars, y, weights);
-    if (rc == GSLNLS_SUCCESS)
+    double t2 = t1, t3 = t1;
+    if (rc == GSLNLS_SUCCESS) {
+        if (trace) {
+            cudaStreamSynchronize(pb->stream);
+            t2 = now();
+        }
         rc = gslnls_problem_fit(pb, start, control_int, control_dbl, want_resid_grad, out);
+        t3 = now();
+    }
     gslnls_problem_free(pb);
+    if (trace)
+        std::fprintf(stderr, "gslnls_fit_large: create %.2f ms, upload %.2f ms, fit %.2f ms, free %.2f ms\n", t1 - t0,
+                     t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 

@@ -78,11 +78,26 @@ TRS_HD inline bool finite_d(double v) { return (v - v) == 0.0; }
 // Reproduced on purpose: results must match the reference on the same inputs.
 TRS_HD inline double norm_of(double sumsq, double nbad) { return nbad >= 2.0 ? NAN : sqrt(sumsq); }
 
-template <int PMAX, class Lanes>
+// number of parameters: a run-time value bounded by PMAX, or -- FIXED -- the compile-time constant
+// PMAX itself, which lets the compiler unroll the p-loops and keep the private vectors in registers
+// (the resident server instantiates the small sizes that way)
+template <int PMAX, bool FIXED>
+struct Dim {
+    int v;
+    TRS_HD explicit Dim(int x) : v(x) {}
+    TRS_HD operator int() const { return v; }
+};
+template <int PMAX>
+struct Dim<PMAX, true> {
+    TRS_HD explicit Dim(int) {}
+    TRS_HD constexpr operator int() const { return PMAX; }
+};
+
+template <int PMAX, class Lanes, bool FIXED = false>
 struct Solver {
     const Params &P;
     Lanes L;
-    const int p;
+    const Dim<PMAX, FIXED> p;
     double *JTJ; // p*p row-major, lower triangle valid; shared by the lanes
     double *A;   // p*p work / factor; shared by the lanes
     // private vectors

@@ -69,7 +69,7 @@ static __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-template <int PMAX>
+template <int PMAX, bool FIXED>
 __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *channel, int nranks, int pk_count,
                                                  double *state, double *packet, double *req, double *partrace,
                                                  double *ssrtrace, double *condtrace, int *ndone,
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
     const unsigned long long *abort_w = (const unsigned long long *)(channel + NLS_CH_ABORT);
     const double *mbox = (const double *)(channel + NLS_CH_DATA);
     unsigned long long k = __ldcg((const unsigned long long *)(channel + NLS_CH_FIT_SEQ0));
-    trs::Solver<PMAX, trs::WarpLanes> S(P, trs::WarpLanes(), trs_smem, trs_smem + P.p * P.p);
+    trs::Solver<PMAX, trs::WarpLanes, FIXED> S(P, trs::WarpLanes(), trs_smem, trs_smem + P.p * P.p);
     if ((int)__ldcg(state + trs::S_PHASE) == trs::PH_DONE)
         return;
     for (;; ++k) {
@@ -227,12 +227,20 @@ cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, i
                               int *ndone, int *host_flags_dev, unsigned long long watchdog_ns, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * 2 * (size_t)P.p * P.p;
-    if (P.p <= 8)
-        trs_server<8><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace,
-                                               condtrace, ndone, host_flags_dev, watchdog_ns);
+#define TRS_SERVER_LAUNCH(PM, FX)                                                                                  \
+    trs_server<PM, FX><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace, \
+                                                condtrace, ndone, host_flags_dev, watchdog_ns)
+    if (P.p == 2)
+        TRS_SERVER_LAUNCH(2, true);
+    else if (P.p == 3)
+        TRS_SERVER_LAUNCH(3, true);
+    else if (P.p == 4)
+        TRS_SERVER_LAUNCH(4, true);
+    else if (P.p <= 8)
+        TRS_SERVER_LAUNCH(8, false);
     else if (P.p <= 32)
-        trs_server<32><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace,
-                                                condtrace, ndone, host_flags_dev, watchdog_ns);
+        TRS_SERVER_LAUNCH(32, false);
+#undef TRS_SERVER_LAUNCH
     else
         return cudaErrorInvalidValue;
     return cudaGetLastError();
