@@ -112,4 +112,4 @@ def test_nvrtc_compiles_finite_difference_modes(jac, fvv):
 def test_selfstart_shapes_translate():
     # inst/unit_tests/unit_tests_gslnls.R:272-275 uses SSasymp with gsl_nls_large
     m = Model("SSasymp(x, Asym, R0, lrc)", ["Asym", "R0", "lrc"], ["x"], jac=True, fvv=True)
-    assert "exp" in m.source
+    assert "NLS_EXP(" in m.source
