@@ -35,7 +35,11 @@ SIGNATURES = {
     "gslnls_model_source": (C.c_char_p, [C.c_void_p]),
     "gslnls_fit_large": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p, C.c_int64, c_double_p,
                                    c_int_p, c_double_p, C.c_int, C.c_int, C.POINTER(Result)]),
+    "gslnls_fit_large_sharded": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p, C.c_int64,
+                                           c_double_p, c_int_p, c_double_p, C.c_int, C.c_void_p, C.c_int,
+                                           C.POINTER(Result)]),
     "gslnls_result_free": (None, [C.POINTER(Result)]),
+    "gslnls_cache_clear": (None, []),
     "gslnls_problem_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gslnls_problem_free": (None, [C.c_void_p]),
     "gslnls_problem_upload": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p]),

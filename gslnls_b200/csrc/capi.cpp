@@ -50,7 +50,7 @@ GSLNLS_API int gslnls_model_compile(const char *rhs_expr, const char *const *par
         // compile the default variant now so that NVRTC errors surface at model-build time,
         // like stop("failed to symbolically derive 'jac'") does at R/nls_large.R:298-299
         const KernelTune t = default_tune(p);
-        m->compile(VariantKey{0, 2, 1, t.block, t.unroll, t.minb, t.tiled});
+        m->compile(VariantKey{0, 2, 1, t.block, t.unroll, t.minb, t.tiled, t.stages});
     } catch (const std::exception &e) {
         delete m;
         return fail(GSLNLS_ECOMPILE, e.what());
@@ -59,7 +59,12 @@ GSLNLS_API int gslnls_model_compile(const char *rhs_expr, const char *const *par
     return GSLNLS_SUCCESS;
 }
 
-GSLNLS_API void gslnls_model_free(gslnls_model *m) { delete m; }
+GSLNLS_API void gslnls_model_free(gslnls_model *m)
+{
+    if (m)
+        gslnls::cache_drop(m); // cached one-shot problems hold kernels of this model
+    delete m;
+}
 GSLNLS_API int gslnls_model_p(const gslnls_model *m) { return m ? m->p : 0; }
 GSLNLS_API int gslnls_model_nvar(const gslnls_model *m) { return m ? m->nvar : 0; }
 GSLNLS_API const char *gslnls_model_source(const gslnls_model *m) { return m ? m->source.c_str() : ""; }

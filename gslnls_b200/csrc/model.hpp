@@ -13,15 +13,16 @@ namespace gslnls {
 
 struct KernelTune {
     int block = 256, unroll = 4, minb = 2;
-    int tiled = 0; // 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh)
+    int tiled = 0; // 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh); 2: TMA-staged register kernel
+    int stages = 4; // tiled == 2: tiles in flight per CTA
 };
 
 struct VariantKey {
-    int has_w, vec, stream, block, unroll, minb, tiled;
+    int has_w, vec, stream, block, unroll, minb, tiled, stages;
     bool operator<(const VariantKey &o) const
     {
-        return std::tie(has_w, vec, stream, block, unroll, minb, tiled) <
-               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled);
+        return std::tie(has_w, vec, stream, block, unroll, minb, tiled, stages) <
+               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled, o.stages);
     }
 };
 
@@ -53,5 +54,7 @@ struct gslnls_model {
 namespace gslnls {
 KernelTune default_tune(int p);
 size_t tiled_smem_bytes(int p, int block, int nprod, int nconst); // dynamic shared memory of the tiled pass kernel
+size_t tma_smem_bytes(int narr, int block, int unroll, int stages); // dynamic shared memory of the TMA-staged pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture
+void cache_drop(const gslnls_model *m); // problem.cu: release one-shot problems cached for m (nullptr: all)
 } // namespace gslnls

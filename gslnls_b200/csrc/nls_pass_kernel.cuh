@@ -42,7 +42,8 @@
 #define NLS_STREAM 1
 #endif
 #ifndef NLS_TILED
-#define NLS_TILED 0 /* 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh), for p > 8 */
+#define NLS_TILED 0 /* 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh), for p > 8;
+                       2: register accumulators fed by a TMA bulk-copy shared-memory pipeline */
 #endif
 
 #define NLS_P GSLNLS_P
@@ -65,6 +66,32 @@ static __device__ __forceinline__ double2 nls_ld2(const double *p)
 #endif
     return r;
 }
+#if NLS_STREAM == 2
+// NLS_STREAM 2: every pass re-reads the same columns, so the head of the shard is loaded with an L2
+// evict_last policy (it is still in the 126 MB L2 when the next pass starts) and the rest with
+// evict_first (it cannot fit and must not displace the head)
+struct NlsL2Policy {
+    unsigned long long keep, stream;
+    long long keep_rows;
+};
+static __device__ __forceinline__ NlsL2Policy nls_l2_policy(long long keep_rows)
+{
+    NlsL2Policy P;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(P.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(P.stream));
+    P.keep_rows = keep_rows;
+    return P;
+}
+static __device__ __forceinline__ double2 nls_ld2(const double *p, unsigned long long pol)
+{
+    double2 r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+}
+#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o), l2pol)
+#else
+#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o))
+#endif
 static __device__ __forceinline__ double nls_ld1(const double *p)
 {
     double r;
@@ -233,27 +260,35 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
     }
 }
 
-// stream this CTA's share of the observations through nls_observe<MODE>
+// stream this CTA's share of the observations [lo, n) through nls_observe<MODE>; lo is even
 template <int MODE>
-static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, const NlsThread &T, double *acc)
+static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, const NlsThread &T, double *acc,
+                                                  long long lo = 0, int nbad = 0)
 {
     const long long n = prm.n;
     const long long stride = (long long)gridDim.x * NLS_BLOCK;
     long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
-    int nbad = 0;
 #if NLS_VEC == 2
     const long long nv = n >> 1;
+#if NLS_STREAM == 2
+    const NlsL2Policy L2P = nls_l2_policy(prm.l2_keep_rows);
+#endif
+    i += lo >> 1;
     for (; i + (NLS_UNROLL - 1) * stride < nv; i += NLS_UNROLL * stride) {
         double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+#if NLS_STREAM == 2
+        // one policy per loop trip (decided on the trip's first row): the boundary is fuzzy, nobody cares
+        const unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
+#endif
 #pragma unroll
         for (int u = 0; u < NLS_UNROLL; ++u) {
             const long long o = 2 * (i + u * stride);
 #pragma unroll
             for (int k = 0; k < GSLNLS_NVAR; ++k)
-                xv[u][k] = nls_ld2(prm.vars[k] + o);
-            yv[u] = nls_ld2(prm.y + o);
+                xv[u][k] = NLS_LD2(prm.vars[k], o);
+            yv[u] = NLS_LD2(prm.y, o);
 #if NLS_HAS_W
-            wv[u] = nls_ld2(prm.w + o);
+            wv[u] = NLS_LD2(prm.w, o);
 #else
             wv[u] = make_double2(1.0, 1.0);
 #endif
@@ -272,16 +307,19 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     }
     for (; i < nv; i += stride) {
         const long long o = 2 * i;
+#if NLS_STREAM == 2
+        const unsigned long long l2pol = o < L2P.keep_rows ? L2P.keep : L2P.stream;
+#endif
         double xa[NLS_NV], xb[NLS_NV];
 #pragma unroll
         for (int k = 0; k < GSLNLS_NVAR; ++k) {
-            const double2 t = nls_ld2(prm.vars[k] + o);
+            const double2 t = NLS_LD2(prm.vars[k], o);
             xa[k] = t.x;
             xb[k] = t.y;
         }
-        const double2 yy = nls_ld2(prm.y + o);
+        const double2 yy = NLS_LD2(prm.y, o);
 #if NLS_HAS_W
-        const double2 ww = nls_ld2(prm.w + o);
+        const double2 ww = NLS_LD2(prm.w, o);
 #else
         const double2 ww = make_double2(1.0, 1.0);
 #endif
@@ -302,6 +340,7 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
         nls_observe<MODE>(T, xa, nls_ld1(prm.y + o), ww, acc, nbad);
     }
 #else
+    i += lo;
     for (; i + (NLS_UNROLL - 1) * stride < n; i += NLS_UNROLL * stride) {
         double xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
 #pragma unroll
@@ -337,6 +376,149 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     if (MODE == NLS_MODE_FJ)
         acc[NLS_NPK + NLS_P + 1] = (double)nbad;
 }
+
+#if NLS_TILED == 2
+// ------------------------------------------------------------------------------------ K1, TMA-staged stream
+// The columns arrive in shared memory through the bulk-copy engine (cp.async.bulk, the 1-D TMA form)
+// instead of through per-thread LDG: one producer lane keeps NLS_STAGES tiles of NLS_TILE
+// observations per column in flight per CTA, completion is signalled on a "full" mbarrier by the
+// transaction count, the 8 consumer warps read their observations with conflict-free LDS.128 and
+// release the slot on an "empty" mbarrier as soon as the values sit in registers.  Bytes in flight
+// per SM no longer depend on registers per thread (NLS_STAGES x tile bytes per CTA), and the loop
+// body is pure FP64 work.  Tiles go to CTAs round-robin; the ragged end of the shard (< one tile)
+// runs through the register path above.  Needs 16-byte aligned columns (NLS_VEC == 2).
+#ifndef NLS_STAGES
+#define NLS_STAGES 4
+#endif
+#define NLS_NCONS (NLS_BLOCK - 32)             /* consumer threads; the last warp is the producer */
+#define NLS_NCW (NLS_NCONS / 32)
+#define NLS_TILE (NLS_NCONS * 2 * NLS_UNROLL)  /* observations per stage                          */
+#define NLS_NARR (GSLNLS_NVAR + 1 + NLS_HAS_W)
+#define NLS_STAGE_DOUBLES (NLS_NARR * NLS_TILE)
+
+static __device__ __forceinline__ unsigned nls_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void nls_bar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nls_saddr(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void nls_bar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(nls_saddr(bar)) : "memory");
+}
+static __device__ __forceinline__ void nls_bar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nls_saddr(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void nls_bar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "NLS_WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra NLS_DONE_%=;\n"
+                 "bra NLS_WAIT_%=;\n"
+                 "NLS_DONE_%=:\n"
+                 "}" ::"r"(nls_saddr(bar)), "r"(parity) : "memory");
+}
+static __device__ __forceinline__ void nls_bulk_g2s(double *dst, const double *src, unsigned bytes,
+                                                    unsigned long long *bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(nls_saddr(dst)), "l"(src), "r"(bytes), "r"(nls_saddr(bar)), "l"(policy) : "memory");
+}
+
+template <int MODE>
+static __device__ __forceinline__ void nls_stream_tma(const NlsPassParams &prm, const NlsThread &T, double *acc)
+{
+    extern __shared__ __align__(128) unsigned char nls_dyn[];
+    double *buf = reinterpret_cast<double *>(nls_dyn); // [NLS_STAGES][NLS_NARR][NLS_TILE]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(buf + (size_t)NLS_STAGES * NLS_STAGE_DOUBLES);
+    unsigned long long *empty = full + NLS_STAGES;
+    const long long ntile = prm.n / NLS_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NLS_STAGES; ++s) {
+            nls_bar_init(full + s, 1);
+            nls_bar_init(empty + s, NLS_NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int nbad = 0;
+    if (warp == NLS_NCW) {
+        if (lane == 0) {
+            // every pass re-reads the same columns: the head of the shard is asked to stay in L2
+            // (evict_last) so that it is served from there on the next pass, the rest -- which cannot
+            // fit -- streams through without displacing it (evict_first)
+            unsigned long long pol_stream, pol_keep;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            int s = 0;
+            unsigned ph = 1u; // a fresh barrier lets a wait on the "previous" phase through
+            for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+                nls_bar_wait(empty + s, ph);
+                nls_bar_expect_tx(full + s, (unsigned)(NLS_STAGE_DOUBLES * sizeof(double)));
+                double *dst = buf + (size_t)s * NLS_STAGE_DOUBLES;
+                const long long o = t * NLS_TILE;
+                const unsigned long long policy = o < (long long)prm.l2_keep_rows ? pol_keep : pol_stream;
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k)
+                    nls_bulk_g2s(dst + k * NLS_TILE, prm.vars[k] + o, NLS_TILE * 8u, full + s, policy);
+                nls_bulk_g2s(dst + GSLNLS_NVAR * NLS_TILE, prm.y + o, NLS_TILE * 8u, full + s, policy);
+#if NLS_HAS_W
+                nls_bulk_g2s(dst + (GSLNLS_NVAR + 1) * NLS_TILE, prm.w + o, NLS_TILE * 8u, full + s, policy);
+#endif
+                if (++s == NLS_STAGES) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else {
+        int s = 0;
+        unsigned ph = 0u;
+        for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
+            nls_bar_wait(full + s, ph);
+            const double *b = buf + (size_t)s * NLS_STAGE_DOUBLES;
+            double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < NLS_UNROLL; ++u) {
+                const int o = 2 * (u * NLS_NCONS + (int)threadIdx.x);
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k)
+                    xv[u][k] = *reinterpret_cast<const double2 *>(b + k * NLS_TILE + o);
+                yv[u] = *reinterpret_cast<const double2 *>(b + GSLNLS_NVAR * NLS_TILE + o);
+#if NLS_HAS_W
+                wv[u] = *reinterpret_cast<const double2 *>(b + (GSLNLS_NVAR + 1) * NLS_TILE + o);
+#else
+                wv[u] = make_double2(1.0, 1.0);
+#endif
+            }
+            __syncwarp();
+            if (lane == 0)
+                nls_bar_arrive(empty + s); // the slot can be refilled while we compute
+#pragma unroll
+            for (int u = 0; u < NLS_UNROLL; ++u) {
+                double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k) {
+                    xa[k] = xv[u][k].x;
+                    xb[k] = xv[u][k].y;
+                }
+                nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc, nbad);
+                nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc, nbad);
+            }
+            if (++s == NLS_STAGES) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    }
+    // rows past the last full tile: register path, all warps
+    nls_stream<MODE>(prm, T, acc, ntile * NLS_TILE, nbad);
+}
+#endif // NLS_TILED == 2
 
 // ------------------------------------------------------------------------------------ K1 head / tail
 // Shared by the register-accumulator kernel below and the tiled DMMA kernel (nls_pass_tiled.cuh).
@@ -520,7 +702,7 @@ static __device__ __forceinline__ void nls_grid_finish(const NlsPassParams &prm,
     nls_packet_publish(prm, cand, seq);
 }
 
-#if NLS_TILED
+#if NLS_TILED == 1
 #include "nls_pass_tiled.cuh"
 #else
 // ------------------------------------------------------------------------------------ K1 (register accumulators)
@@ -541,12 +723,21 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     for (int e = 0; e < NLS_PK; ++e)
         acc[e] = 0.0;
 
+#if NLS_TILED == 2
+    if (mode == NLS_MODE_FJ)
+        nls_stream_tma<NLS_MODE_FJ>(prm, T, acc);
+    else if (mode == NLS_MODE_FVV)
+        nls_stream_tma<NLS_MODE_FVV>(prm, T, acc);
+    else
+        nls_stream_tma<NLS_MODE_JVP>(prm, T, acc);
+#else
     if (mode == NLS_MODE_FJ)
         nls_stream<NLS_MODE_FJ>(prm, T, acc);
     else if (mode == NLS_MODE_FVV)
         nls_stream<NLS_MODE_FVV>(prm, T, acc);
     else
         nls_stream<NLS_MODE_JVP>(prm, T, acc);
+#endif
 
     // ---- CTA reduction: fixed shuffle tree, then warps summed in warp order ----
     __shared__ double sred[NLS_NW][NLS_PK];
@@ -573,7 +764,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     }
     nls_grid_finish(prm, cand);
 }
-#endif // NLS_TILED
+#endif // NLS_TILED == 1
 
 // ------------------------------------------------------------------------------------ K4
 // resid_i = sqrt(w_i) (fn_i - y_i) and grad[i + n j] = sqrt(w_i) J_ij at the final parameters:

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -52,6 +53,7 @@ struct gslnls_problem {
     size_t prof_flags_cap = 0;
     // data
     std::vector<double *> owned; // buffers we allocated
+    int64_t owned_cap = 0;       // rows each owned buffer can hold
     const double *dvars[NLS_MAX_VARS] = {nullptr};
     const double *dy = nullptr, *dw = nullptr;
     bool bound = false;
@@ -81,6 +83,7 @@ struct gslnls_problem {
     double h_df = 0, h_fvv = 0;
     int64_t launches = 0, passes = 0;
     int chunk = 8;
+    double l2_keep_mb = 0.0; // megabytes of the shard's head kept in L2 between passes (0: no cache hints)
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
     bool allow_server = true, server_on = false;
@@ -115,8 +118,12 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             vec = 1;
     if ((reinterpret_cast<uintptr_t>(pb->dy) & 15u) || (pb->dw && (reinterpret_cast<uintptr_t>(pb->dw) & 15u)))
         vec = 1;
-    const KernelTune t = default_tune(pb->p);
-    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb, batch ? 0 : t.tiled};
+    KernelTune t = default_tune(pb->p);
+    if (t.tiled == 2 && (vec != 2 || batch)) { // bulk copies need 16-byte aligned columns; fall back to LDG
+        t.tiled = 0;
+        t.block = std::max(32, t.block - 32);
+    }
+    VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;
     try {
@@ -136,7 +143,10 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
 static int pick_grid(const gslnls_problem *pb, int ncand, bool reserve_slot = false)
 {
     int64_t need;
-    if (pb->vkey.tiled) { // a producer warp takes slabs of 32 observations
+    if (pb->vkey.tiled == 2) { // tiles of (consumer threads x 2 x unroll) observations go to CTAs round-robin
+        const int64_t tile = (int64_t)(pb->vkey.block - 32) * 2 * pb->vkey.unroll;
+        need = std::max<int64_t>(1, pb->n / tile);
+    } else if (pb->vkey.tiled) { // a producer warp takes slabs of 32 observations
         const int64_t nslab = (pb->n + 31) / 32, nw = pb->vkey.block / 32;
         const int64_t np = nw / (1 + pb->vkey.unroll) * pb->vkey.unroll;
         need = std::max<int64_t>(1, (nslab + np - 1) / np);
@@ -214,6 +224,8 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
         prm.group_partials = pb->d_gparts;
         prm.group_ticket = pb->d_gticket;
     }
+    if (pb->l2_keep_mb > 0 && ncand == 1) // rows of the shard's head that are asked to stay in L2
+        prm.l2_keep_rows = (int)std::min(2.0e9, pb->l2_keep_mb * 1.0e6 / (8.0 * (pb->nvar + 1 + pb->has_w)));
     prm.nranks = 1;
     if (pb->server_on) {
         prm.channel = channel_of(pb);
@@ -291,6 +303,76 @@ static int wait_server_caught_up(gslnls_problem *pb)
     return GSLNLS_SUCCESS;
 }
 
+// ---- one-shot call cache -------------------------------------------------------------------
+// gslnls_fit_large() is called once per fit from the host language, so everything that does not depend on
+// the data values -- the n-sized device buffers, the solver workspace, streams, events, pinned words, the
+// loaded kernels -- is kept from one call to the next (one problem per device).  Measured on B200 at
+// n = 1e8: cudaMalloc/cudaFree of the 1.6 GB of columns plus the pinned allocations cost 5-90 ms per
+// call against 30 ms of PCIe copy and 4 ms of fit.  gslnls_cache_clear() returns the memory.
+namespace {
+std::mutex g_cache_mu;
+std::vector<gslnls_problem *> g_cache;
+bool cache_enabled()
+{
+    const char *c = std::getenv("GSLNLS_CACHE");
+    return !(c && std::atoi(c) == 0);
+}
+gslnls_problem *cache_take(const gslnls_model *m, int has_w, int device)
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+        gslnls_problem *pb = g_cache[i];
+        if (pb->model == m && pb->has_w == has_w && pb->device == device) {
+            g_cache.erase(g_cache.begin() + (long)i);
+            return pb;
+        }
+    }
+    return nullptr;
+}
+} // namespace
+
+extern "C" void gslnls_problem_free(gslnls_problem *pb);
+
+static void cache_put(gslnls_problem *pb)
+{
+    std::vector<gslnls_problem *> evict;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (g_cache[i]->device == pb->device) {
+                evict.push_back(g_cache[i]);
+                g_cache.erase(g_cache.begin() + (long)i);
+            } else {
+                ++i;
+            }
+        }
+        g_cache.push_back(pb);
+    }
+    for (gslnls_problem *e : evict)
+        gslnls_problem_free(e);
+}
+
+namespace gslnls {
+// a model is going away (gslnls_model_free) or the user asked for the memory back (m == nullptr: all)
+void cache_drop(const gslnls_model *m)
+{
+    std::vector<gslnls_problem *> evict;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (!m || g_cache[i]->model == m) {
+                evict.push_back(g_cache[i]);
+                g_cache.erase(g_cache.begin() + (long)i);
+            } else {
+                ++i;
+            }
+        }
+    }
+    for (gslnls_problem *e : evict)
+        gslnls_problem_free(e);
+}
+} // namespace gslnls
+
 // ------------------------------------------------------------------------------------ C ABI
 
 extern "C" {
@@ -338,6 +420,8 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
     if (const char *c = std::getenv("GSLNLS_CHUNK"))
         pb->chunk = std::max(1, std::atoi(c));
+    if (const char *c = std::getenv("GSLNLS_L2_KEEP_MB"))
+        pb->l2_keep_mb = std::atof(c);
     if (const char *c = std::getenv("GSLNLS_SERVER"))
         pb->allow_server = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
@@ -391,16 +475,19 @@ GSLNLS_API int gslnls_problem_upload(gslnls_problem *pb, const double *const *va
     if (!pb || !y || (pb->nvar > 0 && !vars) || (pb->has_w && !weights))
         return GSLNLS_EINVAL;
     CK(cudaSetDevice(pb->device));
-    const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(pb->n, 1);
-    if (pb->bound || pb->owned.empty()) {
+    const int nbuf = pb->nvar + 1 + pb->has_w;
+    if (pb->bound || (int)pb->owned.size() != nbuf || pb->owned_cap < pb->n) {
         for (double *b : pb->owned)
             cudaFree(b);
         pb->owned.clear();
-        for (int k = 0; k < pb->nvar + 1 + pb->has_w; ++k) {
+        pb->owned_cap = 0;
+        const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(pb->n, 1);
+        for (int k = 0; k < nbuf; ++k) {
             double *d = nullptr;
             CK(cudaMalloc(&d, bytes));
             pb->owned.push_back(d);
         }
+        pb->owned_cap = std::max<int64_t>(pb->n, 1);
         pb->bound = false;
     }
     for (int k = 0; k < pb->nvar; ++k) {
@@ -963,14 +1050,16 @@ GSLNLS_API int gslnls_problem_channel_stats(gslnls_problem *pb, int reset, doubl
     return GSLNLS_SUCCESS;
 }
 
-GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars, const double *y,
-                                const double *weights, int64_t n, const double *start, const int *control_int,
-                                const double *control_dbl, int device, int want_resid_grad, gslnls_result *out)
+GSLNLS_API int gslnls_fit_large_sharded(const gslnls_model *m, const double *const *vars, const double *y,
+                                        const double *weights, int64_t n_local, const double *start,
+                                        const int *control_int, const double *control_dbl, int device,
+                                        gslnls_comm *comm, int want_resid_grad, gslnls_result *out)
 {
     if (!m || !y || !start || !control_int || !control_dbl || !out)
         return GSLNLS_EINVAL;
     std::memset(out, 0, sizeof(*out));
-    if (n < m->p) {
+    const bool sharded = comm && comm->nranks > 1;
+    if (!sharded && n_local < m->p) {
         // R/nls_large.R:286-288
         set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
         return GSLNLS_EINVAL;
@@ -978,12 +1067,27 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
     static const bool trace = std::getenv("GSLNLS_TRACE_E2E") != nullptr; // developer aid: phase times on stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    gslnls_problem *pb = nullptr;
-    int rc = gslnls_problem_create(m, n, weights != nullptr, device, &pb);
-    if (rc)
-        return rc;
+    const bool use_cache = cache_enabled();
+    gslnls_problem *pb = use_cache ? cache_take(m, weights != nullptr, device) : nullptr;
+    int rc = GSLNLS_SUCCESS;
+    if (pb) {
+        pb->n = n_local; // the buffers grow on demand in upload(); grid and workspace follow in prepare()
+        pb->n_total = n_local;
+        pb->comm = nullptr;
+    } else {
+        rc = gslnls_problem_create(m, n_local, weights != nullptr, device, &pb);
+        if (rc)
+            return rc;
+    }
     const double t1 = now();
     rc = gslnls_problem_upload(pb, vars, y, weights);
+    if (rc == GSLNLS_SUCCESS && sharded) {
+        rc = gslnls_problem_set_comm(pb, comm);
+        if (rc == GSLNLS_SUCCESS && pb->n_total < m->p) {
+            set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
+            rc = GSLNLS_EINVAL;
+        }
+    }
     double t2 = t1, t3 = t1;
     if (rc == GSLNLS_SUCCESS) {
         if (trace) {
@@ -993,12 +1097,27 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
         rc = gslnls_problem_fit(pb, start, control_int, control_dbl, want_resid_grad, out);
         t3 = now();
     }
-    gslnls_problem_free(pb);
+    if (use_cache && rc < 1000) {
+        pb->comm = nullptr; // the caller owns the comm and may free it before the next call
+        cache_put(pb);
+    } else {
+        gslnls_problem_free(pb);
+    }
     if (trace)
         std::fprintf(stderr, "gslnls_fit_large: create %.2f ms, upload %.2f ms, fit %.2f ms, free %.2f ms\n", t1 - t0,
                      t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
+
+GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars, const double *y,
+                                const double *weights, int64_t n, const double *start, const int *control_int,
+                                const double *control_dbl, int device, int want_resid_grad, gslnls_result *out)
+{
+    return gslnls_fit_large_sharded(m, vars, y, weights, n, start, control_int, control_dbl, device, nullptr,
+                                    want_resid_grad, out);
+}
+
+GSLNLS_API void gslnls_cache_clear(void) { cache_drop(nullptr); }
 
 GSLNLS_API void gslnls_result_free(gslnls_result *r)
 {

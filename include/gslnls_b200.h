@@ -130,7 +130,19 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
                                 const double *weights, int64_t n, const double *start,
                                 const int *control_int, const double *control_dbl, int device,
                                 int want_resid_grad, gslnls_result *out);
+/* The same call for one rank of a multi-GPU job (one process per GPU): vars/y/weights hold this rank's
+ * contiguous shard of n_local rows, `comm` is the exchange context every rank created with
+ * gslnls_comm_create (NULL or a 1-rank comm = single GPU).  Every rank calls it with the same start and
+ * control and receives the same result; resid/grad, when requested, cover the local rows only. */
+GSLNLS_API int gslnls_fit_large_sharded(const gslnls_model *m, const double *const *vars, const double *y,
+                                        const double *weights, int64_t n_local, const double *start,
+                                        const int *control_int, const double *control_dbl, int device,
+                                        gslnls_comm *comm, int want_resid_grad, gslnls_result *out);
 GSLNLS_API void gslnls_result_free(gslnls_result *r);
+/* gslnls_fit_large[_sharded] keeps the device buffers, workspace and streams of the last call per device
+ * for the next one (same model); this returns them (also done for a model by gslnls_model_free).
+ * GSLNLS_CACHE=0 in the environment disables the cache. */
+GSLNLS_API void gslnls_cache_clear(void);
 
 /* ---- resident-data API (data stays in HBM across fits; used by benchmarks and multi-GPU) ---- */
 
