@@ -38,6 +38,9 @@ SIGNATURES = {
     "gslnls_fit_large_sharded": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p, C.c_int64,
                                            c_double_p, c_int_p, c_double_p, C.c_int, C.c_void_p, C.c_int,
                                            C.POINTER(Result)]),
+    "gslnls_fit_large_multi": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p, C.c_int64,
+                                         c_double_p, c_int_p, c_double_p, C.c_int, c_int_p, C.c_int,
+                                         C.POINTER(Result)]),
     "gslnls_result_free": (None, [C.POINTER(Result)]),
     "gslnls_cache_clear": (None, []),
     "gslnls_problem_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -63,6 +66,7 @@ SIGNATURES = {
                                            c_double_p, c_double_p, c_int_p, c_int_p]),
     "gslnls_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "gslnls_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "gslnls_comm_create_local": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_void_p)]),
     "gslnls_comm_free": (None, [C.c_void_p]),
     "gslnls_comm_has_peer_memory": (C.c_int, [C.c_void_p]),
     "gslnls_comm_rank": (C.c_int, [C.c_void_p]),

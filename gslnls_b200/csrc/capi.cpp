@@ -50,7 +50,7 @@ GSLNLS_API int gslnls_model_compile(const char *rhs_expr, const char *const *par
         // compile the default variant now so that NVRTC errors surface at model-build time,
         // like stop("failed to symbolically derive 'jac'") does at R/nls_large.R:298-299
         const KernelTune t = default_tune(p);
-        m->compile(VariantKey{0, 2, 1, t.block, t.unroll, t.minb, t.tiled, t.stages});
+        m->compile(VariantKey{0, 2, 1, t.block, t.unroll, t.minb, t.tiled, t.stages, t.prefetch, t.fexp});
     } catch (const std::exception &e) {
         delete m;
         return fail(GSLNLS_ECOMPILE, e.what());

@@ -25,6 +25,7 @@ typedef int (*fn_CommInitRank)(void **, int, ncclUniqueId_t, int);
 typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
 typedef int (*fn_AllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*fn_CommDestroy)(void *);
+typedef int (*fn_CommInitAll)(void **, int, const int *);
 typedef const char *(*fn_GetErrorString)(int);
 
 struct Nccl {
@@ -34,6 +35,7 @@ struct Nccl {
     fn_AllReduce AllReduce = nullptr;
     fn_AllGather AllGather = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
+    fn_CommInitAll CommInitAll = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
     bool ok = false;
 };
@@ -56,6 +58,7 @@ Nccl &nccl()
     N.AllReduce = (fn_AllReduce)dlsym(N.h, "ncclAllReduce");
     N.AllGather = (fn_AllGather)dlsym(N.h, "ncclAllGather");
     N.CommDestroy = (fn_CommDestroy)dlsym(N.h, "ncclCommDestroy");
+    N.CommInitAll = (fn_CommInitAll)dlsym(N.h, "ncclCommInitAll");
     N.GetErrorString = (fn_GetErrorString)dlsym(N.h, "ncclGetErrorString");
     N.ok = N.GetUniqueId && N.CommInitRank && N.AllReduce && N.AllGather && N.CommDestroy;
     return N;
@@ -165,6 +168,8 @@ static void setup_peer_channel(gslnls_comm *c)
 
 extern "C" {
 
+GSLNLS_API void gslnls_comm_free(gslnls_comm *c);
+
 GSLNLS_API int gslnls_comm_get_unique_id(void *id_bytes)
 {
     if (!id_bytes)
@@ -223,12 +228,101 @@ GSLNLS_API int gslnls_comm_create(const void *id_bytes, int rank, int nranks, in
     return GSLNLS_SUCCESS;
 }
 
+// All ranks of one process (one host thread per GPU drives its own rank): the channel blocks are
+// reached through peer access in the unified address space, no cudaIpc, no rendezvous.  NCCL is
+// initialised too when available (ncclCommInitAll) for the paths that do not use the mailboxes.
+GSLNLS_API int gslnls_comm_create_local(int ndev, const int *devices, gslnls_comm **out)
+{
+    if (!out || !devices || ndev < 1 || ndev > NLS_MAX_RANKS)
+        return GSLNLS_EINVAL;
+    for (int r = 0; r < ndev; ++r)
+        out[r] = nullptr;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess)
+        have = 0;
+    for (int r = 0; r < ndev; ++r) {
+        if (devices[r] < 0 || devices[r] >= have) {
+            set_error("no such CUDA device");
+            return GSLNLS_ENODEVICE;
+        }
+        for (int q = 0; q < r; ++q)
+            if (devices[q] == devices[r]) {
+                set_error("a device may appear only once");
+                return GSLNLS_EINVAL;
+            }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    bool ok = true;
+    for (int r = 0; r < ndev && ok; ++r) {
+        gslnls_comm *c = new gslnls_comm();
+        c->rank = r;
+        c->nranks = ndev;
+        c->device = devices[r];
+        c->local = true;
+        out[r] = c;
+        if (ndev > 1) {
+            ok = cudaSetDevice(devices[r]) == cudaSuccess && cudaMalloc(&c->channel, NLS_CH_BYTES) == cudaSuccess &&
+                 cudaMemset(c->channel, 0, NLS_CH_BYTES) == cudaSuccess;
+        }
+    }
+    bool p2p = ok && ndev > 1;
+    for (int r = 0; r < ndev && p2p; ++r) {
+        cudaSetDevice(devices[r]);
+        for (int q = 0; q < ndev && p2p; ++q) {
+            if (q == r)
+                continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[r], devices[q]);
+            if (!can) {
+                p2p = false;
+                break;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                p2p = false;
+            cudaGetLastError();
+        }
+    }
+    const char *env = std::getenv("GSLNLS_P2P");
+    if (env && std::atoi(env) == 0)
+        p2p = false;
+    for (int r = 0; r < ndev && ok; ++r) {
+        out[r]->p2p = p2p;
+        for (int q = 0; q < ndev; ++q)
+            out[r]->peer_channel[q] = out[q]->channel;
+    }
+    if (ok && ndev > 1) {
+        Nccl &N = nccl();
+        if (N.ok && N.CommInitAll) {
+            void *comms[NLS_MAX_RANKS] = {nullptr};
+            if (N.CommInitAll(comms, ndev, devices) == 0)
+                for (int r = 0; r < ndev; ++r)
+                    out[r]->nccl = comms[r];
+        }
+        if (!p2p && !out[0]->nccl) {
+            set_error("the devices have neither peer access nor a usable libnccl.so.2");
+            ok = false;
+        }
+    }
+    cudaSetDevice(prev);
+    if (!ok) {
+        set_error("could not set up the device group (allocation, peer access or NCCL initialisation failed)");
+        for (int r = 0; r < ndev; ++r) {
+            gslnls_comm_free(out[r]);
+            out[r] = nullptr;
+        }
+        return GSLNLS_ECOMM;
+    }
+    return GSLNLS_SUCCESS;
+}
+
 GSLNLS_API void gslnls_comm_free(gslnls_comm *c)
 {
     if (!c)
         return;
     cudaSetDevice(c->device);
-    for (int r = 0; r < c->nranks && r < NLS_MAX_RANKS; ++r)
+    for (int r = 0; r < c->nranks && r < NLS_MAX_RANKS && !c->local; ++r)
         if (r != c->rank && c->peer_channel[r])
             cudaIpcCloseMemHandle(c->peer_channel[r]);
     if (c->channel)

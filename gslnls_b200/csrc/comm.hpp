@@ -9,6 +9,8 @@ struct gslnls_comm {
     char *channel = nullptr;
     char *peer_channel[8] = {nullptr};
     bool p2p = false;
+    bool local = false;         // created by gslnls_comm_create_local: peers are mapped by peer access, not cudaIpc
+    long long n_total_hint = -1; // local groups: the caller knows the global row count (no size exchange needed)
 };
 
 namespace gslnls {

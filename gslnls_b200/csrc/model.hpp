@@ -15,14 +15,16 @@ struct KernelTune {
     int block = 256, unroll = 4, minb = 2;
     int tiled = 0; // 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh); 2: TMA-staged register kernel
     int stages = 4; // tiled == 2: tiles in flight per CTA
+    int prefetch = 0; // register kernel: software-pipelined loads (next trip's loads before this trip's arithmetic)
+    int fexp = 0;     // exp() of the model: 0 CUDA library, 1 branch-free table variant, 2 branch-free polynomial
 };
 
 struct VariantKey {
-    int has_w, vec, stream, block, unroll, minb, tiled, stages;
+    int has_w, vec, stream, block, unroll, minb, tiled, stages, prefetch, fexp;
     bool operator<(const VariantKey &o) const
     {
-        return std::tie(has_w, vec, stream, block, unroll, minb, tiled, stages) <
-               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled, o.stages);
+        return std::tie(has_w, vec, stream, block, unroll, minb, tiled, stages, prefetch, fexp) <
+               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled, o.stages, o.prefetch, o.fexp);
     }
 };
 
@@ -33,6 +35,7 @@ struct Variant {
     cudaKernel_t pass = nullptr, materialise = nullptr;
     bool loaded = false;
     size_t pass_smem = 0; // dynamic shared memory of one nls_pass CTA (tiled variant)
+    std::vector<int> smem_devices; // devices on which the dynamic shared-memory limit has been raised
 };
 
 } // namespace gslnls
@@ -42,7 +45,7 @@ struct gslnls_model {
     std::string source; // generated device functions
     int p = 0, nvar = 0;
     std::map<gslnls::VariantKey, gslnls::Variant> variants;
-    std::mutex mu;
+    std::mutex mu, load_mu;
 
     // NVRTC-compile (if needed) the kernel variant; no device required. Throws std::runtime_error.
     gslnls::Variant &compile(const gslnls::VariantKey &key);

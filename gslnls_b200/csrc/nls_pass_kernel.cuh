@@ -41,6 +41,9 @@
 #ifndef NLS_STREAM
 #define NLS_STREAM 1
 #endif
+#ifndef NLS_PREFETCH
+#define NLS_PREFETCH 0 /* 1: register kernel issues the next trip's loads before this trip's arithmetic */
+#endif
 #ifndef NLS_TILED
 #define NLS_TILED 0 /* 1: shared-memory J tiles + FP64 DMMA SYRK (nls_pass_tiled.cuh), for p > 8;
                        2: register accumulators fed by a TMA bulk-copy shared-memory pipeline */
@@ -274,6 +277,75 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     const NlsL2Policy L2P = nls_l2_policy(prm.l2_keep_rows);
 #endif
     i += lo >> 1;
+#if NLS_PREFETCH
+    // software pipeline: the loads of trip k+1 are issued before the arithmetic of trip k, so every
+    // warp has NLS_UNROLL 16-byte loads per column in flight while it computes (without this a warp's
+    // loads and its arithmetic alternate and only the other warps of the scheduler cover the latency)
+    if (i + (NLS_UNROLL - 1) * stride < nv) {
+        double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+        double2 xn[NLS_UNROLL][NLS_NV], yn[NLS_UNROLL], wn[NLS_UNROLL];
+#if NLS_STREAM == 2
+        unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
+#endif
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            const long long o = 2 * (i + u * stride);
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k)
+                xv[u][k] = NLS_LD2(prm.vars[k], o);
+            yv[u] = NLS_LD2(prm.y, o);
+#if NLS_HAS_W
+            wv[u] = NLS_LD2(prm.w, o);
+#else
+            wv[u] = make_double2(1.0, 1.0);
+#endif
+        }
+        for (;;) {
+            const long long j = i + NLS_UNROLL * stride;
+            const bool more = j + (NLS_UNROLL - 1) * stride < nv;
+            if (more) {
+#if NLS_STREAM == 2
+                l2pol = 2 * j < L2P.keep_rows ? L2P.keep : L2P.stream;
+#endif
+#pragma unroll
+                for (int u = 0; u < NLS_UNROLL; ++u) {
+                    const long long o = 2 * (j + u * stride);
+#pragma unroll
+                    for (int k = 0; k < GSLNLS_NVAR; ++k)
+                        xn[u][k] = NLS_LD2(prm.vars[k], o);
+                    yn[u] = NLS_LD2(prm.y, o);
+#if NLS_HAS_W
+                    wn[u] = NLS_LD2(prm.w, o);
+#else
+                    wn[u] = make_double2(1.0, 1.0);
+#endif
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NLS_UNROLL; ++u) {
+                double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k) {
+                    xa[k] = xv[u][k].x;
+                    xb[k] = xv[u][k].y;
+                }
+                nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc, nbad);
+                nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc, nbad);
+            }
+            i = j;
+            if (!more)
+                break;
+#pragma unroll
+            for (int u = 0; u < NLS_UNROLL; ++u) {
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k)
+                    xv[u][k] = xn[u][k];
+                yv[u] = yn[u];
+                wv[u] = wn[u];
+            }
+        }
+    }
+#else
     for (; i + (NLS_UNROLL - 1) * stride < nv; i += NLS_UNROLL * stride) {
         double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
 #if NLS_STREAM == 2
@@ -305,6 +377,49 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
             nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc, nbad);
         }
     }
+#endif // NLS_PREFETCH
+#if NLS_UNROLL > 1
+    // what is left is less than one full trip: at most NLS_UNROLL - 1 strided slots per thread.  All their
+    // loads go out together (a one-slot-at-a-time loop would pay one memory round trip per slot, which is
+    // what a 200 MB shard of an 8-GPU run spent 10 % of its pass on)
+    if (i < nv) {
+        double2 xt[NLS_UNROLL - 1][NLS_NV], yt[NLS_UNROLL - 1], wt[NLS_UNROLL - 1];
+#if NLS_STREAM == 2
+        const unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
+#endif
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL - 1; ++u) {
+            const long long o = 2 * (i + u * stride);
+            if (o < 2 * nv) {
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k)
+                    xt[u][k] = NLS_LD2(prm.vars[k], o);
+                yt[u] = NLS_LD2(prm.y, o);
+#if NLS_HAS_W
+                wt[u] = NLS_LD2(prm.w, o);
+#endif
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL - 1; ++u) {
+            if (i + u * stride < nv) {
+                double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+                for (int k = 0; k < GSLNLS_NVAR; ++k) {
+                    xa[k] = xt[u][k].x;
+                    xb[k] = xt[u][k].y;
+                }
+#if NLS_HAS_W
+                const double2 ww = wt[u];
+#else
+                const double2 ww = make_double2(1.0, 1.0);
+#endif
+                nls_observe<MODE>(T, xa, yt[u].x, ww.x, acc, nbad);
+                nls_observe<MODE>(T, xb, yt[u].y, ww.y, acc, nbad);
+            }
+        }
+    }
+#else
     for (; i < nv; i += stride) {
         const long long o = 2 * i;
 #if NLS_STREAM == 2
@@ -326,6 +441,7 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
         nls_observe<MODE>(T, xa, yy.x, ww.x, acc, nbad);
         nls_observe<MODE>(T, xb, yy.y, ww.y, acc, nbad);
     }
+#endif // NLS_UNROLL > 1
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long o = n - 1;
         double xa[NLS_NV];
@@ -420,11 +536,23 @@ static __device__ __forceinline__ void nls_bar_wait(unsigned long long *bar, uns
                  "NLS_DONE_%=:\n"
                  "}" ::"r"(nls_saddr(bar)), "r"(parity) : "memory");
 }
+// NLS_TMA_HINT 1: L2 evict_first / evict_last policies on the bulk copies (see l2_keep_rows); 0: none.
+// Measured: evict_first on everything loses the partial L2 hits a 200 MB shard gets from pass to pass
+// under the default policy, and evict_last never made the head of a shard stay.
+#ifndef NLS_TMA_HINT
+#define NLS_TMA_HINT 0
+#endif
 static __device__ __forceinline__ void nls_bulk_g2s(double *dst, const double *src, unsigned bytes,
                                                     unsigned long long *bar, unsigned long long policy)
 {
+#if NLS_TMA_HINT
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(nls_saddr(dst)), "l"(src), "r"(bytes), "r"(nls_saddr(bar)), "l"(policy) : "memory");
+#else
+    (void)policy;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(nls_saddr(dst)), "l"(src), "r"(bytes), "r"(nls_saddr(bar)) : "memory");
+#endif
 }
 
 template <int MODE>

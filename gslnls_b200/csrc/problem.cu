@@ -16,6 +16,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gslnls_b200.h"
@@ -123,7 +124,7 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
         t.tiled = 0;
         t.block = std::max(32, t.block - 32);
     }
-    VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages};
+    VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;
     try {
@@ -422,6 +423,15 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
         pb->chunk = std::max(1, std::atoi(c));
     if (const char *c = std::getenv("GSLNLS_L2_KEEP_MB"))
         pb->l2_keep_mb = std::atof(c);
+    if (pb->l2_keep_mb > 0 && !std::getenv("GSLNLS_L2_NO_CARVEOUT")) {
+        // evict_last lines live in the persisting part of L2, which is empty until it is given a size
+        const size_t want = (size_t)(pb->l2_keep_mb * 1.0e6);
+        const size_t cap = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, cap));
+        cudaGetLastError();
+        if (std::getenv("GSLNLS_TRACE_E2E"))
+            std::fprintf(stderr, "persisting L2: asked %zu, device max %zu, L2 %d bytes\n", want, cap, prop.l2CacheSize);
+    }
     if (const char *c = std::getenv("GSLNLS_SERVER"))
         pb->allow_server = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
@@ -526,7 +536,9 @@ GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm)
         return GSLNLS_EINVAL;
     pb->comm = comm;
     pb->n_total = pb->n;
-    if (comm && comm->nranks > 1) {
+    if (comm && comm->nranks > 1 && comm->n_total_hint >= 0) {
+        pb->n_total = comm->n_total_hint; // single-process group: the caller split the rows itself
+    } else if (comm && comm->nranks > 1) {
         // global number of observations: gather the shard sizes once
         CK(cudaSetDevice(pb->device));
         const int R = comm->nranks;
@@ -1117,7 +1129,116 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
                                     want_resid_grad, out);
 }
 
-GSLNLS_API void gslnls_cache_clear(void) { cache_drop(nullptr); }
+// ---- one call, several GPUs, one process -------------------------------------------------------
+namespace {
+struct LocalGroup {
+    std::vector<int> devices;
+    std::vector<gslnls_comm *> comms;
+};
+std::mutex g_group_mu;
+LocalGroup g_group; // the last device group, kept for the next call (NCCL and peer-access setup are slow)
+} // namespace
+
+GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const *vars, const double *y,
+                                      const double *weights, int64_t n, const double *start,
+                                      const int *control_int, const double *control_dbl, int ngpu,
+                                      const int *devices, int want_resid_grad, gslnls_result *out)
+{
+    if (!m || !y || !start || !control_int || !control_dbl || !out || ngpu < 1 || ngpu > NLS_MAX_RANKS)
+        return GSLNLS_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    if (n < m->p) {
+        set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
+        return GSLNLS_EINVAL;
+    }
+    std::vector<int> dev(ngpu);
+    for (int r = 0; r < ngpu; ++r)
+        dev[r] = devices ? devices[r] : r;
+    // contiguous, 2-aligned row ranges (keeps every shard's columns 16-byte aligned); no empty shards
+    int R = (int)std::min<int64_t>(ngpu, std::max<int64_t>(1, n / 2));
+    if (R == 1)
+        return gslnls_fit_large_sharded(m, vars, y, weights, n, start, control_int, control_dbl, dev[0], nullptr,
+                                        want_resid_grad, out);
+    dev.resize(R);
+    int64_t per = (n + R - 1) / R;
+    per += per & 1;
+    std::lock_guard<std::mutex> lk(g_group_mu); // one multi-GPU fit at a time per process
+    if (g_group.devices != dev) {
+        for (gslnls_comm *c : g_group.comms)
+            gslnls_comm_free(c);
+        g_group.comms.assign(R, nullptr);
+        g_group.devices.clear();
+        int rc = gslnls_comm_create_local(R, dev.data(), g_group.comms.data());
+        if (rc) {
+            g_group.comms.clear();
+            return rc;
+        }
+        g_group.devices = dev;
+    }
+    std::vector<gslnls_result> res(R);
+    std::vector<int> rcs(R, GSLNLS_SUCCESS);
+    std::vector<std::string> errs(R);
+    std::vector<std::thread> th;
+    const int nvar = m->nvar;
+    for (int r = 0; r < R; ++r) {
+        g_group.comms[r]->n_total_hint = n;
+        th.emplace_back([&, r] {
+            const int64_t lo = std::min<int64_t>(n, (int64_t)r * per), hi = std::min<int64_t>(n, lo + per);
+            std::vector<const double *> v(std::max(nvar, 1), nullptr);
+            for (int k = 0; k < nvar; ++k)
+                v[k] = vars[k] + lo;
+            rcs[r] = gslnls_fit_large_sharded(m, v.data(), y + lo, weights ? weights + lo : nullptr, hi - lo, start,
+                                              control_int, control_dbl, dev[r], g_group.comms[r], want_resid_grad,
+                                              &res[r]);
+            errs[r] = g_last_error;
+        });
+    }
+    for (std::thread &t : th)
+        t.join();
+    int rc = rcs[0];
+    for (int r = 0; r < R; ++r)
+        if (rcs[r] >= 1000 || rcs[r] == GSLNLS_EINVAL) {
+            rc = rcs[r];
+            set_error(errs[r]);
+            break;
+        }
+    if (rc >= 1000 || rc == GSLNLS_EINVAL) {
+        for (int r = 0; r < R; ++r)
+            gslnls_result_free(&res[r]);
+        return rc;
+    }
+    *out = res[0];
+    out->n_local = n;
+    if (want_resid_grad) {
+        // stitch the per-rank pieces: resid is n, grad is n x p column-major (src/nls_large.c:339-385)
+        const int p = m->p;
+        double *resid = (double *)std::malloc(sizeof(double) * (size_t)n);
+        double *grad = (double *)std::malloc(sizeof(double) * (size_t)n * p);
+        for (int r = 0; r < R; ++r) {
+            const int64_t lo = std::min<int64_t>(n, (int64_t)r * per), nl = res[r].n_local;
+            std::memcpy(resid + lo, res[r].resid, sizeof(double) * (size_t)nl);
+            for (int j = 0; j < p; ++j)
+                std::memcpy(grad + (size_t)j * n + lo, res[r].grad + (size_t)j * nl, sizeof(double) * (size_t)nl);
+        }
+        std::free(res[0].resid);
+        std::free(res[0].grad);
+        out->resid = resid;
+        out->grad = grad;
+    }
+    for (int r = 1; r < R; ++r)
+        gslnls_result_free(&res[r]);
+    return rc;
+}
+
+GSLNLS_API void gslnls_cache_clear(void)
+{
+    cache_drop(nullptr);
+    std::lock_guard<std::mutex> lk(g_group_mu);
+    for (gslnls_comm *c : g_group.comms)
+        gslnls_comm_free(c);
+    g_group.comms.clear();
+    g_group.devices.clear();
+}
 
 GSLNLS_API void gslnls_result_free(gslnls_result *r)
 {

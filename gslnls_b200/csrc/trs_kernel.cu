@@ -258,14 +258,11 @@ cudaError_t trs_launch_step(const trs::Params &P, double *state, const double *p
     } else if (P.p <= 32) {
         trs_step_warp<32><<<1, 32, smem, stream>>>(P, state, packet, req, partrace, ssrtrace, condtrace, ndone);
     } else if (P.p <= 100) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(trs_step_warp<100>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)warp_smem_bytes(100));
-            if (e != cudaSuccess)
-                return e;
-            attr_set = true;
-        }
+        // per device, and cheap: set it on every launch rather than remembering which devices have it
+        cudaError_t e = cudaFuncSetAttribute(trs_step_warp<100>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)warp_smem_bytes(100));
+        if (e != cudaSuccess)
+            return e;
         trs_step_warp<100><<<1, 32, smem, stream>>>(P, state, packet, req, partrace, ssrtrace, condtrace, ndone);
     } else {
         return cudaErrorInvalidValue;

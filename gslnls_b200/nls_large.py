@@ -340,7 +340,7 @@ class GslNls:
         """evaluate the fitted curve on new predictor values (on the device, like everything O(n))"""
         cols = [np.ascontiguousarray(newdata[v], dtype=np.float64) for v in self._model.var_names]
         n = cols[0].size if cols else 1
-        pb = Problem(self._model, n, False, self._problem.device)
+        pb = Problem(self._model, n, False, self._problem.device if self._problem is not None else self._device)
         pb.upload(cols, np.zeros(n))
         out = pb.residuals(self.cfit["par"])
         pb.close()
@@ -356,8 +356,30 @@ class GslNls:
                     self.convInfo["finTol"]))
 
 
+def fit_large_multi(model, cols, y, weights, start, algorithm="lm", control=None, trace=False, devices=(0,),
+                    want_resid_grad=False):
+    """gslnls_fit_large_multi(): one call, host arrays in, the rows split over `devices` inside the library
+    (one host thread and one PCIe link per GPU, packets over NVLink peer memory)"""
+    ctrl = gsl_nls_control() if control is None else control
+    ci, cd = pack_control(ctrl, algorithm, trace)
+    st = np.ascontiguousarray(start, dtype=np.float64)
+    cols = [np.ascontiguousarray(c, dtype=np.float64) for c in cols]
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    arr = (_lib.c_double_p * max(len(cols), 1))(*[_dptr(c) for c in cols])
+    dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+    res = _lib.Result()
+    rc = _lib.lib().gslnls_fit_large_multi(model.handle, arr, _dptr(y), _dptr(w) if w is not None else None, y.size,
+                                           _dptr(st), ci.ctypes.data_as(_lib.c_int_p), _dptr(cd), dev.size,
+                                           dev.ctypes.data_as(_lib.c_int_p), int(want_resid_grad), C.byref(res))
+    _lib.check(rc)
+    out = _result_to_dict(res, st.size, y.size, int(ci[0]), trace, want_resid_grad)
+    _lib.lib().gslnls_result_free(C.byref(res))
+    return out
+
+
 def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=None, fvv=None, trace=False,
-                  weights=None, y=None, device=0, comm=None, model=None, **kwargs):
+                  weights=None, y=None, device=0, comm=None, model=None, devices=None, **kwargs):
     """Fit a nonlinear least-squares model with the large-problem trust-region path on a B200.
 
     fn        two-sided formula text "y ~ A * exp(-lam * x) + b" (formula method, R/nls_large.R:135),
@@ -434,6 +456,14 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     st = np.array([float(start[k]) for k in pnames], dtype=np.float64)
 
     mdl = model if model is not None else Model(rhs, pnames, var_names, jac=jac, fvv=fvv)
+    if devices is not None and len(devices) > 1:
+        # several GPUs from this one process: the library splits the rows and runs one thread per GPU
+        cfit = fit_large_multi(mdl, cols, lhs, weights, st, algorithm, ctrl, bool(trace), devices,
+                               want_resid_grad=True)
+        obj = GslNls(fn, pnames, cfit, None, mdl, ctrl, algorithm, weights, lhs, bool(trace))
+        obj._resid = -cfit["resid"]
+        obj._device = int(devices[0])
+        return obj
     pb = Problem(mdl, lhs.size, weights is not None, device)
     pb.upload(cols, lhs, weights)
     if comm is not None:

@@ -138,6 +138,15 @@ GSLNLS_API int gslnls_fit_large_sharded(const gslnls_model *m, const double *con
                                         const double *weights, int64_t n_local, const double *start,
                                         const int *control_int, const double *control_dbl, int device,
                                         gslnls_comm *comm, int want_resid_grad, gslnls_result *out);
+/* The same call over several GPUs of the box from ONE process (what an R session is): the rows are split
+ * into ngpu contiguous shards, one host thread per GPU uploads its shard over that GPU's own PCIe link and
+ * runs the sharded fit; packets cross NVLink peer memory.  devices == NULL means 0..ngpu-1.  The result is
+ * the single-GPU result (resid/grad stitched back to n rows when requested).  This is the
+ * `int ngpu, const int *devices` form of the replacement for src/nls_large.c:66. */
+GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const *vars, const double *y,
+                                      const double *weights, int64_t n, const double *start,
+                                      const int *control_int, const double *control_dbl, int ngpu,
+                                      const int *devices, int want_resid_grad, gslnls_result *out);
 GSLNLS_API void gslnls_result_free(gslnls_result *r);
 /* gslnls_fit_large[_sharded] keeps the device buffers, workspace and streams of the last call per device
  * for the next one (same model); this returns them (also done for a model by gslnls_model_free).
@@ -205,6 +214,10 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
 /* rank 0 creates an id and ships it to the other ranks by any means (MPI, files, a process-group broadcast) */
 GSLNLS_API int gslnls_comm_get_unique_id(void *id_bytes /* GSLNLS_COMM_ID_BYTES */);
 GSLNLS_API int gslnls_comm_create(const void *id_bytes, int rank, int nranks, int device, gslnls_comm **out);
+/* every rank in ONE process (the shape an R session has): out[0..ndev-1] receive one context per device;
+ * the mailboxes are reached through CUDA peer access.  Each context is then driven by its own host thread
+ * (gslnls_fit_large_multi does that), or handed to gslnls_fit_large_sharded from ndev threads. */
+GSLNLS_API int gslnls_comm_create_local(int ndev, const int *devices, gslnls_comm **out);
 GSLNLS_API void gslnls_comm_free(gslnls_comm *c);
 /* 1 when the ranks exchange packets through NVLink peer memory (each pass kernel deposits its packet
  * directly in every GPU's mailbox and a resident trust-region warp consumes it); 0 when the exchange

@@ -51,3 +51,34 @@ def test_sharded_fit_matches_oracle(tmp_path, world, p2p):
         assert np.allclose(f["par"], ref["par"], rtol=1e-8), alg
         assert f["ssr"] == pytest.approx(ref["ssr"], rel=1e-8)
         assert f["n"] == n
+
+
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+@pytest.mark.parametrize("alg", ["lm", "lmaccel", "dogleg"])
+def test_single_process_multi_gpu_call(ngpu, alg):
+    """gslnls_fit_large_multi(): the one-call form an R session would use -- host arrays in, the library
+    splits the rows over the GPUs (one host thread per GPU, peer-memory mailboxes); same answer as the
+    oracle and as the single-GPU call, residuals/gradient stitched back to n rows"""
+    if _ngpu() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    import bench
+    from gslnls_b200 import gsl_nls_large
+    from oracle import oracle as O
+    n = 1_000_003
+    x, y = bench.synth_rows(0, n, n)
+    kw = dict(data={"x": x, "y": y}, start=dict(zip(["A", "lam", "b"], bench.START)), jac=True, fvv=True,
+              algorithm=alg)
+    multi = gsl_nls_large("y ~ A * exp(-lam * x) + b", devices=list(range(ngpu)), **kw)
+    single = gsl_nls_large("y ~ A * exp(-lam * x) + b", **kw)
+    ref = O.nls_large("exp3", y, list(bench.START), x=x, algorithm=alg)
+    assert multi.convInfo["isConv"] and multi.convInfo["finIter"] == ref["niter"] == single.convInfo["finIter"]
+    assert np.allclose(list(multi.coef().values()), ref["par"], rtol=1e-8)
+    assert multi.deviance() == pytest.approx(ref["ssr"], rel=1e-8)
+    assert multi.nobs() == n
+    assert np.allclose(multi.vcov(), single.vcov(), rtol=1e-8)
+    assert np.allclose(multi.residuals(), single.residuals(), rtol=1e-9, atol=1e-12)
+    assert multi.cfit["grad"].shape == (n, 3)
+    assert abs(np.sum(multi.residuals() ** 2) - multi.deviance()) <= 1e-9 * multi.deviance()
+    # twice in a row: the device group and the per-device buffers are reused
+    again = gsl_nls_large("y ~ A * exp(-lam * x) + b", devices=list(range(ngpu)), **kw)
+    assert list(again.coef().values()) == list(multi.coef().values())
