@@ -55,7 +55,8 @@ struct gslnls_model {
 };
 
 namespace gslnls {
-KernelTune default_tune(int p);
+// shard_bytes: bytes one pass reads on this GPU (0 = unknown / small); picks the load path of the p <= 4 kernel
+KernelTune default_tune(int p, double shard_bytes = 0.0);
 size_t tiled_smem_bytes(int p, int block, int nprod, int nconst); // dynamic shared memory of the tiled pass kernel
 size_t tma_smem_bytes(int narr, int block, int unroll, int stages); // dynamic shared memory of the TMA-staged pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture

@@ -119,10 +119,13 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             vec = 1;
     if ((reinterpret_cast<uintptr_t>(pb->dy) & 15u) || (pb->dw && (reinterpret_cast<uintptr_t>(pb->dw) & 15u)))
         vec = 1;
-    KernelTune t = default_tune(pb->p);
+    KernelTune t = default_tune(pb->p, batch ? 0.0 : 8.0 * (pb->nvar + 1 + pb->has_w) * (double)pb->n);
     if (t.tiled == 2 && (vec != 2 || batch)) { // bulk copies need 16-byte aligned columns; fall back to LDG
-        t.tiled = 0;
-        t.block = std::max(32, t.block - 32);
+        t = default_tune(pb->p, 0.0);
+        if (t.tiled == 2) { // forced through GSLNLS_TUNE
+            t.tiled = 0;
+            t.block = std::max(32, t.block - 32);
+        }
     }
     VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))

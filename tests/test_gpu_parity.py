@@ -291,3 +291,65 @@ def test_batched_multistart_inner_loops(G):
         if sign > 0 and np.isfinite(out["logdet"][c]) and np.linalg.cond(JTJ) < 1e8:
             assert out["logdet"][c] == pytest.approx(ld, rel=1e-6, abs=1e-6)
     pb.close()
+
+
+# ---------------------------------------------------------------- K1 load-path variants
+# The library picks the load path of the p <= 4 kernel by shard size: software-pipelined LDG below
+# ~1 GB per pass, the TMA bulk-copy shared-memory ring above.  Both must give the oracle's packet at
+# every size, ragged tails included, so each is forced here through the developer override.
+K1_VARIANTS = {
+    "ldg-prefetch": "tiled=0,block=256,unroll=3,minb=2,prefetch=1,fexp=1",
+    "ldg-plain-libexp": "tiled=0,block=256,unroll=4,minb=2,prefetch=0,fexp=0",
+    "tma-ring": "tiled=2,block=416,unroll=3,minb=1,stages=4,fexp=1",
+    "tma-ring-small": "tiled=2,block=96,unroll=1,minb=4,stages=2,fexp=2",
+}
+
+
+@pytest.mark.parametrize("variant", sorted(K1_VARIANTS))
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 2303, 2304, 2305, 4608, 100_003, 1_000_003])
+def test_packet_parity_k1_variants(G, monkeypatch, variant, n):
+    monkeypatch.setenv("GSLNLS_TUNE", K1_VARIANTS[variant])
+    x, y = synth_exp(n)
+    w = 0.5 + (np.arange(n) % 7) / 3.0
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    for weights in (None, w):
+        pb = G.Problem(m, n, has_weights=weights is not None).upload([x], y, weights)
+        theta = [4.0, 1.2, 0.8]
+        got = pb.eval_packet(theta)
+        ref = O.eval_packet("exp3", y, theta, x=x, weights=weights, longdouble=True)
+        assert rel_packet_err(got, ref, 3) < 1e-12, (variant, n, weights is not None)
+        assert np.array_equal(got, pb.eval_packet(theta))  # run-to-run bitwise
+        pb.close()
+
+
+@pytest.mark.parametrize("variant", ["tma-ring", "ldg-prefetch"])
+@pytest.mark.parametrize("alg", ["lm", "lmaccel", "cgst"])
+def test_fit_k1_variants(G, monkeypatch, variant, alg):
+    """full fits through each load path (FJ, FVV and JVP pass modes) against the oracle"""
+    monkeypatch.setenv("GSLNLS_TUNE", K1_VARIANTS[variant])
+    n = 300_007
+    x, y = synth_exp(n)
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    pb = G.Problem(m, n).upload([x], y)
+    fit = pb.fit([1.0, 1.0, 0.0], algorithm=alg)
+    ref = O.nls_large("exp3", y, [1.0, 1.0, 0.0], x=x, algorithm=alg)
+    _fit_cmp(fit, ref)
+    pb.close()
+
+
+def test_table_exp_special_values(G):
+    """the branch-free exp of the default kernels on overflow / underflow / NaN arguments: the
+    non-finite rule of src/nls_large.c:464-465 must see exactly what the library exp() would show it"""
+    n = 64
+    x = np.linspace(-1.0, 1.0, n)
+    y = np.zeros(n)
+    m = G.Model("A * exp(lam * x) + b", ["A", "lam", "b"], ["x"], jac=True)
+    pb = G.Problem(m, n).upload([x], y)
+    for theta in ([1.0, 800.0, 0.0], [1.0, 5000.0, 0.0], [1.0, 1e308, 0.0]):
+        got = pb.eval_packet(theta)
+        with np.errstate(over="ignore"):
+            f = theta[0] * np.exp(theta[1] * x) + theta[2]
+        nbad = int(np.sum(~np.isfinite(f)))
+        # packet layout: [JTJ(6) | JTf(3) | fTf]; any non-finite residual makes fTf = +Inf
+        assert (not np.isfinite(got[9])) == (nbad > 0), (theta, got[9], nbad)
+    pb.close()
