@@ -16,6 +16,10 @@ Rank 0 prints one JSON line.
 import argparse
 import json
 import os
+
+# NCCL writes its version / INFO lines to stdout by default; the contract is ONE JSON line there
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import subprocess
 import sys
 import threading
@@ -208,12 +212,20 @@ def main():
         """exactly k trial steps as back-to-back fits; returns (outer iterations, fits, last result)"""
         left, iters, fits, last, complete = k, 0, 0, None, None
         while left > 0:
+            t0 = time.perf_counter()
             pb.fit_begin(start, algorithm=args.algorithm, control=ctrl)
+            t1 = time.perf_counter()
             done, run = False, 0
             while not done and run < left:
                 done, r, _ = pb.fit_run(left - run)
                 run += r
+            t2 = time.perf_counter()
             last = pb.fit_end()
+            t3 = time.perf_counter()
+            host_us[0] += (t1 - t0) * 1e6
+            host_us[1] += (t2 - t1) * 1e6
+            host_us[2] += (t3 - t2) * 1e6
+            host_us[3] += 1
             # trailing no-op launches after convergence are not steps
             used = min(run, int(last["npass"]))
             left -= max(used, 1)
@@ -222,6 +234,8 @@ def main():
             if done:
                 complete = last
         return iters, fits, (complete or last)
+
+    host_us = [0.0, 0.0, 0.0, 0]
 
     def barrier():
         if world > 1:
@@ -237,6 +251,7 @@ def main():
     pb.set_profile(args.steps + 64)
     pb.channel_stats(reset=True)
     barrier()
+    host_us[:] = [0.0, 0.0, 0.0, 0]
     pb.timer_start()
     iters, fits, last = run_steps(args.steps)
     ms = pb.timer_stop()
@@ -309,6 +324,9 @@ def main():
                                "(BASELINE.json configs[2])" % (n, args.algorithm),
                    "n_per_gpu": n_loc, "fits": fits, "outer_iterations": iters,
                    "passes_per_iteration": args.steps / max(iters, 1),
+                   "host_us_per_fit": {"fit_begin": host_us[0] / max(host_us[3], 1),
+                                       "fit_run": host_us[1] / max(host_us[3], 1),
+                                       "fit_end": host_us[2] / max(host_us[3], 1)},
                    "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
                    "final": {"par": [float(v) for v in last["par"]], "ssr": float(last["ssr"]),
                              "niter": int(last["niter"]), "status": last["status"]},
