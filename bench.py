@@ -19,6 +19,9 @@ import os
 
 # NCCL writes its version / INFO lines to stdout by default; the contract is ONE JSON line there
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# CUDA-event pairs around every 4th pass launch inside the timed region give roofline.avg_launch_ms; an event
+# record between every two launches would cost each step a few microseconds of stream serialisation
+os.environ.setdefault("GSLNLS_PROF_STRIDE", "4")
 
 import subprocess
 import sys
@@ -342,7 +345,9 @@ def main():
                      "frac": achieved / peak if achieved else None,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                      "kernel": "nls_pass (K1)", "algorithmic_bytes_per_launch": alg_bytes,
-                     "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt), "peak_source": peak_src,
+                     "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt),
+                     "launch_sampling": "every %s-th pass launch of the timed region" % os.environ["GSLNLS_PROF_STRIDE"],
+                     "peak_source": peak_src,
                      "note": "avg_launch_ms = CUDA-event time of the nls_pass launches inside the timed region; in "
                              "resident-server mode a launch starts by waiting (in-kernel) for the trust-region warp's "
                              "request, so it spans wait + stream + grid reduction; stream_us / step_us are the device "

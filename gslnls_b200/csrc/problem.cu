@@ -48,6 +48,11 @@ struct gslnls_problem {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     // optional per-pass timing (bench.py roofline): event pairs around K1 launches
     bool profile = false;
+    int prof_stride = 1;          // time every prof_stride-th pass launch (event records between launches cost a few us)
+    int64_t prof_seen = 0;
+    bool prev_pass_plain = false; // the previous operation on the stream was an untimed pass launch of this fit
+    bool use_pdl = false;         // GSLNLS_PDL=1: back-to-back pass launches use programmatic dependent launch
+                                  // (measured on B200: no effect at any shard size, so off)
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     int *d_prof_flags = nullptr; // one word per timed launch: did it stream, or was it an idle no-op
@@ -83,7 +88,7 @@ struct gslnls_problem {
     std::vector<double> start;
     double h_df = 0, h_fvv = 0;
     int64_t launches = 0, passes = 0;
-    int chunk = 8;
+    int chunk = 4;
     double l2_keep_mb = 0.0; // megabytes of the shard's head kept in L2 between passes (0: no cache hints)
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
@@ -92,6 +97,8 @@ struct gslnls_problem {
     cudaStream_t srv_stream = nullptr, ctl_stream = nullptr;
     cudaEvent_t ev_reset = nullptr, ev_chunk[2] = {nullptr, nullptr};
     int *h_flags = nullptr, *d_flags = nullptr; // mapped pinned: [0] done (1) / watchdog (2)
+    double *h_state = nullptr, *d_hstate = nullptr; // mapped pinned: the server's final state record
+    int h_state_cap = 0;
     unsigned long long watchdog_ns = 60000000000ull;
 };
 
@@ -241,18 +248,39 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
                 prm.peer_channel[r] = pb->comm->peer_channel[r];
         }
     }
-    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size();
+    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size() &&
+                       (pb->prof_seen++ % std::max(pb->prof_stride, 1)) == 0;
     if (timed)
         prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
     void *args[] = {&prm};
     if (timed)
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
-    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
-                        pb->var->pass_smem, pb->stream));
+    if (pb->server_on && pb->use_pdl && pb->prev_pass_plain && !timed) {
+        // Resident mode orders consecutive passes through the device channel (pass k+1 waits in-kernel for
+        // request k+1, which exists only after packet k is complete), so stream order between two pass
+        // launches is redundant: programmatic dependent launch lets the next grid become resident while
+        // the previous one drains, which takes launch latency and grid ramp-up off the step.
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(pb->grid_x, ncand, 1);
+        cfg.blockDim = dim3(pb->vkey.block, 1, 1);
+        cfg.dynamicSmemBytes = pb->var->pass_smem;
+        cfg.stream = pb->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelExC(&cfg, (const void *)pb->var->pass, args));
+    } else {
+        CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
+                            pb->var->pass_smem, pb->stream));
+    }
     if (timed) {
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
         pb->prof_used += 2;
     }
+    pb->prev_pass_plain = pb->server_on && !timed;
     ++pb->launches;
     ++pb->passes;
     return GSLNLS_SUCCESS;
@@ -435,6 +463,10 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
         if (std::getenv("GSLNLS_TRACE_E2E"))
             std::fprintf(stderr, "persisting L2: asked %zu, device max %zu, L2 %d bytes\n", want, cap, prop.l2CacheSize);
     }
+    if (const char *c = std::getenv("GSLNLS_PDL"))
+        pb->use_pdl = std::atoi(c) != 0;
+    if (const char *c = std::getenv("GSLNLS_PROF_STRIDE"))
+        pb->prof_stride = std::max(1, std::atoi(c));
     if (const char *c = std::getenv("GSLNLS_SERVER"))
         pb->allow_server = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
@@ -461,6 +493,7 @@ GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
     cudaFree(pb->own_channel);
     cudaFree(pb->d_prof_flags);
     cudaFreeHost(pb->h_flags);
+    cudaFreeHost(pb->h_state);
     cudaEventDestroy(pb->ev_reset);
     cudaEventDestroy(pb->ev_chunk[0]);
     cudaEventDestroy(pb->ev_chunk[1]);
@@ -740,6 +773,13 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
     rc = prepare(pb, 1, ntrace, false, use_server);
     if (rc)
         return rc;
+    if (use_server && pb->h_state_cap < pb->state_stride) {
+        cudaFreeHost(pb->h_state);
+        pb->h_state = nullptr;
+        CK(cudaHostAlloc(&pb->h_state, sizeof(double) * pb->state_stride, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&pb->d_hstate, pb->h_state, 0));
+        pb->h_state_cap = pb->state_stride;
+    }
     if (use_server && !sharded && !pb->own_channel) {
         CK(cudaMalloc(&pb->own_channel, NLS_CH_BYTES));
         CK(cudaMemsetAsync(pb->own_channel, 0, NLS_CH_BYTES, pb->stream));
@@ -766,13 +806,14 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
         pb->h_flags[0] = 0;
         CK(trs_launch_server(pb->P, channel_of(pb), sharded ? pb->comm->nranks : 1, pb->pk_stride, pb->d_state,
                              pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr, tr ? pb->d_ssrtrace : nullptr,
-                             tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->watchdog_ns,
+                             tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->d_hstate, pb->watchdog_ns,
                              pb->srv_stream));
         pb->launches += 2;
         pb->server_on = true;
     }
     pb->active = true;
     pb->passes = 0;
+    pb->prev_pass_plain = false;
     return GSLNLS_SUCCESS;
 }
 
@@ -787,6 +828,7 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
     int64_t run = 0;
     int fin = 0;
     CK(cudaEventRecord(pb->ev0, pb->stream));
+    pb->prev_pass_plain = false;
     if (pb->server_on) {
         // keep two chunks of pass launches in flight; the only host work per chunk is waiting for the
         // older chunk's event and looking at the done word the server writes into mapped host memory
@@ -803,15 +845,25 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             }
             run += todo;
             CK(cudaEventRecord(pb->ev_chunk[slot], pb->stream));
+            pb->prev_pass_plain = false;
             slot ^= 1;
             if (++inflight == 2) {
-                CK(cudaEventSynchronize(pb->ev_chunk[slot]));
+                // wait for the older chunk -- or for the done word, whichever comes first
+                cudaError_t q;
+                while ((q = cudaEventQuery(pb->ev_chunk[slot])) == cudaErrorNotReady && pb->h_flags[0] == 0) {
+                }
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    CK(q);
                 --inflight;
             }
             fin = pb->h_flags[0] != 0;
         }
-        CK(cudaEventRecord(pb->ev1, pb->stream));
-        CK(cudaEventSynchronize(pb->ev1));
+        if (!fin || device_ms) {
+            // a finished fit needs no synchronisation: its state record is already in host memory and the
+            // launches still queued are no-ops that the next fit's launches simply follow
+            CK(cudaEventRecord(pb->ev1, pb->stream));
+            CK(cudaEventSynchronize(pb->ev1));
+        }
         if (!fin) {
             // the last pass has left the stream; its step may still be running in the server
             int rc = wait_server_caught_up(pb);
@@ -878,18 +930,25 @@ GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, g
     CK(cudaSetDevice(pb->device));
     const int p = pb->p;
     std::memset(out, 0, sizeof(*out));
-    if (pb->server_on) {
-        // wait until the server has digested every pass that was launched (request seq = passes + 1),
-        // then let it go; an unfinished fit leaves its state record current
-        CK(cudaStreamSynchronize(pb->stream));
-        int rc = wait_server_caught_up(pb);
-        if (rc)
-            return rc;
-        stop_server(pb);
-    }
     std::vector<double> S(pb->state_stride);
-    CK(cudaMemcpyAsync(S.data(), pb->d_state, sizeof(double) * pb->state_stride, cudaMemcpyDeviceToHost, pb->stream));
-    CK(cudaStreamSynchronize(pb->stream));
+    if (pb->server_on && pb->h_flags[0] == 1) {
+        // finished fit: the server left its final state record in mapped host memory before raising the
+        // done word; nothing to copy, nothing to wait for
+        std::memcpy(S.data(), pb->h_state, sizeof(double) * pb->state_stride);
+        pb->server_on = false;
+    } else {
+        if (pb->server_on) {
+            // wait until the server has digested every pass that was launched (request seq = passes + 1),
+            // then let it go; an unfinished fit leaves its state record current
+            CK(cudaStreamSynchronize(pb->stream));
+            int rc = wait_server_caught_up(pb);
+            if (rc)
+                return rc;
+            stop_server(pb);
+        }
+        CK(cudaMemcpyAsync(S.data(), pb->d_state, sizeof(double) * pb->state_stride, cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+    }
     pb->active = false;
 
     int status = (int)S[trs::S_STATUS];
@@ -1003,6 +1062,7 @@ GSLNLS_API int gslnls_problem_set_profile(gslnls_problem *pb, int max_passes)
     CK(cudaSetDevice(pb->device));
     pb->profile = max_passes > 0;
     pb->prof_used = 0;
+    pb->prof_seen = 0;
     while (pb->prof_ev.size() < (size_t)2 * (size_t)std::max(max_passes, 0)) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));

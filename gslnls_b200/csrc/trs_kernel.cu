@@ -73,7 +73,8 @@ template <int PMAX, bool FIXED>
 __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *channel, int nranks, int pk_count,
                                                  double *state, double *packet, double *req, double *partrace,
                                                  double *ssrtrace, double *condtrace, int *ndone,
-                                                 volatile int *host_flags, unsigned long long watchdog_ns)
+                                                 volatile int *host_flags, double *host_state,
+                                                 unsigned long long watchdog_ns)
 {
     extern __shared__ double trs_smem[];
     const int lane = threadIdx.x & 31;
@@ -149,6 +150,15 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
             tm[4] += 1ull;
         }
         if (S.phase == trs::PH_DONE) {
+            // the final state record goes straight to mapped host memory, then the done word: the host
+            // needs no copy and no stream synchronisation to return the result
+            if (host_state) {
+                const int ns = trs::state_doubles(P.p);
+                for (int e = lane; e < ns; e += 32)
+                    host_state[e] = __ldcg(state + e);
+            }
+            __threadfence_system();
+            __syncwarp();
             if (lane == 0) {
                 atomicAdd(ndone, 1);
                 __threadfence_system();
@@ -224,12 +234,13 @@ cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream)
 
 cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
                               double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
-                              int *ndone, int *host_flags_dev, unsigned long long watchdog_ns, cudaStream_t stream)
+                              int *ndone, int *host_flags_dev, double *host_state_dev, unsigned long long watchdog_ns,
+                              cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * 2 * (size_t)P.p * P.p;
 #define TRS_SERVER_LAUNCH(PM, FX)                                                                                  \
     trs_server<PM, FX><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace, \
-                                                condtrace, ndone, host_flags_dev, watchdog_ns)
+                                                condtrace, ndone, host_flags_dev, host_state_dev, watchdog_ns)
     if (P.p == 2)
         TRS_SERVER_LAUNCH(2, true);
     else if (P.p == 3)

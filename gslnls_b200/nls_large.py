@@ -157,11 +157,13 @@ class Problem:
         _lib.check(_lib.lib().gslnls_problem_fit_begin(self.handle, _dptr(st), ci.ctypes.data_as(_lib.c_int_p),
                                                        _dptr(cd)))
 
-    def fit_run(self, max_passes=0):
+    def fit_run(self, max_passes=0, want_ms=False):
+        """run up to max_passes trial steps; want_ms=True also returns the device time of the call, which
+        costs a stream synchronisation that a finished fit otherwise does not need"""
         done, run, ms = C.c_int(), C.c_int64(), C.c_float()
         _lib.check(_lib.lib().gslnls_problem_fit_run(self.handle, int(max_passes), C.byref(done), C.byref(run),
-                                                     C.byref(ms)))
-        return bool(done.value), run.value, ms.value
+                                                     C.byref(ms) if want_ms else None))
+        return bool(done.value), run.value, (ms.value if want_ms else None)
 
     def fit_end(self, want_resid_grad=False):
         p, maxiter, trace = self._fit
