@@ -353,3 +353,61 @@ def test_table_exp_special_values(G):
         # packet layout: [JTJ(6) | JTf(3) | fTf]; any non-finite residual makes fTf = +Inf
         assert (not np.isfinite(got[9])) == (nbad > 0), (theta, got[9], nbad)
     pb.close()
+
+
+# ---------------------------------------------------------------- one-shot call and its cache
+def _one_shot(G, m, x, y, start, alg="lm", weights=None, want_rg=False):
+    import ctypes as C
+    from gslnls_b200 import _lib
+    ci, cd = G.pack_control(G.gsl_nls_control(), alg, False)
+    st = np.ascontiguousarray(start, dtype=np.float64)
+    arr = (_lib.c_double_p * 1)(x.ctypes.data_as(_lib.c_double_p))
+    res = _lib.Result()
+    rc = _lib.lib().gslnls_fit_large(m.handle, arr, y.ctypes.data_as(_lib.c_double_p),
+                                     weights.ctypes.data_as(_lib.c_double_p) if weights is not None else None,
+                                     y.size, st.ctypes.data_as(_lib.c_double_p), ci.ctypes.data_as(_lib.c_int_p),
+                                     cd.ctypes.data_as(_lib.c_double_p), 0, int(want_rg), C.byref(res))
+    _lib.check(rc)
+    out = {"par": [res.par[i] for i in range(st.size)], "ssr": res.ssr, "niter": res.niter, "conv": res.conv,
+           "n": res.n, "status": res.status.decode()}
+    if want_rg:
+        out["resid"] = np.ctypeslib.as_array(res.resid, shape=(y.size,)).copy()
+    _lib.lib().gslnls_result_free(C.byref(res))
+    return out
+
+
+def test_one_shot_call_reuses_cached_buffers_correctly(G):
+    """gslnls_fit_large() keeps device buffers / workspace / streams per device between calls: results must
+    not depend on what the previous call was (smaller n, larger n, weights on and off, another model)"""
+    from gslnls_b200 import _lib
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    m2 = G.Model("A * exp(-lam * x)", ["A", "lam"], ["x"], jac=True)
+    start = [1.0, 1.0, 0.0]
+    seen = {}
+    for rnd in range(2):
+        for n in (50_001, 1_000, 200_000, 25):
+            x, y = synth_exp(n, seed=n)
+            w = 0.5 + (np.arange(n) % 5) / 4.0
+            for weights in (None, w):
+                got = _one_shot(G, m, x, y, start, weights=weights, want_rg=(n <= 1000))
+                key = (n, weights is not None)
+                if key not in seen:
+                    ref = O.nls_large("exp3", y, start, x=x, algorithm="lm", weights=weights)
+                    assert got["conv"] == ref["conv"] and got["niter"] == ref["niter"], key
+                    assert np.allclose(got["par"], ref["par"], rtol=1e-8), key
+                    assert got["ssr"] == pytest.approx(ref["ssr"], rel=1e-8)
+                    if "resid" in got:
+                        assert abs(np.sum(got["resid"] ** 2) - got["ssr"]) <= 1e-10 * got["ssr"]
+                    seen[key] = got
+                else:  # second round: bitwise the same answer out of recycled buffers
+                    assert got["par"] == seen[key]["par"] and got["ssr"] == seen[key]["ssr"], key
+            other = _one_shot(G, m2, x, y - 1.0, [1.0, 1.0])  # another model evicts the cached problem
+            assert other["n"] == n
+    _lib.lib().gslnls_cache_clear()
+    x, y = synth_exp(1000, seed=1000)
+    again = _one_shot(G, m, x, y, start)
+    assert again["par"] == seen[(1000, False)]["par"]
+    # freeing a model drops what was cached for it (no dangling kernels): a fresh model fits again
+    del m2
+    m3 = G.Model("A * exp(-lam * x)", ["A", "lam"], ["x"], jac=True)
+    assert _one_shot(G, m3, x, y - 1.0, [1.0, 1.0])["conv"] in (0, 11, 27)
