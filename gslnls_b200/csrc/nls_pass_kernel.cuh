@@ -741,12 +741,15 @@ static __device__ __forceinline__ void nls_packet_publish(const NlsPassParams &p
             tm[1] = __ldcg(tm + 1) + (nls_globaltimer() - __ldcg(tm));
             tm[2] = __ldcg(tm + 2) + 1ull;
             *(unsigned long long *)(prm.channel + NLS_CH_PASS_CTR) = seq;
-            if (prm.nranks > 1) {
-                for (int q = 0; q < prm.nranks; ++q)
-                    nls_st_release_sys((unsigned long long *)(prm.peer_channel[q] + NLS_CH_FLAGS + 128 * prm.rank), seq);
-            } else {
-                nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_FLAGS + 128 * prm.rank), seq);
-            }
+        }
+        if (prm.nranks > 1) {
+            // one lane per peer: the release stores (each is a system-scope fence + store, i.e. one NVLink
+            // round trip) go out side by side.  Issued one after the other by a single thread they cost
+            // ~2 us per rank: 17 us of every 79 us step on 8 GPUs.
+            if ((int)threadIdx.x < prm.nranks)
+                nls_st_release_sys((unsigned long long *)(prm.peer_channel[threadIdx.x] + NLS_CH_FLAGS + 128 * prm.rank), seq);
+        } else if (threadIdx.x == 0) {
+            nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_FLAGS + 128 * prm.rank), seq);
         }
         return;
     }

@@ -134,6 +134,25 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             t.block = std::max(32, t.block - 32);
         }
     }
+    if (t.tiled == 2) {
+        // the ring must fit one SM's shared memory whatever the number of columns: fewer stages first,
+        // then shorter tiles, and the LDG path when even two stages of the shortest tile do not fit
+        const int narr = pb->nvar + 1 + pb->has_w;
+        const size_t budget = 200 * 1024;
+        while (tma_smem_bytes(narr, t.block, t.unroll, t.stages) > budget && t.stages > 3)
+            --t.stages;
+        while (tma_smem_bytes(narr, t.block, t.unroll, t.stages) > budget && t.unroll > 1)
+            --t.unroll;
+        while (tma_smem_bytes(narr, t.block, t.unroll, t.stages) > budget && t.stages > 2)
+            --t.stages;
+        if (tma_smem_bytes(narr, t.block, t.unroll, t.stages) > budget) {
+            t = default_tune(pb->p, 0.0);
+            if (t.tiled == 2) {
+                t.tiled = 0;
+                t.block = std::max(32, t.block - 32);
+            }
+        }
+    }
     VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;

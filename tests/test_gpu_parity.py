@@ -411,3 +411,28 @@ def test_one_shot_call_reuses_cached_buffers_correctly(G):
     del m2
     m3 = G.Model("A * exp(-lam * x)", ["A", "lam"], ["x"], jac=True)
     assert _one_shot(G, m3, x, y - 1.0, [1.0, 1.0])["conv"] in (0, 11, 27)
+
+
+def test_tma_ring_shrinks_to_fit_many_columns(G, monkeypatch):
+    """three predictors + response + weights = 5 columns: the default 4-stage ring of 2304-row tiles would
+    need 369 KB of shared memory; the library must shrink it (or fall back) and still match the oracle"""
+    monkeypatch.setenv("GSLNLS_TUNE", K1_VARIANTS["tma-ring"])
+    rng = np.random.Generator(np.random.Philox(key=11))
+    n = 200_003
+    x1, x2, x3 = rng.uniform(0, 2, n), rng.uniform(-1, 1, n), rng.uniform(0.5, 1.5, n)
+    y = 2.0 * np.exp(-0.7 * x1) + 0.5 * x2 * x3 + 0.1 * rng.standard_normal(n)
+    w = 0.5 + (np.arange(n) % 3) / 2.0
+    m = G.Model("a * exp(-b * x1) + c * x2 * x3", ["a", "b", "c"], ["x1", "x2", "x3"], jac=True)
+    pb = G.Problem(m, n, has_weights=True).upload([x1, x2, x3], y, w)
+    a, b, c = theta = np.array([1.5, 0.5, 0.3])
+    got = pb.eval_packet(theta)
+    e = np.exp(-b * x1)
+    sw = np.sqrt(w)
+    r = (a * e + c * x2 * x3 - y) * sw
+    Jw = np.stack([e, -a * x1 * e, x2 * x3], axis=1) * sw[:, None]
+    JTJ = Jw.T @ Jw
+    ref = np.concatenate([JTJ[np.tril_indices(3)], Jw.T @ r, [r @ r]])
+    assert rel_packet_err(got, ref, 3) < 1e-10  # numpy double sums here, not the long-double oracle
+    fit = pb.fit([1.0, 1.0, 0.0])
+    assert fit["conv"] == 0 and np.allclose(fit["par"], [2.0, 0.7, 0.5], rtol=2e-2)
+    pb.close()
