@@ -39,8 +39,7 @@ struct NlsPassParams {
     char *channel;                    // this GPU's channel block
     char *peer_channel[NLS_MAX_RANKS];// every rank's channel block as mapped on this GPU ([rank] == channel)
     int rank;
-    int l2_keep_rows;                 // the first rows of the shard are loaded with an L2 evict_last policy (they stay
-                                      // in the 126 MB L2 from pass to pass), the rest evict_first; 0 = no cache hints
+    int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
     // two-level grid reduction (single-candidate launches): CTAs in groups of NLS_RED_GROUP, the last
     // arriver of a group sums the group's partials, the last group sums the group sums

@@ -20,7 +20,8 @@
 //
 // Tunables (NVRTC -D): NLS_BLOCK threads per CTA, NLS_UNROLL independent loads in flight per
 // thread and array, NLS_MINB CTAs per SM for __launch_bounds__, NLS_VEC 2 = 16-byte loads (needs
-// 16-byte aligned columns) or 1, NLS_HAS_W weights present, NLS_STREAM 1 = L1::no_allocate loads.
+// 16-byte aligned columns) or 1, NLS_HAS_W weights present, NLS_STREAM 1 = L1::no_allocate loads,
+// NLS_PREFETCH software-pipelined loads, NLS_TILED 2 + NLS_STAGES the TMA ring, NLS_FAST_EXP the exp() flavour.
 #include "nls_abi.h"
 
 #ifndef NLS_BLOCK
@@ -69,32 +70,7 @@ static __device__ __forceinline__ double2 nls_ld2(const double *p)
 #endif
     return r;
 }
-#if NLS_STREAM == 2
-// NLS_STREAM 2: every pass re-reads the same columns, so the head of the shard is loaded with an L2
-// evict_last policy (it is still in the 126 MB L2 when the next pass starts) and the rest with
-// evict_first (it cannot fit and must not displace the head)
-struct NlsL2Policy {
-    unsigned long long keep, stream;
-    long long keep_rows;
-};
-static __device__ __forceinline__ NlsL2Policy nls_l2_policy(long long keep_rows)
-{
-    NlsL2Policy P;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(P.keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(P.stream));
-    P.keep_rows = keep_rows;
-    return P;
-}
-static __device__ __forceinline__ double2 nls_ld2(const double *p, unsigned long long pol)
-{
-    double2 r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o), l2pol)
-#else
 #define NLS_LD2(ptr, o) nls_ld2((ptr) + (o))
-#endif
 static __device__ __forceinline__ double nls_ld1(const double *p)
 {
     double r;
@@ -273,9 +249,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
 #if NLS_VEC == 2
     const long long nv = n >> 1;
-#if NLS_STREAM == 2
-    const NlsL2Policy L2P = nls_l2_policy(prm.l2_keep_rows);
-#endif
     i += lo >> 1;
 #if NLS_PREFETCH
     // software pipeline: the loads of trip k+1 are issued before the arithmetic of trip k, so every
@@ -284,9 +257,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     if (i + (NLS_UNROLL - 1) * stride < nv) {
         double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
         double2 xn[NLS_UNROLL][NLS_NV], yn[NLS_UNROLL], wn[NLS_UNROLL];
-#if NLS_STREAM == 2
-        unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
-#endif
 #pragma unroll
         for (int u = 0; u < NLS_UNROLL; ++u) {
             const long long o = 2 * (i + u * stride);
@@ -304,9 +274,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
             const long long j = i + NLS_UNROLL * stride;
             const bool more = j + (NLS_UNROLL - 1) * stride < nv;
             if (more) {
-#if NLS_STREAM == 2
-                l2pol = 2 * j < L2P.keep_rows ? L2P.keep : L2P.stream;
-#endif
 #pragma unroll
                 for (int u = 0; u < NLS_UNROLL; ++u) {
                     const long long o = 2 * (j + u * stride);
@@ -348,10 +315,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #else
     for (; i + (NLS_UNROLL - 1) * stride < nv; i += NLS_UNROLL * stride) {
         double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
-#if NLS_STREAM == 2
-        // one policy per loop trip (decided on the trip's first row): the boundary is fuzzy, nobody cares
-        const unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
-#endif
 #pragma unroll
         for (int u = 0; u < NLS_UNROLL; ++u) {
             const long long o = 2 * (i + u * stride);
@@ -384,9 +347,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     // what a 200 MB shard of an 8-GPU run spent 10 % of its pass on)
     if (i < nv) {
         double2 xt[NLS_UNROLL - 1][NLS_NV], yt[NLS_UNROLL - 1], wt[NLS_UNROLL - 1];
-#if NLS_STREAM == 2
-        const unsigned long long l2pol = 2 * i < L2P.keep_rows ? L2P.keep : L2P.stream;
-#endif
 #pragma unroll
         for (int u = 0; u < NLS_UNROLL - 1; ++u) {
             const long long o = 2 * (i + u * stride);
@@ -422,9 +382,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
 #else
     for (; i < nv; i += stride) {
         const long long o = 2 * i;
-#if NLS_STREAM == 2
-        const unsigned long long l2pol = o < L2P.keep_rows ? L2P.keep : L2P.stream;
-#endif
         double xa[NLS_NV], xb[NLS_NV];
 #pragma unroll
         for (int k = 0; k < GSLNLS_NVAR; ++k) {
@@ -536,8 +493,7 @@ static __device__ __forceinline__ void nls_bar_wait(unsigned long long *bar, uns
                  "NLS_DONE_%=:\n"
                  "}" ::"r"(nls_saddr(bar)), "r"(parity) : "memory");
 }
-// NLS_TMA_HINT 1: the bulk copies carry an L2 evict_first policy (evict_last for the first l2_keep_rows
-// rows).  The pass itself runs equally fast with or without (240.0 vs 240.4 us at n = 1e8), but without
+// NLS_TMA_HINT 1: the bulk copies carry an L2 evict_first policy.  The pass itself runs equally fast with or without (240.0 vs 240.4 us at n = 1e8), but without
 // the hint 1.6 GB of streamed columns push the trust-region server's state, packet and request lines out
 // of L2 and every step then starts with DRAM round trips: measured step latency 9.8 us (lm) / 18.7 us
 // (dogleg) without the hint, 6.3 / 9.0 us with it.
@@ -578,12 +534,8 @@ static __device__ __forceinline__ void nls_stream_tma(const NlsPassParams &prm, 
     int nbad = 0;
     if (warp == NLS_NCW) {
         if (lane == 0) {
-            // every pass re-reads the same columns: the head of the shard is asked to stay in L2
-            // (evict_last) so that it is served from there on the next pass, the rest -- which cannot
-            // fit -- streams through without displacing it (evict_first)
-            unsigned long long pol_stream, pol_keep;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            unsigned long long policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             int s = 0;
             unsigned ph = 1u; // a fresh barrier lets a wait on the "previous" phase through
             for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
@@ -591,7 +543,6 @@ static __device__ __forceinline__ void nls_stream_tma(const NlsPassParams &prm, 
                 nls_bar_expect_tx(full + s, (unsigned)(NLS_STAGE_DOUBLES * sizeof(double)));
                 double *dst = buf + (size_t)s * NLS_STAGE_DOUBLES;
                 const long long o = t * NLS_TILE;
-                const unsigned long long policy = o < (long long)prm.l2_keep_rows ? pol_keep : pol_stream;
 #pragma unroll
                 for (int k = 0; k < GSLNLS_NVAR; ++k)
                     nls_bulk_g2s(dst + k * NLS_TILE, prm.vars[k] + o, NLS_TILE * 8u, full + s, policy);

@@ -50,9 +50,6 @@ struct gslnls_problem {
     bool profile = false;
     int prof_stride = 1;          // time every prof_stride-th pass launch (event records between launches cost a few us)
     int64_t prof_seen = 0;
-    bool prev_pass_plain = false; // the previous operation on the stream was an untimed pass launch of this fit
-    bool use_pdl = false;         // GSLNLS_PDL=1: back-to-back pass launches use programmatic dependent launch
-                                  // (measured on B200: no effect at any shard size, so off)
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
     int *d_prof_flags = nullptr; // one word per timed launch: did it stream, or was it an idle no-op
@@ -89,7 +86,6 @@ struct gslnls_problem {
     double h_df = 0, h_fvv = 0;
     int64_t launches = 0, passes = 0;
     int chunk = 4;
-    double l2_keep_mb = 0.0; // megabytes of the shard's head kept in L2 between passes (0: no cache hints)
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
     bool allow_server = true, server_on = false;
@@ -153,7 +149,7 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             }
         }
     }
-    VariantKey key{pb->has_w, vec, batch ? 0 : ((pb->l2_keep_mb > 0 && vec == 2) ? 2 : 1), t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
+    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;
     try {
@@ -254,8 +250,6 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
         prm.group_partials = pb->d_gparts;
         prm.group_ticket = pb->d_gticket;
     }
-    if (pb->l2_keep_mb > 0 && ncand == 1) // rows of the shard's head that are asked to stay in L2
-        prm.l2_keep_rows = (int)std::min(2.0e9, pb->l2_keep_mb * 1.0e6 / (8.0 * (pb->nvar + 1 + pb->has_w)));
     prm.nranks = 1;
     if (pb->server_on) {
         prm.channel = channel_of(pb);
@@ -274,32 +268,12 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     void *args[] = {&prm};
     if (timed)
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
-    if (pb->server_on && pb->use_pdl && pb->prev_pass_plain && !timed) {
-        // Resident mode orders consecutive passes through the device channel (pass k+1 waits in-kernel for
-        // request k+1, which exists only after packet k is complete), so stream order between two pass
-        // launches is redundant: programmatic dependent launch lets the next grid become resident while
-        // the previous one drains, which takes launch latency and grid ramp-up off the step.
-        cudaLaunchConfig_t cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(pb->grid_x, ncand, 1);
-        cfg.blockDim = dim3(pb->vkey.block, 1, 1);
-        cfg.dynamicSmemBytes = pb->var->pass_smem;
-        cfg.stream = pb->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        CK(cudaLaunchKernelExC(&cfg, (const void *)pb->var->pass, args));
-    } else {
-        CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
-                            pb->var->pass_smem, pb->stream));
-    }
+    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
+                        pb->var->pass_smem, pb->stream));
     if (timed) {
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
         pb->prof_used += 2;
     }
-    pb->prev_pass_plain = pb->server_on && !timed;
     ++pb->launches;
     ++pb->passes;
     return GSLNLS_SUCCESS;
@@ -471,19 +445,6 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
     if (const char *c = std::getenv("GSLNLS_CHUNK"))
         pb->chunk = std::max(1, std::atoi(c));
-    if (const char *c = std::getenv("GSLNLS_L2_KEEP_MB"))
-        pb->l2_keep_mb = std::atof(c);
-    if (pb->l2_keep_mb > 0 && !std::getenv("GSLNLS_L2_NO_CARVEOUT")) {
-        // evict_last lines live in the persisting part of L2, which is empty until it is given a size
-        const size_t want = (size_t)(pb->l2_keep_mb * 1.0e6);
-        const size_t cap = (size_t)std::max(prop.persistingL2CacheMaxSize, 0);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, cap));
-        cudaGetLastError();
-        if (std::getenv("GSLNLS_TRACE_E2E"))
-            std::fprintf(stderr, "persisting L2: asked %zu, device max %zu, L2 %d bytes\n", want, cap, prop.l2CacheSize);
-    }
-    if (const char *c = std::getenv("GSLNLS_PDL"))
-        pb->use_pdl = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_PROF_STRIDE"))
         pb->prof_stride = std::max(1, std::atoi(c));
     if (const char *c = std::getenv("GSLNLS_SERVER"))
@@ -832,7 +793,6 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
     }
     pb->active = true;
     pb->passes = 0;
-    pb->prev_pass_plain = false;
     return GSLNLS_SUCCESS;
 }
 
@@ -842,12 +802,10 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
     if (!pb || !pb->active)
         return GSLNLS_EINVAL;
     CK(cudaSetDevice(pb->device));
-    const int p = pb->p;
     const bool tr = pb->P.trace != 0;
     int64_t run = 0;
     int fin = 0;
     CK(cudaEventRecord(pb->ev0, pb->stream));
-    pb->prev_pass_plain = false;
     if (pb->server_on) {
         // keep two chunks of pass launches in flight; the only host work per chunk is waiting for the
         // older chunk's event and looking at the done word the server writes into mapped host memory
@@ -864,8 +822,7 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             }
             run += todo;
             CK(cudaEventRecord(pb->ev_chunk[slot], pb->stream));
-            pb->prev_pass_plain = false;
-            slot ^= 1;
+                    slot ^= 1;
             if (++inflight == 2) {
                 // wait for the older chunk -- or for the done word, whichever comes first
                 cudaError_t q;
