@@ -60,6 +60,8 @@ struct SingleLane {
     TRS_HD int lane() const { return 0; }
     TRS_HD int nlanes() const { return 1; }
     TRS_HD void sync() const {}
+    TRS_HD double bcast(double v, int) const { return v; }
+    TRS_HD bool all(bool b) const { return b; }
 };
 
 #if defined(__CUDACC__)
@@ -67,6 +69,8 @@ struct WarpLanes {
     __device__ int lane() const { return threadIdx.x & 31; }
     __device__ int nlanes() const { return 32; }
     __device__ void sync() const { __syncwarp(); }
+    __device__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ bool all(bool b) const { return __all_sync(0xffffffffu, b) != 0; }
 };
 #endif
 
@@ -154,9 +158,40 @@ struct Solver {
         }
         return sqrt(e2);
     }
-    // y = JTJ v using the stored lower triangle (every lane computes all of y privately)
+    // p above which the lanes share the O(p^2) loops of symv() and solve_neg() instead of each running
+    // them privately; below it the private loops (vectors in registers) are faster
+    static constexpr int kCoopMinP = 9;
+    static constexpr int kSlots = (PMAX + 31) / 32;
+
+    // y = JTJ v using the stored lower triangle.  Small p: every lane computes all of y privately.
+    // Large p with a warp: lane l computes the elements j = l, l + 32, ... and the results are exchanged
+    // by shuffles.  Each element sees exactly the operations of the private loop in the same order
+    // (row part in k order, then the diagonal term, then the column part in i order), so both forms --
+    // and the one-lane host build the tests compare against -- give bitwise the same y.
     TRS_HD void symv(const double *v, double *y) const
     {
+        const int nl = L.nlanes();
+        if (nl > 1 && p >= kCoopMinP) {
+            const int ln = L.lane();
+            for (int q = 0; q * nl < p; ++q) {
+                const int j = q * nl + ln;
+                double yj = 0.0;
+                if (j < p) {
+                    double t2 = 0.0;
+                    for (int k = 0; k < j; ++k)
+                        t2 += JTJ[j * p + k] * v[k];
+                    yj += v[j] * JTJ[j * p + j] + t2;
+                    for (int i = j + 1; i < p; ++i)
+                        yj += v[i] * JTJ[i * p + j];
+                }
+                for (int l = 0; l < nl; ++l) {
+                    const double b = L.bcast(yj, l);
+                    if (q * nl + l < p)
+                        y[q * nl + l] = b;
+                }
+            }
+            return;
+        }
         for (int i = 0; i < p; ++i)
             y[i] = 0.0;
         for (int i = 0; i < p; ++i) {
@@ -205,9 +240,53 @@ struct Solver {
         factor_valid = (st == E_SUCCESS);
         return st;
     }
-    // out = -(L L^T)^-1 b, private substitution on the shared factor
+    // out = -(L L^T)^-1 b on the shared factor.  Small p: private substitution.  Large p with a warp: the
+    // substitutions run column by column, lane l owning the elements l, l + 32, ...; the finished
+    // component is broadcast by a shuffle and every lane updates its own elements.  Per element the
+    // subtractions happen in the order of the private loops (j ascending forward, i descending
+    // backward), so the result is bitwise the same.
     TRS_HD void solve_neg(const double *b, double *out) const
     {
+        const int nl = L.nlanes();
+        if (nl > 1 && p >= kCoopMinP) {
+            const int ln = L.lane();
+            double t[kSlots];
+            for (int q = 0; q < kSlots; ++q)
+                t[q] = (q * nl + ln < p) ? b[q * nl + ln] : 0.0;
+            for (int j = 0; j < p; ++j) { // forward: L z = b
+                const int oq = j / nl;
+                double own = 0.0;
+                for (int q = 0; q < kSlots; ++q)
+                    if (q == oq)
+                        own = t[q];
+                const double zj = L.bcast(own / A[j * p + j], j % nl);
+                out[j] = zj;
+                for (int q = 0; q < kSlots; ++q) {
+                    const int i = q * nl + ln;
+                    if (i > j && i < p)
+                        t[q] -= A[i * p + j] * zj;
+                }
+            }
+            for (int q = 0; q < kSlots; ++q)
+                t[q] = (q * nl + ln < p) ? out[q * nl + ln] : 0.0;
+            for (int i = p - 1; i >= 0; --i) { // backward: L^T x = z
+                const int oq = i / nl;
+                double own = 0.0;
+                for (int q = 0; q < kSlots; ++q)
+                    if (q == oq)
+                        own = t[q];
+                const double xi = L.bcast(own / A[i * p + i], i % nl);
+                out[i] = xi;
+                for (int q = 0; q < kSlots; ++q) {
+                    const int j = q * nl + ln;
+                    if (j < i)
+                        t[q] -= A[i * p + j] * xi;
+                }
+            }
+            for (int i = 0; i < p; ++i)
+                out[i] = -out[i];
+            return;
+        }
         for (int i = 0; i < p; ++i)
             out[i] = b[i];
         for (int i = 0; i < p; ++i) {
@@ -269,13 +348,15 @@ struct Solver {
     // ---------------------------------------------------------------- packet -> (JTJ, g, f2)
     // packet: [JTJ lower packed row-major | JTf | fTf].  Returns false if anything is non-finite
     // (the reference's NaN/Inf scan of jac, src/nls_large.c:515-522, on the reduced quantities).
+    // the lanes share the scan (a private short-circuit loop over the 1224 entries of a p = 48 packet is
+    // 1224 dependent global loads: 180 us of a 350 us step, measured)
     TRS_HD bool packet_finite(const double *pk) const
     {
         const int npk = p * (p + 1) / 2;
         bool ok = true;
-        for (int e = 0; e < npk + p; ++e)
-            ok = ok && finite_d(pk[e]);
-        return ok;
+        for (int e = L.lane(); e < npk + p; e += L.nlanes())
+            ok = ok & finite_d(pk[e]);
+        return L.all(ok);
     }
     TRS_HD void take_packet(const double *pk)
     {
