@@ -113,3 +113,55 @@ def test_selfstart_shapes_translate():
     # inst/unit_tests/unit_tests_gslnls.R:272-275 uses SSasymp with gsl_nls_large
     m = Model("SSasymp(x, Asym, R0, lrc)", ["Asym", "R0", "lrc"], ["x"], jac=True, fvv=True)
     assert "NLS_EXP(" in m.source
+
+
+@pytest.mark.skipif(_lib.lib().gslnls_device_count() > 0, reason="a GPU is present")
+def test_every_fit_entry_point_refuses_without_a_device():
+    """gslnls_fit_large / _sharded / _multi and the device-group constructor: a library error, no crash,
+    no silent CPU path"""
+    L = _lib.lib()
+    m = Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True)
+    x = np.linspace(0, 3, 32)
+    y = 2 * np.exp(-x) + 1
+    ci, cd = pack_control(gsl_nls_control(), "lm", False)
+    st = np.array([1.0, 1.0, 0.0])
+    arr = (_lib.c_double_p * 1)(x.ctypes.data_as(_lib.c_double_p))
+    dp = _lib.c_double_p
+    common = (y.size, st.ctypes.data_as(dp), ci.ctypes.data_as(_lib.c_int_p), cd.ctypes.data_as(dp))
+    res = _lib.Result()
+    rc = L.gslnls_fit_large(m.handle, arr, y.ctypes.data_as(dp), None, *common, 0, 0, C.byref(res))
+    assert rc == 1004 and not res.par
+    rc = L.gslnls_fit_large_sharded(m.handle, arr, y.ctypes.data_as(dp), None, *common, 0, None, 0, C.byref(res))
+    assert rc == 1004
+    dev = np.array([0, 1], dtype=np.int32)
+    rc = L.gslnls_fit_large_multi(m.handle, arr, y.ctypes.data_as(dp), None, *common, 2,
+                                  dev.ctypes.data_as(_lib.c_int_p), 0, C.byref(res))
+    assert rc >= 1000
+    out = (C.c_void_p * 2)()
+    assert L.gslnls_comm_create_local(2, dev.ctypes.data_as(_lib.c_int_p), out) >= 1000
+    assert not out[0] and not out[1]
+    # fewer observations than parameters is an argument error before any device is touched (R/nls_large.R:286)
+    rc = L.gslnls_fit_large_multi(m.handle, arr, y.ctypes.data_as(dp), None, 2, st.ctypes.data_as(dp),
+                                  ci.ctypes.data_as(_lib.c_int_p), cd.ctypes.data_as(dp), 2,
+                                  dev.ctypes.data_as(_lib.c_int_p), 0, C.byref(res))
+    assert rc == 4 and b"degrees of freedom" in L.gslnls_last_error()
+    L.gslnls_cache_clear()  # nothing cached: must be a no-op
+
+
+K1_TUNES = [
+    "tiled=0,block=256,unroll=3,minb=2,prefetch=1,fexp=1",      # LDG-pipelined default
+    "tiled=0,block=256,unroll=4,minb=2,prefetch=0,fexp=0",      # plain LDG, library exp
+    "tiled=2,block=416,unroll=3,minb=1,stages=4,fexp=1",        # TMA ring default
+    "tiled=2,block=96,unroll=1,minb=4,stages=2,fexp=2",         # smallest ring, polynomial exp
+]
+
+
+@pytest.mark.parametrize("tune", K1_TUNES)
+def test_nvrtc_compiles_every_k1_load_path_for_sm100a(monkeypatch, tune):
+    """both load paths of the p <= 4 pass kernel (and the exp flavours) compile for sm_100a without a GPU;
+    the developer override is how the GPU tests force each of them"""
+    monkeypatch.setenv("GSLNLS_TUNE", tune)
+    m = Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    assert "nls_model_fj" in m.source
+    m2 = Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac="center", fvv="fd")
+    assert "nls_model_f" in m2.source
