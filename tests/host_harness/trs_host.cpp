@@ -1,8 +1,11 @@
 // tests/host_harness/trs_host.cpp -- TEST INFRASTRUCTURE: compiles the device trust-region state
 // machine (gslnls_b200/csrc/trs_core.h) for the host with the SingleLane policy so that the CPU
 // test-suite can step it against the oracle without a GPU.  Never linked into libgslnls_b200.so.
+#include <barrier>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "../../gslnls_b200/csrc/trs_core.h"
@@ -44,6 +47,86 @@ long trs_host_fit(const trs_host_params *hp, const double *start, packet_cb cb, 
         ++n;
     }
     delete solver;
+    return n;
+}
+
+// ---- the warp, emulated: one host thread per lane --------------------------------------------
+// The device runs the state machine with 32 lanes that share the p x p matrices and the O(p^2) / O(p^3)
+// loops (trs::WarpLanes: __syncwarp, shuffles, votes).  Here every lane is a thread with its own Solver
+// (private vectors), the matrices are shared, sync() is a barrier, bcast() / all() go through a shared
+// exchange array.  Unlike a warp the threads are scheduled independently, so a missing sync() in
+// trs_core.h shows up here as a wrong answer (or under -fsanitize=thread) instead of going unnoticed.
+}  // extern "C"
+
+namespace {
+struct LaneShared {
+    explicit LaneShared(int n) : bar(n), xch(n), flag(n), n(n) {}
+    std::barrier<> bar;
+    std::vector<double> xch;
+    std::vector<int> flag;
+    int n;
+};
+struct ThreadLanes {
+    LaneShared *sh;
+    int id;
+    int lane() const { return id; }
+    int nlanes() const { return sh->n; }
+    void sync() const { sh->bar.arrive_and_wait(); }
+    double bcast(double v, int src) const
+    {
+        sh->xch[id] = v;
+        sync();
+        const double r = sh->xch[src];
+        sync();
+        return r;
+    }
+    bool all(bool b) const
+    {
+        sh->flag[id] = b ? 1 : 0;
+        sync();
+        bool r = true;
+        for (int i = 0; i < sh->n; ++i)
+            r = r && sh->flag[i] != 0;
+        sync();
+        return r;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+long trs_host_fit_lanes(const trs_host_params *hp, const double *start, packet_cb cb, void *ctx, double *state,
+                        double *partrace, double *ssrtrace, double *condtrace, long max_packets, int nlanes)
+{
+    trs::Params P;
+    P.p = hp->p; P.maxiter = hp->maxiter; P.trs = hp->trs; P.scale = hp->scale; P.trace = hp->trace;
+    P.batch_iters = hp->batch_iters; P.cg_maxit = hp->cg_maxit; P.factor_up = hp->factor_up;
+    P.factor_down = hp->factor_down; P.avmax = hp->avmax; P.h_df = hp->h_df; P.h_fvv = hp->h_fvv;
+    P.xtol = hp->xtol; P.ftol = hp->ftol; P.gtol = hp->gtol; P.cg_tol = hp->cg_tol;
+    const int p = P.p;
+    if (nlanes != 32)
+        return -1; // the lane-slot arithmetic of trs_core.h assumes a 32-wide warp
+    std::vector<double> req(trs::request_doubles(p)), pk(trs::packet_doubles(p) + 2), jtj(p * p), work(p * p);
+    trs::state_reset(state, req.data(), start, p);
+    typedef trs::Solver<128, ThreadLanes> S;
+    LaneShared shared(nlanes);
+    std::vector<std::unique_ptr<S>> solver;
+    for (int l = 0; l < nlanes; ++l)
+        solver.emplace_back(new S(P, ThreadLanes{&shared, l}, jtj.data(), work.data()));
+    long n = 0;
+    while ((int)state[trs::S_PHASE] != trs::PH_DONE && n < max_packets) {
+        const int mode = (int)req[0];
+        if (mode == trs::MODE_IDLE)
+            break;
+        if (cb(ctx, mode, req.data() + 1, req.data() + 1 + p, pk.data()))
+            break;
+        std::vector<std::thread> th;
+        for (int l = 0; l < nlanes; ++l)
+            th.emplace_back([&, l] { solver[l]->advance(state, pk.data(), req.data(), partrace, ssrtrace, condtrace); });
+        for (auto &t : th)
+            t.join();
+        ++n;
+    }
     return n;
 }
 }

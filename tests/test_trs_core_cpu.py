@@ -106,3 +106,66 @@ def test_boxbod_reproduces_reference_nan_norm_quirk(nist_problems):
         assert int(r["status"]) == o["conv"], alg
         assert int(r["niter"]) == o["niter"], alg
     assert O.nls_large(rows, data["y"], pr["start"], algorithm="dogleg")["conv"] == 9
+
+
+# ---------------------------------------------------------------- the warp, emulated on the host
+def _gaussmix_problem(K, n=400, seed=7):
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    x = np.linspace(0.0, 100.0, n)
+    th = []
+    for k in range(1, K + 1):
+        th += [5.0 + ((7 * k) % 11), 100.0 * (k - 0.5) / K, 2.5 * 16 / K]
+    th = np.array(th)
+    y = np.zeros(n)
+    for k in range(K):
+        y += th[3 * k] * np.exp(-((x - th[3 * k + 1]) ** 2) / th[3 * k + 2] ** 2)
+    y += 0.5 * rng.standard_normal(n)
+    start = th * (1.0 + 0.02 * (-1.0) ** np.arange(3 * K))
+    return x, y, start
+
+
+@pytest.mark.parametrize("K,alg", [(1, "lm"), (3, "lm"), (3, "dogleg"), (3, "lmaccel"), (3, "subspace2D"),
+                                   (3, "cgst"), (7, "ddogleg"), (16, "dogleg"), (16, "lm")])
+def test_thirty_two_lanes_walk_bitwise_the_single_lane_path(K, alg):
+    """On the device 32 lanes share the p x p matrices, the Cholesky factorisation and -- from p = 9 up -- the
+    symmetric matrix-vector product, the triangular solves and the packet scan (trs_core.h, WarpLanes).  The
+    host harness runs the same code with one thread per lane (barriers for __syncwarp, an exchange array for
+    the shuffles).  Every lane-shared loop keeps the per-element operation order of the private loop, so the
+    32-lane run must reproduce the one-lane run bit for bit: state record, traces, covariance.  p = 3, 9, 21,
+    48 cover both sides of the sharing threshold and one / two elements per lane."""
+    x, y, start = _gaussmix_problem(K)
+    p = 3 * K
+
+    def prov(mode, theta, v):
+        if mode == 1:
+            return O.eval_packet("gaussmix", y, theta, x=x)
+        rows = O.sympy_rows(" + ".join("a%d * exp(-(x - m%d)^2 / s%d^2)" % (k, k, k) for k in range(1, K + 1)),
+                            [n + str(k) for k in range(1, K + 1) for n in ("a", "m", "s")], {"x": x})
+        return T.packet_from_rows(rows, y)(mode, theta, v)
+    kw = dict(algorithm=alg, maxiter=12 if p > 20 else 30)
+    one = T.fit(prov, start, lanes=1, **kw)
+    warp = T.fit(prov, start, lanes=32, **kw)
+    assert one["npackets"] == warp["npackets"] > 2
+    assert np.array_equal(one["state"], warp["state"], equal_nan=True), (K, alg)
+    assert np.array_equal(one["partrace"], warp["partrace"]) and np.array_equal(one["ssrtrace"], warp["ssrtrace"])
+    assert np.array_equal(one["condtrace"], warp["condtrace"], equal_nan=True)
+    assert p == len(one["par"])
+
+
+def test_lane_shared_loops_are_race_free_under_thread_sanitizer(tmp_path):
+    """the 32-lane host emulation under -fsanitize=thread: no unsynchronised access to the shared matrices
+    (a missing __syncwarp() on the device), and bitwise the one-lane answers, for all six methods at
+    p = 3, 12, 40"""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_harness", "tsan_main.cpp")
+    exe = str(tmp_path / "tsan_main")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-pthread", "-ffp-contract=off", "-fsanitize=thread",
+                           src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    if "FATAL: ThreadSanitizer" in out.stderr and "unexpected memory mapping" in out.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory in this container")
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("p ")]
+    assert len(lines) == 18 and all(ln.endswith("bitwise same") for ln in lines), out.stdout

@@ -62,7 +62,9 @@ def packet_from_rows(rows, y, weights=None):
 
 
 def fit(provider, start, algorithm="lm", maxiter=100, scale="more", trace=True, factor_up=2.0, factor_down=3.0,
-        avmax=0.75, h_df=None, h_fvv=0.02, xtol=None, ftol=None, gtol=None, n=1000, batch_iters=0):
+        avmax=0.75, h_df=None, h_fvv=0.02, xtol=None, ftol=None, gtol=None, n=1000, batch_iters=0, lanes=1):
+    """lanes=1: the SingleLane host build; lanes=32: the warp emulated with one host thread per lane (the
+    cooperative loops of trs_core.h run exactly as on the device, with barriers for __syncwarp)"""
     from oracle.oracle import SCALE, SQRT_EPS, TRS
     L = lib()
     start = np.ascontiguousarray(start, dtype=float)
@@ -83,13 +85,19 @@ def fit(provider, start, algorithm="lm", maxiter=100, scale="more", trace=True, 
         np.ctypeslib.as_array(out, shape=(npk,))[: pk.size] = pk
         return 0
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
-    npass = L.trs_host_fit(C.byref(hp), dp(start), _CB(cb), None, dp(state), dp(partrace), dp(ssrtrace),
-                           dp(condtrace), 100000)
+    if lanes == 1:
+        npass = L.trs_host_fit(C.byref(hp), dp(start), _CB(cb), None, dp(state), dp(partrace), dp(ssrtrace),
+                               dp(condtrace), 100000)
+    else:
+        L.trs_host_fit_lanes.restype = C.c_long
+        npass = L.trs_host_fit_lanes(C.byref(hp), dp(start), _CB(cb), None, dp(state), dp(partrace), dp(ssrtrace),
+                                     dp(condtrace), 100000, int(lanes))
+        assert npass >= 0
     out = {k: state[i] for i, k in enumerate(S_NAMES)}
     v = state[S_COUNT:]
     out.update(par=v[:p].copy(), dx=v[p:2 * p].copy(), g=v[2 * p:3 * p].copy(), diag=v[3 * p:4 * p].copy(),
                jtj=v[6 * p:6 * p + p * p].reshape(p, p).copy(),
-               covar=v[6 * p + p * p:6 * p + 2 * p * p].reshape(p, p).copy(), npackets=npass)
+               covar=v[6 * p + p * p:6 * p + 2 * p * p].reshape(p, p).copy(), npackets=npass, state=state.copy())
     nit = int(out["niter"])
     out["partrace"] = partrace.reshape(p, maxiter + 1).T[: nit + 1].copy()
     out["ssrtrace"] = ssrtrace[: nit + 1].copy()
