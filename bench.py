@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- LM iterations/sec of gsl_nls_large(method='lm') on the synthetic exponential model
-y ~ A*exp(-lam*x)+b, n = 1e8, p = 3 (BASELINE.json configs[2]), observation-sharded over N B200s.
+"""bench.py -- throughput of the gsl_nls_large() hot path on B200, one JSON line per run.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+    python bench.py --gpus N --steps K --warmup W             # this repo (CUDA path), headline config
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port)
+    python bench.py --config gaussmix48 [--algorithm ddogleg] # BASELINE.json configs[3]
+    python bench.py --config mstart8192                       # BASELINE.json configs[4]
 
-A "step" is one trust-region trial iteration: one fused pass over all n observations (residuals,
-Jacobian rows, J^T J, J^T f, f^T f) followed by the device-side trust-region step.  Whole fits are
-run back to back from the README start values until exactly K steps have been executed; `value` is
-the number of LM (outer) iterations those steps completed per second of device time, with the data
-resident in HBM.  `e2e` is the same metric through gslnls_fit_large() with HOST buffers: pinned-host
-to device copies of x and y, the fit, and the result read-back all inside the timed region.
-Rank 0 prints one JSON line.
+Headline (`--config exp3`, BASELINE.json configs[2]): LM iterations/sec of gsl_nls_large(method='lm') on the
+synthetic exponential model y ~ A*exp(-lam*x)+b, n = 1e8, p = 3, observation-sharded over N B200s.
+
+A "step" is one trust-region trial: one fused pass over all n observations (residuals, Jacobian rows,
+J^T J, J^T f, f^T f) followed by the device-side trust-region step.  Exactly K steps are timed, as whole
+fits run back to back from the start values (the last fit is cut when the K-th step has run).
+`ms_per_step` is that time / K.  `value` converts it to the metric with the constants of ONE COMPLETE fit,
+run before the timed region: value = (outer iterations per fit / passes per fit) / ms_per_step -- so it
+does not depend on where K happens to cut the last fit.  `e2e` is the same metric through
+gslnls_fit_large[_sharded]() with PAGEABLE host buffers (what R passes): the library's own pinned staging,
+H2D copies, the fit and the result read-back are all inside the timed region.  Rank 0 prints the line.
 """
 import argparse
 import json
@@ -40,8 +45,9 @@ START = (1.0, 1.0, 0.0)   # well-conditioned start; README's (0,0,0)
 FORMULA_RHS = "A * exp(-lam * x) + b"
 
 
+# ------------------------------------------------------------------------------------------------ data
 def synth_rows(lo, hi, n_total, seed=1):
-    """rows [lo, hi) of the synthetic data set; any shard regenerates identical doubles
+    """rows [lo, hi) of the headline data set; any shard regenerates identical doubles
     (counter-based Philox stream keyed by (seed, chunk index))"""
     x = 3.0 * np.arange(lo, hi, dtype=np.float64) / float(n_total - 1)
     z = np.empty(hi - lo)
@@ -55,6 +61,90 @@ def synth_rows(lo, hi, n_total, seed=1):
     return x, y
 
 
+def gaussmix_formula(K=16):
+    terms, names = [], []
+    for k in range(1, K + 1):
+        terms.append("a%d * exp(-(x - m%d)^2 / s%d^2)" % (k, k, k))
+        names += ["a%d" % k, "m%d" % k, "s%d" % k]
+    return " + ".join(terms), names
+
+
+def gaussmix_truth(K=16):
+    th = []
+    for k in range(1, K + 1):
+        th += [5.0 + ((7 * k) % 11), 100.0 * (k - 0.5) / K, 2.5]
+    return np.array(th)
+
+
+def gaussmix_rows(lo, hi, n_total, K=16, seed=4):
+    """x on [0, 100], 16 Gaussians of width 2.5, noise sd 0.5; shard-independent"""
+    th = gaussmix_truth(K)
+    x = 100.0 * np.arange(lo, hi, dtype=np.float64) / float(n_total - 1)
+    y = np.zeros(hi - lo)
+    for k in range(K):
+        y += th[3 * k] * np.exp(-((x - th[3 * k + 1]) ** 2) / th[3 * k + 2] ** 2)
+    z = np.empty(hi - lo)
+    for c in range(lo // CHUNK, (hi - 1) // CHUNK + 1):
+        a, b = max(lo, c * CHUNK), min(hi, (c + 1) * CHUNK)
+        full = np.random.Generator(np.random.Philox(key=[seed, c])).standard_normal(CHUNK)
+        z[a - lo:b - lo] = full[a - c * CHUNK:b - c * CHUNK]
+    return x, y + 0.5 * z
+
+
+def gaussmix_start(K=16):
+    return gaussmix_truth(K) * (1.0 + 0.02 * (-1.0) ** np.arange(3 * K))
+
+
+def mstart_problem(n=4096, seed=5):
+    """two-exponential mixture on [0, 10], truth (3, 0.5, 2, 3), noise 0.05"""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    x = np.linspace(0, 10, n)
+    y = 3 * np.exp(-0.5 * x) + 2 * np.exp(-3 * x) + 0.05 * rng.standard_normal(n)
+    return x, y
+
+
+class Workload:
+    """one fit-shaped configuration of BASELINE.json: model, data, start, roofline of the pass kernel"""
+
+    def __init__(self, name, args):
+        self.name = name
+        if name == "exp3":
+            self.n = args.n or N_FULL
+            self.rhs, self.pnames, self.p = FORMULA_RHS, ["A", "lam", "b"], 3
+            self.start = np.array(START)
+            self.algorithm = args.algorithm or "lm"
+            self.rows = synth_rows
+            self.oracle_model = "exp3"
+            self.fvv = True
+            self.metric = "LM iterations/sec, gsl_nls_large(%s), exp model n=1e8 p=3" % self.algorithm
+            self.workload = ("y ~ A*exp(-lam*x)+b, n=%d, p=3, %s, scale=more, start=(1,1,0) "
+                             "(BASELINE.json configs[2])" % (self.n, self.algorithm))
+            self.cpu_sample = args.cpu_sample or 20_000_000
+        elif name == "gaussmix48":
+            self.n = args.n or 10_000_000
+            self.rhs, self.pnames = gaussmix_formula(16)
+            self.p = 48
+            self.start = gaussmix_start(16)
+            self.algorithm = args.algorithm or "dogleg"
+            self.rows = gaussmix_rows
+            self.oracle_model = "gaussmix"
+            self.fvv = None
+            self.metric = "%s iterations/sec, gsl_nls_large, sum of 16 Gaussians n=1e7 p=48" % self.algorithm
+            self.workload = ("y ~ sum_k a_k exp(-(x - m_k)^2 / s_k^2), K=16, n=%d, p=48, %s, start = truth x (1 +- 0.02) "
+                             "(BASELINE.json configs[3])" % (self.n, self.algorithm))
+            self.cpu_sample = args.cpu_sample or 200_000
+        else:
+            raise ValueError(name)
+
+    def bound(self, n_loc):
+        """(bound, algorithmic work per launch, unit divisor) of the dominant kernel"""
+        if self.name == "exp3":
+            return "hbm", 16.0 * n_loc   # 8 B x (1 predictor + 1 response) per observation, nothing O(n) written
+        p = self.p
+        return "tensor", n_loc * (p * (p + 1) + 2.0 * p + 2.0)  # J^T J (SYRK) + J^T f + f^T f; model flops not counted
+
+
+# ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -105,56 +195,68 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic():
-    """dram bytes per K1 launch from the committed ncu --set full capture, if any"""
+def recorded_traffic(name):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
+    fn = {"exp3": "k1_traffic.json", "gaussmix48": "k1b_traffic.json"}.get(name)
     try:
-        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", fn)) as fh:
             return json.load(fh)
     except Exception:  # noqa: BLE001
         return None
 
 
-def cpu_fit(n_sample, threads, n_total):
-    """the reference's CPU data flow (oracle port of src/nls_large.c + GSL multilarge) on a sample"""
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_fit(wl, n_sample, threads, maxiter=100):
+    """the reference's CPU data flow (oracle port of src/nls_large.c + GSL multilarge) on the first rows
+    of the same design at size n_sample (same x grid and noise law, so the trajectory matches the full fit's)"""
     from oracle import oracle as O
-    # same design (x grid on [0,3], same noise law) at reduced n, so that the trajectory matches the full fit's
-    x, y = synth_rows(0, n_sample, n_sample)
+    x, y = wl.rows(0, n_sample, n_sample)
     t0 = time.perf_counter()
-    r = O.nls_large("exp3", y, START, x=x, algorithm="lm", threads=threads)
-    dt = time.perf_counter() - t0
-    return r, dt
+    r = O.nls_large(wl.oracle_model, y, wl.start, x=x, algorithm=wl.algorithm, threads=threads, maxiter=maxiter)
+    return r, time.perf_counter() - t0
 
 
 def run_reference(args):
+    """--impl reference: the reference's own algorithm for this path on the host cores, at the arm's full n.
+    R and libgsl cannot be installed here, so this is the oracle port (cpu_baseline.kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_s = args.cpu_sample
     from oracle import oracle as O
     O.build()
-    iters, elapsed, last = 0, 0.0, None
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_fit(min(n_s, 1_000_000), cores, N_FULL)
+    if args.config == "mstart8192":
+        return run_reference_mstart(args, cores)
+    wl = Workload(args.config, args)
+    n_s = args.cpu_sample or wl.n     # the real size unless told otherwise: same_config
+    if args.warmup > 0:
+        cpu_fit(wl, min(n_s, 200_000 if wl.p > 8 else 1_000_000), cores, maxiter=3)
+    # bounded: whole fits until >= --steps outer iterations have run (p = 48 at n = 1e7 is ~10 s per iteration on
+    # 16 cores, so that configuration stops at --steps iterations inside its first fit)
+    iters, elapsed, fits, last = 0, 0.0, 0, None
+    cap = args.steps if wl.p > 8 else 100
     while iters < args.steps:
-        r, dt = cpu_fit(n_s, cores, N_FULL)
+        r, dt = cpu_fit(wl, n_s, cores, maxiter=cap)
         iters += r["niter"]
         elapsed += dt
+        fits += 1
         last = r
-    scale = n_s / float(N_FULL)
+    scale = n_s / float(wl.n)
     value = iters / elapsed * scale
     line = {
-        "impl": "reference", "metric": "LM iterations/sec, gsl_nls_large(lm), exp model n=1e8 p=3",
-        "value": value, "unit": "iterations/s", "n_gpus": args.gpus, "steps": iters, "warmup": args.warmup,
-        "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "y ~ A*exp(-lam*x)+b, n=1e8, p=3, lm, scale=more (BASELINE.json configs[2])",
-                   "note": "reference CPU algorithm (oracle port: src/nls_large.c data flow + GSL multilarge "
-                           "restatement; R and libgsl are not installable here); timed on a row sample and "
-                           "scaled by n_sample/n (the path is O(n) per iteration)"},
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": iters, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.workload,
+                   "note": "reference CPU algorithm (oracle port: src/nls_large.c data flow -- f (n) and J (n x p) "
+                           "materialised, dgemv + dsyrk -- and the GSL multilarge trust-region restatement; R and "
+                           "libgsl are not installable here), OpenMP over all host cores, at n = %d%s; a step is one "
+                           "outer iteration" % (n_s, "" if scale == 1.0 else " (row sample, scaled x%g)" % scale),
+                   "final": {"par": [float(v) for v in last["par"][:8]], "ssr": float(last["ssr"]),
+                             "niter": int(last["niter"]), "status": last["status"]}},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port",
-                         "sample": "same design at n=%d, %d full lm fits (%d iterations), scaled x%g" % (
-                             n_s, max(1, iters // max(last["niter"], 1)), iters, scale)},
+                         "sample": "%d %s fit(s) of the full configuration, n=%d (%d iterations in %.1f s)" % (
+                             fits, wl.algorithm, n_s, iters, elapsed)},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -162,21 +264,34 @@ def run_reference(args):
     return 0
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
-    ap.add_argument("--algorithm", default="lm")
-    ap.add_argument("--cpu-sample", type=int, default=4_000_000)
-    ap.add_argument("--e2e-fits", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
+def run_reference_mstart(args, cores):
+    from oracle import oracle as O
+    x, y = mstart_problem()
+    S, iters = args.n or 8192, 5
+    starts = mstart_starts(S)
+    k = min(S, max(64, args.steps * 64))
+    t0 = time.perf_counter()
+    for c in range(k):
+        O.nls_large("expmix2", y, starts[c], x=x, algorithm="lm", maxiter=iters)
+    dt = time.perf_counter() - t0
+    value = k * iters / dt
+    line = {
+        "impl": "reference", "metric": MSTART_METRIC, "value": value, "unit": "candidate-iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * S * iters / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": MSTART_WORKLOAD % S,
+                   "note": "oracle port, candidates one after the other on one core as src/nls_mstart.c:75-91 runs them"},
+        "cpu_baseline": {"value": value, "unit": "candidate-iterations/s", "cores": 1, "kind": "port",
+                         "sample": "%d of the %d candidates" % (k, S)},
+        "e2e": {"value": value, "unit": "candidate-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
 
+
+# ------------------------------------------------------------------------------------------------ CUDA arm: fits
+def run_fit_config(args):
     import torch
     import torch.distributed as dist
 
@@ -184,39 +299,36 @@ def main():
     from gslnls_b200 import _lib
     from gslnls_b200.distributed import init_comm_from_torch, shard_bounds
 
+    wl = Workload(args.config, args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = args.n
+    n = wl.n
     lo, hi = shard_bounds(n, rank, world)
     n_loc = hi - lo
 
-    # ---- synthetic shard: pinned host buffers (for the e2e leg) and a resident device copy --------
-    x_h = torch.empty(n_loc, dtype=torch.float64).pin_memory()
-    y_h = torch.empty(n_loc, dtype=torch.float64).pin_memory()
-    xs, ys = synth_rows(lo, hi, n)
-    x_h.numpy()[:] = xs
-    y_h.numpy()[:] = ys
-    del xs, ys
-    model = Model(FORMULA_RHS, ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    # ---- synthetic shard in ordinary (pageable) host memory, as the host language would hold it; a resident
+    #      device copy for the device-timed leg
+    x_h, y_h = wl.rows(lo, hi, n)
+    x_h, y_h = np.ascontiguousarray(x_h), np.ascontiguousarray(y_h)
+    model = Model(wl.rhs, wl.pnames, ["x"], jac=True, fvv=wl.fvv)
     comm = init_comm_from_torch(local) if world > 1 else None
-    pb = Problem(model, n_loc, False, local).upload([x_h.numpy()], y_h.numpy())
+    pb = Problem(model, n_loc, False, local).upload([x_h], y_h)
     if comm is not None:
         pb.set_comm(comm)
     ctrl = gsl_nls_control()
-    start = np.array(START)
+    start = wl.start
+    host_us = [0.0, 0.0, 0.0, 0]
 
     def run_steps(k):
-        """exactly k trial steps as back-to-back fits; returns (outer iterations, fits, last result)"""
+        """exactly k trial steps as back-to-back fits; returns (outer iterations, fits, last complete result)"""
         left, iters, fits, last, complete = k, 0, 0, None, None
         while left > 0:
             t0 = time.perf_counter()
-            pb.fit_begin(start, algorithm=args.algorithm, control=ctrl)
+            pb.fit_begin(start, algorithm=wl.algorithm, control=ctrl)
             t1 = time.perf_counter()
             done, run = False, 0
             while not done and run < left:
@@ -238,13 +350,14 @@ def main():
                 complete = last
         return iters, fits, (complete or last)
 
-    host_us = [0.0, 0.0, 0.0, 0]
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one complete fit: the conversion constants of `value`, and the parity record of the line
+    whole = pb.fit(start, algorithm=wl.algorithm, control=ctrl)
+    iters_per_fit, passes_per_fit = int(whole["niter"]), int(whole["npass"])
     run_steps(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
@@ -267,19 +380,21 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = iters / (ms * 1e-3)
+    ms_per_step = ms / args.steps
+    value = (iters_per_fit / max(passes_per_fit, 1)) / (ms_per_step * 1e-3)
 
-    # ---- e2e: gslnls_fit_large[_sharded]() from pinned host buffers, copies inside the timed region ----
-    # every rank passes its shard as HOST pointers; the call uploads it over that GPU's PCIe link, fits
-    # (packets cross NVLink) and returns the result record.  Host wall clock around the call between
-    # barriers (the call is synchronous and includes host work), max over ranks.
+    # ---- e2e: gslnls_fit_large[_sharded]() from PAGEABLE host buffers, copies inside the timed region ----
+    # every rank passes its shard as plain host pointers; the call stages them through the library's pinned
+    # ring over that GPU's PCIe link, fits (packets cross NVLink) and returns the result record.  Host wall
+    # clock around the call between barriers (the call is synchronous and includes host work), max over ranks.
     e2e = None
     if args.e2e_fits > 0:
         import ctypes as C
-        ci, cd = pack_control(ctrl, args.algorithm, False)
+        ci, cd = pack_control(ctrl, wl.algorithm, False)
         L = _lib.lib()
-        arr = (_lib.c_double_p * 1)(C.cast(x_h.data_ptr(), _lib.c_double_p))
-        yp = C.cast(y_h.data_ptr(), _lib.c_double_p)
+        arr = (_lib.c_double_p * 1)(x_h.ctypes.data_as(_lib.c_double_p))
+        yp = y_h.ctypes.data_as(_lib.c_double_p)
+        p = wl.p
         e_iters, e_t, d2h, e_last = 0, 0.0, 0, None
         for rep in range(args.e2e_fits + 1):
             res = _lib.Result()
@@ -298,80 +413,190 @@ def main():
             if rep > 0:  # the first call loads the kernels and fills the library's buffer cache
                 e_iters += res.niter
                 e_t += dt
-                d2h += 8 * (24 + 6 * 3 + 2 * 9) * world
-                e_last = [res.par[i] for i in range(3)]
+                d2h += 8 * (24 + 6 * p + 2 * p * p) * world
+                e_last = [res.par[i] for i in range(min(p, 8))]
             L.gslnls_result_free(C.byref(res))
         e2e = {"value": e_iters / e_t, "unit": "iterations/s",
                "h2d_bytes_per_step": int(16 * n * args.e2e_fits / max(e_iters, 1)),
                "d2h_bytes_per_step": int(d2h / max(e_iters, 1)),
-               "ms_per_fit": 1e3 * e_t / args.e2e_fits, "par": e_last,
-               "note": "gslnls_fit_large_sharded() per rank: pinned-host H2D of the rank's x,y shard + full lm fit "
-                       "to convergence + result D2H per call; %d calls, %d iterations; wall clock between "
-                       "barriers, max over ranks; bytes are totals over all ranks per outer iteration"
-                       % (args.e2e_fits, e_iters)}
+               "ms_per_fit": 1e3 * e_t / args.e2e_fits, "par": e_last, "host_memory": "pageable",
+               "note": "gslnls_fit_large_sharded() per rank from pageable host arrays: library-side pinned staging + "
+                       "H2D of the rank's x,y shard + full %s fit to convergence + result D2H per call; %d calls, "
+                       "%d iterations; wall clock between barriers, max over ranks; bytes are totals over all ranks "
+                       "per outer iteration" % (wl.algorithm, args.e2e_fits, e_iters)}
 
     # the sampler ran through both timed regions (device-resident steps and the e2e calls)
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         return 0
 
-    peak, peak_src = measured_peaks()
-    alg_bytes = 16.0 * n_loc  # 8 B x (1 predictor + 1 response) per observation, nothing O(n) written
-    achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
-    traffic = recorded_traffic()
-    line = {
-        "metric": "LM iterations/sec, gsl_nls_large(%s), exp model n=1e8 p=3" % args.algorithm,
-        "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "y ~ A*exp(-lam*x)+b, n=%d, p=3, %s, scale=more, start=(1,1,0) "
-                               "(BASELINE.json configs[2])" % (n, args.algorithm),
-                   "n_per_gpu": n_loc, "fits": fits, "outer_iterations": iters,
-                   "passes_per_iteration": args.steps / max(iters, 1),
-                   "host_us_per_fit": {"fit_begin": host_us[0] / max(host_us[3], 1),
-                                       "fit_run": host_us[1] / max(host_us[3], 1),
-                                       "fit_end": host_us[2] / max(host_us[3], 1)},
-                   "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (alg_bytes / 1e9),
-                   "final": {"par": [float(v) for v in last["par"]], "ssr": float(last["ssr"]),
-                             "niter": int(last["niter"]), "status": last["status"]},
-                   "parallelism": "observation-sharded x%d; per pass one %d-double packet per rank, %s" % (
-                       world, 3 * 4 // 2 + 3 + 2,
-                       "deposited by the pass kernel in every GPU's mailbox over NVLink peer memory and summed in "
-                       "rank order by the resident trust-region warp (no collective call)"
-                       if (comm is not None and comm.has_peer_memory) else
-                       ("NCCL all-gather + rank-order sum" if world > 1 else "single GPU, resident trust-region warp"))},
-        "clocks": clocks,
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None,
-                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                     "kernel": "nls_pass (K1)", "algorithmic_bytes_per_launch": alg_bytes,
-                     "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt),
-                     "launch_sampling": "every %s-th pass launch of the timed region" % os.environ["GSLNLS_PROF_STRIDE"],
-                     "peak_source": peak_src,
+    bound, work = wl.bound(n_loc)
+    roof = {"bound": bound, "kernel": "nls_pass (K1)" if bound == "hbm" else "nls_pass (K1b, tiled FP64 DMMA SYRK)",
+            "avg_launch_ms": pass_ms, "launches_timed": int(pass_cnt),
+            "launch_sampling": "every %s-th pass launch of the timed region" % os.environ["GSLNLS_PROF_STRIDE"]}
+    traffic = recorded_traffic(wl.name)
+    roof["traffic"] = traffic["dram_bytes_per_launch"] if traffic else None
+    if bound == "hbm":
+        peak, peak_src = measured_peaks()
+        achieved = work / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
+        roof.update({"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "algorithmic_bytes_per_launch": work, "peak_source": peak_src,
                      "note": "avg_launch_ms = CUDA-event time of the nls_pass launches inside the timed region; in "
                              "resident-server mode a launch starts by waiting (in-kernel) for the trust-region warp's "
                              "request, so it spans wait + stream + grid reduction; stream_us / step_us are the device "
                              "globaltimer splits (request seen -> packet out, packet complete -> next request)",
                      "stream_us": stream_us, "step_us": step_us,
-                     "frac_stream": (alg_bytes / (stream_us * 1e-6) / 1e9 / peak) if stream_us > 0 else None},
+                     "frac_stream": (work / (stream_us * 1e-6) / 1e9 / peak) if stream_us > 0 else None})
+    else:
+        import ctypes as C
+        dfma, dmma = C.c_double(), C.c_double()
+        _lib.check(_lib.lib().gslnls_measure_fp64_peak(local, C.byref(dfma), C.byref(dmma)))
+        peak = max(dfma.value, dmma.value)
+        achieved = work / (pass_ms * 1e-3) / 1e12 if pass_ms > 0 else None
+        roof.update({"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                     "algorithmic_flops_per_launch": work,
+                     "peak_source": "FP64 pipe measured live in this run (gslnls_measure_fp64_peak: DFMA %.1f, DMMA "
+                                    "m8n8k4 %.1f TFLOP/s; they issue to the same units); MEASURED_PEAKS.json has no "
+                                    "FP64 entry" % (dfma.value, dmma.value),
+                     "note": "flops count J^T J (n p (p+1)), J^T f and f^T f only; the model's 16 exp per row and "
+                             "the padding of the 8x8 blocking are extra work on the same pipe"})
+    line = {
+        "metric": wl.metric, "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.workload, "n_per_gpu": n_loc,
+                   "value_is": "(outer iterations per complete fit / passes per complete fit) / ms_per_step = "
+                               "(%d / %d) / %.6g ms; independent of where --steps cuts the last fit" % (
+                                   iters_per_fit, passes_per_fit, ms_per_step),
+                   "iterations_per_fit": iters_per_fit, "passes_per_fit": passes_per_fit,
+                   "timed": {"fits_started": fits, "outer_iterations": iters},
+                   "host_us_per_fit": {"fit_begin": host_us[0] / max(host_us[3], 1),
+                                       "fit_run": host_us[1] / max(host_us[3], 1),
+                                       "fit_end": host_us[2] / max(host_us[3], 1)},
+                   "l2": "inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed" % (16.0 * n_loc / 1e9),
+                   "final": {"par": [float(v) for v in whole["par"][:8]], "ssr": float(whole["ssr"]),
+                             "niter": int(whole["niter"]), "status": whole["status"]},
+                   "parallelism": "observation-sharded x%d; per pass one %d-double packet per rank, %s" % (
+                       world, wl.p * (wl.p + 1) // 2 + wl.p + 2,
+                       "deposited by the pass kernel in every GPU's mailbox over NVLink peer memory and summed in "
+                       "rank order by the resident trust-region warp (no collective call)"
+                       if (comm is not None and comm.has_peer_memory and wl.p <= 32) else
+                       ("NCCL all-gather + rank-order sum" if world > 1 else
+                        ("single GPU, resident trust-region warp" if wl.p <= 32 else
+                         "single GPU, launch-ordered trust-region step")))},
+        "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
     }
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
-        n_s = args.cpu_sample
-        r, dt = cpu_fit(n_s, 1, N_FULL)
-        scale = n_s / float(N_FULL)
+        n_s = min(wl.cpu_sample, n)
+        cap = 100 if wl.p <= 8 else 3
+        r, dt = cpu_fit(wl, n_s, 1, maxiter=cap)
+        scale = n_s / float(n)
         line["cpu_baseline"] = {"value": r["niter"] / dt * scale, "unit": "iterations/s", "cores": 1, "kind": "port",
-                                "sample": "one full lm fit (%d iterations) on the same design at n=%d, 1 thread "
-                                          "(the reference is single-threaded), scaled x%g; omits the R interpreter"
-                                          % (r["niter"], n_s, scale)}
+                                "sample": "%s, %d iterations on the same design at n=%d in %.1f s, 1 thread (the "
+                                          "reference is single-threaded), scaled x%g; omits the R interpreter"
+                                          % (wl.algorithm, r["niter"], n_s, dt, scale)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm: multistart
+MSTART_METRIC = "multi-start candidate-iterations/sec, 8192 starts x 5 LM iterations, exp mixture n=4096 p=4"
+MSTART_WORKLOAD = ("y ~ A1*exp(-l1*x)+A2*exp(-l2*x), n=4096, p=4, S=%d Sobol starts in [0,10]^4, mstart_p=5 LM "
+                   "iterations each + log det(J^T J) screen (BASELINE.json configs[4])")
+
+
+def mstart_starts(S):
+    from scipy.stats import qmc
+    return np.ascontiguousarray(qmc.Sobol(4, scramble=False).random(S) * 10.0)
+
+
+def run_mstart(args):
+    import torch
+
+    from gslnls_b200 import Model, Problem
+    from oracle import oracle as O
+    n, S, iters = 4096, args.n or 8192, 5
+    torch.cuda.set_device(0)
+    x, y = mstart_problem(n)
+    starts = mstart_starts(S)
+    m = Model("A1*exp(-l1*x)+A2*exp(-l2*x)", ["A1", "l1", "A2", "l2"], ["x"], jac=True)
+    pb = Problem(m, n).upload([x], y)
+    for _ in range(max(args.warmup, 3)):
+        out = pb.fit_batch(starts, iters=iters)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = pb.launch_count
+    pb.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = pb.fit_batch(starts, iters=iters)
+    wall = time.perf_counter() - t0
+    ms = pb.timer_stop()
+    launches = pb.launch_count - launches0
+    clocks = sampler.stop()
+    ok = np.isfinite(out["ssr"])
+    best = int(np.argmin(np.where(ok, out["ssr"], np.inf)))
+    k = 64
+    t0 = time.perf_counter()
+    agree = 0
+    for c in range(k):
+        ref = O.nls_large("expmix2", y, starts[c], x=x, algorithm="lm", maxiter=iters)
+        agree += int(ref["conv"] not in (0, 11) or np.allclose(out["par"][c], ref["par"], rtol=1e-6, atol=1e-9))
+    cdt = time.perf_counter() - t0
+    value = S * iters * args.steps / (ms * 1e-3)
+    line = {
+        "metric": MSTART_METRIC, "value": value, "unit": "candidate-iterations/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": MSTART_WORKLOAD % S,
+                   "l2": "the 64 KB of data are read by every candidate and are meant to stay in cache; no flush",
+                   "step": "one batch: start upload, all passes and batched trust-region steps, result download",
+                   "best": {"candidate": best, "par": [float(v) for v in out["par"][best]],
+                            "ssr": float(out["ssr"][best])},
+                   "oracle_agreement": "%d of %d sampled candidates within 1e-6" % (agree, k)},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": None,
+        "e2e": {"value": S * iters * args.steps / wall, "unit": "candidate-iterations/s",
+                "h2d_bytes_per_step": int(starts.nbytes), "d2h_bytes_per_step": int(S * 8 * 40),
+                "note": "host wall clock around Problem.fit_batch() with host start / result arrays"},
+        "cpu_baseline": {"value": k * iters / cdt, "unit": "candidate-iterations/s", "cores": 1, "kind": "port",
+                         "sample": "%d candidates through the oracle, 1 thread" % k},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="exp3", choices=["exp3", "gaussmix48", "mstart8192"])
+    ap.add_argument("--n", type=int, default=0, help="rows (exp3, gaussmix48) or candidates (mstart8192)")
+    ap.add_argument("--algorithm", default=None)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="rows of the CPU legs (default: reference arm the full n, cpu_baseline a bounded sample)")
+    ap.add_argument("--e2e-fits", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 10 if args.config == "mstart8192" else 40
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    if args.config == "mstart8192":
+        return run_mstart(args)
+    return run_fit_config(args)
 
 
 if __name__ == "__main__":

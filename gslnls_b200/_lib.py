@@ -47,6 +47,8 @@ SIGNATURES = {
     "gslnls_problem_free": (None, [C.c_void_p]),
     "gslnls_problem_upload": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p]),
     "gslnls_problem_bind_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gslnls_problem_set_weights_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "gslnls_set_weights_mode": (C.c_int, [C.c_int]),
     "gslnls_problem_set_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gslnls_problem_fit": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, C.c_int, C.POINTER(Result)]),
     "gslnls_problem_eval_packet": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
@@ -71,6 +73,8 @@ SIGNATURES = {
     "gslnls_comm_has_peer_memory": (C.c_int, [C.c_void_p]),
     "gslnls_comm_rank": (C.c_int, [C.c_void_p]),
     "gslnls_comm_size": (C.c_int, [C.c_void_p]),
+    "gslnls_measure_fp64_peak": (C.c_int, [C.c_int, c_double_p, c_double_p]),
+    "gslnls_measure_read_bandwidth": (C.c_int, [C.c_int, C.c_size_t, c_double_p]),
     "gslnls_strerror": (C.c_char_p, [C.c_int]),
     "gslnls_trs_name": (C.c_char_p, [C.c_int]),
     "gslnls_last_error": (C.c_char_p, []),

@@ -21,10 +21,11 @@ struct KernelTune {
 
 struct VariantKey {
     int has_w, vec, stream, block, unroll, minb, tiled, stages, prefetch, fexp;
+    int wgsl = 0; // weights as GSL's multilarge applies them: sqrt(w) on f and fvv only, J^T J unweighted
     bool operator<(const VariantKey &o) const
     {
-        return std::tie(has_w, vec, stream, block, unroll, minb, tiled, stages, prefetch, fexp) <
-               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled, o.stages, o.prefetch, o.fexp);
+        return std::tie(has_w, vec, stream, block, unroll, minb, tiled, stages, prefetch, fexp, wgsl) <
+               std::tie(o.has_w, o.vec, o.stream, o.block, o.unroll, o.minb, o.tiled, o.stages, o.prefetch, o.fexp, o.wgsl);
     }
 };
 

@@ -14,7 +14,11 @@
 #define NLS_CH_PASS_CTR 128   /* u64: passes completed so far (last CTA of K1 -> next K1)       */
 #define NLS_CH_FIT_SEQ0 256   /* u64: sequence number of the first pass of the current fit      */
 #define NLS_CH_ABORT 384      /* u64: host -> server, leave the fit early                       */
-#define NLS_CH_TIMER 512      /* u64[2]: globaltimer ns, first CTA past the wait / last CTA out  */
+#define NLS_CH_TIMER 512      /* u64[5]: globaltimer ns, first CTA past the wait / last CTA out  */
+#define NLS_CH_PASS_SEEN 640  /* u64: sequence number of the latest pass kernel that has STARTED running (K1 ->
+                                 server): the start-of-fit handshake that proves pass and server kernels execute
+                                 concurrently (they do not under ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING) */
+#define NLS_CH_GONE_BUMP (1ull << 40) /* added to REQ_SEQ by a server that gives up: every queued pass falls through idle */
 #define NLS_CH_FLAGS 1024     /* u64 x NLS_MAX_RANKS, 128 B apart: latest sequence deposited by rank r */
 #define NLS_CH_DATA 2048      /* double [2 parities][NLS_MAX_RANKS][NLS_CH_MAXPK]               */
 #define NLS_CH_MAXPK 1280
@@ -41,6 +45,7 @@ struct NlsPassParams {
     int rank;
     int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
+    unsigned long long watchdog_ns;   // server mode: longest in-kernel wait for a request (GSLNLS_WATCHDOG_S)
     // two-level grid reduction (single-candidate launches): CTAs in groups of NLS_RED_GROUP, the last
     // arriver of a group sums the group's partials, the last group sums the group sums
     double *group_partials;           // [ceil(gridDim.x / NLS_RED_GROUP)][pk_stride] or nullptr (flat reduction)

@@ -39,6 +39,12 @@
 #ifndef NLS_HAS_W
 #define NLS_HAS_W 0
 #endif
+#ifndef NLS_W_GSL
+#define NLS_W_GSL 0 /* 1: weights the way GSL's multilarge applies them (reference-compatible): sqrt(w) scales
+                       f and fvv only, the Jacobian rows -- hence J^T J -- stay unweighted.  0: rows of J are
+                       scaled too, so that g = J^T W f and J^T W J belong to the same weighted problem. */
+#endif
+#define NLS_W_ROWS (NLS_HAS_W && !NLS_W_GSL) /* Jacobian rows carry sqrt(w) */
 #ifndef NLS_STREAM
 #define NLS_STREAM 1
 #endif
@@ -109,7 +115,7 @@ static __device__ __forceinline__ unsigned long long nls_globaltimer()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define NLS_WATCHDOG_NS 60000000000ull /* a pass never waits a minute for its request */
+#define NLS_WATCHDOG_NS 60000000000ull /* default when the host passes no period (prm.watchdog_ns == 0) */
 
 // ------------------------------------------------------------------------------------ model glue
 struct NlsThread {
@@ -176,6 +182,8 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
         nbad += bad ? 1 : 0;
 #if NLS_HAS_W
         r *= sw;
+#endif
+#if NLS_W_ROWS
 #pragma unroll
         for (int j = 0; j < NLS_P; ++j)
             J[j] *= sw;
@@ -214,6 +222,8 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
 #endif
 #if NLS_HAS_W
         h *= sw;
+#endif
+#if NLS_W_ROWS
 #pragma unroll
         for (int j = 0; j < NLS_P; ++j)
             J[j] *= sw;
@@ -223,7 +233,7 @@ static __device__ __forceinline__ void nls_observe(const NlsThread &T, const dou
             acc[j] = fma(J[j], h, acc[j]);
         acc[NLS_P] = fma(h, h, acc[NLS_P]);
     } else { // NLS_MODE_JVP: u = J d ; J^T u ; u^T u   (matrix-free products for Steihaug CG)
-#if NLS_HAS_W
+#if NLS_W_ROWS
 #pragma unroll
         for (int j = 0; j < NLS_P; ++j)
             J[j] *= sw;
@@ -623,13 +633,19 @@ static __device__ __forceinline__ int nls_begin(const NlsPassParams &prm, const 
         if (threadIdx.x == 0) {
             const unsigned long long k = __ldcg((const unsigned long long *)(prm.channel + NLS_CH_PASS_CTR)) + 1ull;
             const unsigned long long *rs = (const unsigned long long *)(prm.channel + NLS_CH_REQ_SEQ);
+            // start-of-fit handshake: tell the server that pass k is executing (i.e. that the two kernels
+            // run concurrently); a server that never sees this gives up and the host falls back to
+            // launch-ordered stepping instead of deadlocking under a serialising tool
+            if (blockIdx.x == 0 && blockIdx.y == 0)
+                nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_PASS_SEEN), k);
+            const unsigned long long wd = prm.watchdog_ns ? prm.watchdog_ns : NLS_WATCHDOG_NS;
             unsigned long long t0 = 0ull, spins = 0ull, kk = k;
             while (nls_ld_acquire_gpu(rs) < k) {
                 if ((++spins & 1023ull) == 0ull) {
                     const unsigned long long t = nls_globaltimer();
                     if (t0 == 0ull)
                         t0 = t;
-                    else if (t - t0 > NLS_WATCHDOG_NS) {
+                    else if (t - t0 > wd) {
                         kk = 0ull; // give up: behave like an idle launch
                         break;
                     }
@@ -883,9 +899,14 @@ extern "C" __global__ void __launch_bounds__(256) nls_materialise(const NlsMater
         if (prm.resid)
             prm.resid[i] = r * sw;
         if (prm.grad) {
+#if NLS_W_GSL
+            const double swj = 1.0; // the reference returns params.J as the callback left it: unweighted
+#else
+            const double swj = sw;
+#endif
 #pragma unroll
             for (int j = 0; j < NLS_P; ++j)
-                prm.grad[i + prm.n * (long long)j] = J[j] * sw;
+                prm.grad[i + prm.n * (long long)j] = J[j] * swj;
         }
     }
 }

@@ -169,7 +169,11 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
         }
         nt_bar_wait(empty, (r & 1u) ^ 1u); // the consumer is done with this tile's previous contents
         // sqrt(w) scaling folded into the tile store; invalid (padding) lanes store zeros
+#if NLS_W_GSL
+        const double swv = valid ? 1.0 : 0.0; // reference-compatible weights: the rows of J stay unweighted
+#else
         const double swv = valid ? sw : 0.0;
+#endif
         double f, u = 0.0;
 #if defined(NT_DEBUG_SKIP_A)
         f = xa[0]; // timing experiment: no model evaluation, tile keeps its initial contents
@@ -208,7 +212,11 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
                     tp[k] = T.th[k] + T.h_fvv * T.vv[k];
                 const double fp = nls_model_f(tp, xa);
                 const double hinv = 1.0 / T.h_fvv;
+#if NLS_W_GSL
+                rr = (2.0 * hinv) * ((fp - f) * hinv - u) * sw; // u = J v, unweighted rows
+#else
                 rr = (2.0 * hinv) * (((fp - f) * hinv) * sw - u);
+#endif
             }
 #else
             rr = 0.0;

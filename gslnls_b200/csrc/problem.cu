@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,7 @@
 #include "model.hpp"
 #include "nls_abi.h"
 #include "trs_launch.hpp"
+#include "upload.hpp"
 
 namespace gslnls {
 thread_local std::string g_last_error;
@@ -60,6 +62,8 @@ struct gslnls_problem {
     const double *dvars[NLS_MAX_VARS] = {nullptr};
     const double *dy = nullptr, *dw = nullptr;
     bool bound = false;
+    int wgsl = 0; // weights mode: 0 rows of J weighted too (default), 1 GSL multilarge's (f, fvv only)
+    int upload_sharing = 1; // uploads running side by side in this process (one per GPU of a multi-GPU call)
     // kernels
     Variant *var = nullptr;
     VariantKey vkey{};
@@ -89,6 +93,8 @@ struct gslnls_problem {
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
     bool allow_server = true, server_on = false;
+    bool server_pending = false; // fit_begin chose the server; it is launched with the first pass (fit_run)
+    unsigned long long handshake_ns = 100000000ull; // start-of-fit handshake period (GSLNLS_HANDSHAKE_MS)
     char *own_channel = nullptr; // single-GPU problems own their channel; sharded ones use the comm's
     cudaStream_t srv_stream = nullptr, ctl_stream = nullptr;
     cudaEvent_t ev_reset = nullptr, ev_chunk[2] = {nullptr, nullptr};
@@ -149,7 +155,8 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             }
         }
     }
-    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp};
+    VariantKey key{pb->has_w, vec, batch ? 0 : 1, t.block, t.unroll, t.minb, batch ? 0 : t.tiled, t.stages, batch ? 0 : t.prefetch, t.fexp,
+                   pb->has_w ? pb->wgsl : 0};
     if (pb->var && !(key < pb->vkey) && !(pb->vkey < key))
         return GSLNLS_SUCCESS;
     try {
@@ -244,6 +251,7 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.req_stride = pb->req_stride;
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
+    prm.watchdog_ns = pb->watchdog_ns;
     static const bool flat_red = std::getenv("GSLNLS_FLAT_RED") != nullptr; // developer aid
     // two-level grid reduction for long packets (p > 8); a short packet is summed faster by one CTA
     if (ncand == 1 && pb->grid_x > NLS_RED_GROUP && pb->pk_stride >= 48 && !flat_red) {
@@ -302,6 +310,11 @@ static void stop_server(gslnls_problem *pb)
 {
     if (!pb->server_on)
         return;
+    if (pb->server_pending) { // chosen by fit_begin but never launched (no fit_run in between)
+        pb->server_pending = false;
+        pb->server_on = false;
+        return;
+    }
     char *ch = channel_of(pb);
     if (pb->h_flags[0] == 0 && ch) {
         static const unsigned long long one = 1ull;
@@ -318,12 +331,20 @@ static int wait_server_caught_up(gslnls_problem *pb)
 {
     unsigned long long *w = reinterpret_cast<unsigned long long *>(pb->h_ndone); // pinned, 16 bytes
     char *ch = channel_of(pb);
-    for (long spin = 0; pb->h_flags[0] == 0 && spin < 50000000L; ++spin) {
+    if (pb->server_pending)
+        return GSLNLS_SUCCESS; // never launched: nothing to catch up with
+    const auto t0 = std::chrono::steady_clock::now();
+    const double limit_s = 1e-9 * (double)pb->watchdog_ns + 1.0;
+    while (pb->h_flags[0] == 0) {
         CK(cudaMemcpyAsync(&w[0], ch + NLS_CH_REQ_SEQ, sizeof(w[0]), cudaMemcpyDeviceToHost, pb->ctl_stream));
         CK(cudaMemcpyAsync(&w[1], ch + NLS_CH_PASS_CTR, sizeof(w[1]), cudaMemcpyDeviceToHost, pb->ctl_stream));
         CK(cudaStreamSynchronize(pb->ctl_stream));
         if (w[0] >= w[1] + 1ull)
-            break;
+            return GSLNLS_SUCCESS;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
+            set_error("the resident trust-region server did not digest the last pass within the watchdog period");
+            return GSLNLS_ECOMM;
+        }
     }
     return GSLNLS_SUCCESS;
 }
@@ -398,9 +419,60 @@ void cache_drop(const gslnls_model *m)
 }
 } // namespace gslnls
 
+// The resident trust-region server needs the pass kernel to run NEXT TO it.  CUDA does not promise
+// concurrent kernels, and some environments rule them out: CUDA_LAUNCH_BLOCKING=1, and the injection
+// libraries of ncu / compute-sanitizer / cuda-gdb serialise launches.  Those are detected up front; anything
+// else is caught by the start-of-fit handshake (trs_server), after which the process stops using the server.
+namespace {
+std::atomic<bool> g_server_unsafe{false};
+bool env_set(const char *name)
+{
+    const char *c = std::getenv(name);
+    return c && *c && !(c[0] == '0' && c[1] == '\0');
+}
+bool serialising_environment()
+{
+    return env_set("CUDA_LAUNCH_BLOCKING") || env_set("CUDA_INJECTION64_PATH") || env_set("CUDA_INJECTION32_PATH") ||
+           env_set("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || env_set("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") ||
+           env_set("NV_SANITIZER_INJECTION_PORT_BASE");
+}
+} // namespace
+
+// weights mode of problems created from now on: gslnls_set_weights_mode(), else GSLNLS_WEIGHTS_MODE=gsl|consistent
+namespace {
+std::atomic<int> g_weights_mode{-1};
+int default_weights_mode()
+{
+    const int m = g_weights_mode.load();
+    if (m >= 0)
+        return m;
+    const char *c = std::getenv("GSLNLS_WEIGHTS_MODE");
+    return (c && (std::strcmp(c, "gsl") == 0 || std::strcmp(c, "1") == 0)) ? GSLNLS_WEIGHTS_GSL : GSLNLS_WEIGHTS_CONSISTENT;
+}
+} // namespace
+
 // ------------------------------------------------------------------------------------ C ABI
 
 extern "C" {
+
+GSLNLS_API int gslnls_set_weights_mode(int mode)
+{
+    if (mode != GSLNLS_WEIGHTS_CONSISTENT && mode != GSLNLS_WEIGHTS_GSL)
+        return GSLNLS_EINVAL;
+    g_weights_mode.store(mode);
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_set_weights_mode(gslnls_problem *pb, int mode)
+{
+    if (!pb || (mode != GSLNLS_WEIGHTS_CONSISTENT && mode != GSLNLS_WEIGHTS_GSL))
+        return GSLNLS_EINVAL;
+    if (pb->wgsl != mode) {
+        pb->wgsl = mode;
+        pb->var = nullptr; // another kernel variant
+    }
+    return GSLNLS_SUCCESS;
+}
 
 GSLNLS_API int gslnls_device_count(void)
 {
@@ -449,8 +521,13 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
         pb->prof_stride = std::max(1, std::atoi(c));
     if (const char *c = std::getenv("GSLNLS_SERVER"))
         pb->allow_server = std::atoi(c) != 0;
+    else if (serialising_environment())
+        pb->allow_server = false;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
         pb->watchdog_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000000ull;
+    pb->wgsl = default_weights_mode();
+    if (const char *c = std::getenv("GSLNLS_HANDSHAKE_MS"))
+        pb->handshake_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000ull;
     CK(cudaStreamCreateWithFlags(&pb->srv_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&pb->ctl_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&pb->ev_reset, cudaEventDisableTiming));
@@ -516,17 +593,28 @@ GSLNLS_API int gslnls_problem_upload(gslnls_problem *pb, const double *const *va
         pb->owned_cap = std::max<int64_t>(pb->n, 1);
         pb->bound = false;
     }
+    // pageable host memory (what R hands over) is pinned by the library: multi-threaded staging ring, upload.cpp
+    const void *src[NLS_MAX_VARS + 2];
+    void *dst[NLS_MAX_VARS + 2];
     for (int k = 0; k < pb->nvar; ++k) {
-        CK(cudaMemcpyAsync(pb->owned[k], vars[k], sizeof(double) * pb->n, cudaMemcpyHostToDevice, pb->stream));
+        src[k] = vars[k];
+        dst[k] = pb->owned[k];
         pb->dvars[k] = pb->owned[k];
     }
-    CK(cudaMemcpyAsync(pb->owned[pb->nvar], y, sizeof(double) * pb->n, cudaMemcpyHostToDevice, pb->stream));
+    src[pb->nvar] = y;
+    dst[pb->nvar] = pb->owned[pb->nvar];
     pb->dy = pb->owned[pb->nvar];
     pb->dw = nullptr;
     if (pb->has_w) {
-        CK(cudaMemcpyAsync(pb->owned[pb->nvar + 1], weights, sizeof(double) * pb->n, cudaMemcpyHostToDevice,
-                           pb->stream));
+        src[pb->nvar + 1] = weights;
+        dst[pb->nvar + 1] = pb->owned[pb->nvar + 1];
         pb->dw = pb->owned[pb->nvar + 1];
+    }
+    if (pb->n > 0) {
+        int rc = staged_upload(pb->device, src, dst, nbuf, sizeof(double) * (size_t)pb->n, pb->stream,
+                               upload_threads_default(pb->upload_sharing));
+        if (rc)
+            return rc;
     }
     pb->var = nullptr;
     return GSLNLS_SUCCESS;
@@ -674,6 +762,10 @@ GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta,
         return rc;
     const int p = pb->p;
     double *d_resid = nullptr, *d_grad = nullptr;
+    struct Guard { // the scratch arrays go back on every exit path
+        double *&a, *&b;
+        ~Guard() { cudaFree(a); cudaFree(b); }
+    } guard{d_resid, d_grad};
     const size_t n1 = (size_t)std::max<int64_t>(pb->n, 1);
     if (resid)
         CK(cudaMalloc(&d_resid, sizeof(double) * n1));
@@ -700,8 +792,6 @@ GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta,
     if (grad)
         CK(cudaMemcpyAsync(grad, d_grad, sizeof(double) * pb->n * p, cudaMemcpyDeviceToHost, pb->stream));
     CK(cudaStreamSynchronize(pb->stream));
-    cudaFree(d_resid);
-    cudaFree(d_grad);
     return GSLNLS_SUCCESS;
 }
 
@@ -737,20 +827,16 @@ static int fill_params(gslnls_problem *pb, const int *ci, const double *cd, int 
     return GSLNLS_SUCCESS;
 }
 
-GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start, const int *control_int,
-                                        const double *control_dbl)
+// device-side start of a fit with the parameters already in pb->P / pb->start: records, channel, traces.
+// Called by fit_begin, and again by fit_run when the resident server had to be abandoned.
+static int fit_setup(gslnls_problem *pb)
 {
-    if (!pb || !start || !control_int || !control_dbl)
-        return GSLNLS_EINVAL;
-    int rc = fill_params(pb, control_int, control_dbl, 0);
-    if (rc)
-        return rc;
     const int ntrace = pb->P.trace ? pb->P.maxiter + 1 : 0;
     stop_server(pb);
     const bool sharded = pb->comm && pb->comm->nranks > 1;
-    const bool use_server = pb->allow_server && pb->p <= trs_server_max_p() &&
+    const bool use_server = pb->allow_server && !g_server_unsafe.load() && pb->p <= trs_server_max_p() &&
                             trs::packet_doubles(pb->p) + 1 <= NLS_CH_MAXPK && (!sharded || pb->comm->p2p);
-    rc = prepare(pb, 1, ntrace, false, use_server);
+    int rc = prepare(pb, 1, ntrace, false, use_server);
     if (rc)
         return rc;
     if (use_server && pb->h_state_cap < pb->state_stride) {
@@ -765,9 +851,8 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
         CK(cudaMemsetAsync(pb->own_channel, 0, NLS_CH_BYTES, pb->stream));
     }
     const int p = pb->p;
-    pb->start.assign(start, start + p);
     pb->ncand = 1;
-    CK(cudaMemcpyAsync(pb->d_starts, start, sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+    CK(cudaMemcpyAsync(pb->d_starts, pb->start.data(), sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
     if (ntrace) {
         CK(cudaMemsetAsync(pb->d_partrace, 0, sizeof(double) * (size_t)ntrace * p, pb->stream));
         CK(cudaMemsetAsync(pb->d_ssrtrace, 0, sizeof(double) * ntrace, pb->stream));
@@ -777,23 +862,48 @@ GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start,
                         pb->stream));
     ++pb->launches;
     if (use_server) {
-        // the server starts once the records above are in place; the pass launches that follow on
-        // the main stream find their request through the channel, not through stream order
-        const bool tr = pb->P.trace != 0;
+        // the pass launches that follow on the main stream find their request through the channel, not
+        // through stream order; the server kernel itself goes out with the first pass (fit_run)
         CK(trs_launch_channel_begin(channel_of(pb), pb->stream));
         CK(cudaEventRecord(pb->ev_reset, pb->stream));
-        CK(cudaStreamWaitEvent(pb->srv_stream, pb->ev_reset, 0));
+        ++pb->launches;
         pb->h_flags[0] = 0;
-        CK(trs_launch_server(pb->P, channel_of(pb), sharded ? pb->comm->nranks : 1, pb->pk_stride, pb->d_state,
-                             pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr, tr ? pb->d_ssrtrace : nullptr,
-                             tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->d_hstate, pb->watchdog_ns,
-                             pb->srv_stream));
-        pb->launches += 2;
         pb->server_on = true;
+        pb->server_pending = true;
     }
     pb->active = true;
     pb->passes = 0;
     return GSLNLS_SUCCESS;
+}
+
+// launch the resident server chosen by fit_setup, right before the first pass of the fit is enqueued: its
+// start-of-fit handshake expects a running pass kernel within handshake_ns
+static int launch_pending_server(gslnls_problem *pb)
+{
+    if (!pb->server_pending)
+        return GSLNLS_SUCCESS;
+    const bool sharded = pb->comm && pb->comm->nranks > 1;
+    const bool tr = pb->P.trace != 0;
+    CK(cudaStreamWaitEvent(pb->srv_stream, pb->ev_reset, 0));
+    CK(trs_launch_server(pb->P, channel_of(pb), sharded ? pb->comm->nranks : 1, pb->pk_stride, pb->d_state,
+                         pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr, tr ? pb->d_ssrtrace : nullptr,
+                         tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->d_hstate, pb->watchdog_ns,
+                         pb->handshake_ns, pb->srv_stream));
+    ++pb->launches;
+    pb->server_pending = false;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_fit_begin(gslnls_problem *pb, const double *start, const int *control_int,
+                                        const double *control_dbl)
+{
+    if (!pb || !start || !control_int || !control_dbl)
+        return GSLNLS_EINVAL;
+    int rc = fill_params(pb, control_int, control_dbl, 0);
+    if (rc)
+        return rc;
+    pb->start.assign(start, start + pb->p);
+    return fit_setup(pb);
 }
 
 GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *done, int64_t *passes_run,
@@ -807,6 +917,9 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
     int fin = 0;
     CK(cudaEventRecord(pb->ev0, pb->stream));
     if (pb->server_on) {
+        int rc0 = launch_pending_server(pb);
+        if (rc0)
+            return rc0;
         // keep two chunks of pass launches in flight; the only host work per chunk is waiting for the
         // older chunk's event and looking at the done word the server writes into mapped host memory
         int slot = 0, inflight = 0;
@@ -834,6 +947,26 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             }
             fin = pb->h_flags[0] != 0;
         }
+        if (pb->h_flags[0] == 3) {
+            // The server never saw a pass kernel running beside it (start-of-fit handshake): kernels are being
+            // serialised by a tool or by the platform.  Nothing has been consumed; what is queued drains as idle
+            // launches.  Step this fit -- and every later one in this process -- launch-ordered instead.
+            CK(cudaStreamSynchronize(pb->stream));
+            CK(cudaStreamSynchronize(pb->srv_stream));
+            pb->server_on = false;
+            g_server_unsafe.store(true);
+            if (pb->comm && pb->comm->nranks > 1) {
+                set_error("the resident trust-region server cannot run next to the pass kernel on this rank "
+                          "(kernels are serialised); rerun every rank with GSLNLS_SERVER=0");
+                return GSLNLS_ECOMM;
+            }
+            int rc = fit_setup(pb);
+            if (rc)
+                return rc;
+            run = 0;
+            fin = 0;
+            goto launch_ordered;
+        }
         if (!fin || device_ms) {
             // a finished fit needs no synchronisation: its state record is already in host memory and the
             // launches still queued are no-ops that the next fit's launches simply follow
@@ -848,7 +981,11 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             fin = pb->h_flags[0] != 0;
         }
         if (pb->h_flags[0] == 2) {
-            set_error("trust-region server watchdog: a rank never delivered its packet");
+            if (pb->comm && pb->comm->nranks > 1)
+                set_error("trust-region server watchdog: a rank never delivered its packet");
+            else
+                set_error("trust-region server watchdog: the pass kernel never delivered its packet "
+                          "(GSLNLS_WATCHDOG_S seconds; GSLNLS_SERVER=0 selects launch-ordered stepping)");
             return GSLNLS_ECOMM;
         }
         if (device_ms)
@@ -859,6 +996,7 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             *passes_run = run;
         return GSLNLS_SUCCESS;
     }
+launch_ordered:
     while (!fin && (max_passes <= 0 || run < max_passes)) {
         int todo = pb->chunk;
         if (max_passes > 0)
@@ -1125,11 +1263,13 @@ GSLNLS_API int gslnls_fit_large_sharded(const gslnls_model *m, const double *con
         pb->n = n_local; // the buffers grow on demand in upload(); grid and workspace follow in prepare()
         pb->n_total = n_local;
         pb->comm = nullptr;
+        gslnls_problem_set_weights_mode(pb, default_weights_mode());
     } else {
         rc = gslnls_problem_create(m, n_local, weights != nullptr, device, &pb);
         if (rc)
             return rc;
     }
+    pb->upload_sharing = (comm && comm->local) ? comm->nranks : 1; // local group: all shards upload at once
     const double t1 = now();
     rc = gslnls_problem_upload(pb, vars, y, weights);
     if (rc == GSLNLS_SUCCESS && sharded) {
@@ -1195,12 +1335,17 @@ GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const
         dev[r] = devices ? devices[r] : r;
     // contiguous, 2-aligned row ranges (keeps every shard's columns 16-byte aligned); no empty shards
     int R = (int)std::min<int64_t>(ngpu, std::max<int64_t>(1, n / 2));
+    auto rows_per = [&](int r) {
+        int64_t q = (n + r - 1) / r;
+        return q + (q & 1);
+    };
+    while (R > 1 && (int64_t)(R - 1) * rows_per(R) >= n) // rounding the shard length up to even can empty the last shard
+        --R;
     if (R == 1)
         return gslnls_fit_large_sharded(m, vars, y, weights, n, start, control_int, control_dbl, dev[0], nullptr,
                                         want_resid_grad, out);
     dev.resize(R);
-    int64_t per = (n + R - 1) / R;
-    per += per & 1;
+    const int64_t per = rows_per(R);
     std::lock_guard<std::mutex> lk(g_group_mu); // one multi-GPU fit at a time per process
     if (g_group.devices != dev) {
         for (gslnls_comm *c : g_group.comms)
@@ -1272,6 +1417,7 @@ GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const
 GSLNLS_API void gslnls_cache_clear(void)
 {
     cache_drop(nullptr);
+    upload_pools_release();
     std::lock_guard<std::mutex> lk(g_group_mu);
     for (gslnls_comm *c : g_group.comms)
         gslnls_comm_free(c);

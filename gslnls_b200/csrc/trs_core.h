@@ -346,15 +346,17 @@ struct Solver {
     }
 
     // ---------------------------------------------------------------- packet -> (JTJ, g, f2)
-    // packet: [JTJ lower packed row-major | JTf | fTf].  Returns false if anything is non-finite
-    // (the reference's NaN/Inf scan of jac, src/nls_large.c:515-522, on the reduced quantities).
-    // the lanes share the scan (a private short-circuit loop over the 1224 entries of a p = 48 packet is
-    // 1224 dependent global loads: 180 us of a 350 us step, measured)
+    // packet: [JTJ lower packed row-major | JTf | fTf].  Returns false if the Jacobian was non-finite: the
+    // reference scans the n x p matrix J itself (src/nls_large.c:515-522); here a NaN or Inf entry of J
+    // shows as a NaN or Inf in its column's J^T J entries.  J^T f is NOT part of the scan: a +Inf residual
+    // next to a finite Jacobian makes g infinite or NaN and the reference iterates on with it.
+    // the lanes share the scan (a private short-circuit loop over the 1176 entries of a p = 48 packet is
+    // 1176 dependent global loads: 180 us of a 350 us step, measured)
     TRS_HD bool packet_finite(const double *pk) const
     {
         const int npk = p * (p + 1) / 2;
         bool ok = true;
-        for (int e = L.lane(); e < npk + p; e += L.nlanes())
+        for (int e = L.lane(); e < npk; e += L.nlanes())
             ok = ok & finite_d(pk[e]);
         return L.all(ok);
     }
@@ -913,32 +915,87 @@ struct Solver {
         return E_CONTINUE;
     }
 
-    // cond(J) = 1 / sqrt(rcond_1(J^T J)) with exact 1-norms; 0-dimensional failures give +inf
+    // cond(J) as callback_large prints it (src/nls_large.c:733-738): 1 / gsl_multilarge_nlinear_rcond, i.e.
+    // 1 / sqrt(rcond_1(J^T J)) from the Cholesky solver's gsl_linalg_cholesky_rcond: ||J^T J||_1 rebuilt from
+    // the factor (diagonal) and the saved off-diagonals, ||(J^T J)^-1||_1 by the Hager/Higham estimator
+    // (gsl_linalg_invnorm1: at most 5 power-like sweeps + the alternating-sign safeguard vector) -- not the
+    // exact norm: the trace shows the number the reference shows.  A failed factorisation prints +Inf.
     TRS_HD double cond_J()
     {
-        double anorm = 0.0;
-        for (int j = 0; j < p; ++j) {
-            double s = 0.0;
-            for (int i = 0; i < p; ++i)
-                s += fabs(i >= j ? JTJ[i * p + j] : JTJ[j * p + i]);
-            anorm = anorm > s ? anorm : s;
-        }
         if (factor(0.0))
             return HUGE_VAL;
-        double ainv = 0.0;
-        // column sums of |A^-1| from p unit solves (each lane does all of them privately)
-        for (int j = 0; j < p; ++j)
-            w2[j] = 0.0;
-        for (int k = 0; k < p; ++k) {
-            for (int i = 0; i < p; ++i)
-                w1[i] = (i == k) ? 1.0 : 0.0;
-            solve_neg(w1, w3);
-            double s = 0.0;
-            for (int i = 0; i < p; ++i)
-                s += fabs(w3[i]);
-            ainv = ainv > s ? ainv : s;
+        double anorm = 0.0;
+        for (int j = 0; j < p; ++j) {
+            double ajj = 0.0, sum = 0.0;
+            for (int k = 0; k <= j; ++k)
+                ajj += A[j * p + k] * A[j * p + k];
+            for (int i = 0; i < j; ++i) {
+                const double a = fabs(JTJ[j * p + i]);
+                sum += a;
+                w2[i] += a;
+            }
+            w2[j] = sum + fabs(ajj);
         }
-        return sqrt(anorm * ainv);
+        for (int i = 0; i < p; ++i)
+            anorm = anorm > w2[i] ? anorm : w2[i];
+        if (anorm == 0.0)
+            return HUGE_VAL;
+        double *xv = w1, *v = w2, *xi = w3, *t = W0;
+        const int n = p;
+        for (int i = 0; i < n; ++i)
+            xv[i] = 1.0 / (double)n;
+        solve_neg(xv, t);
+        double gamma = 0.0;
+        for (int i = 0; i < n; ++i) {
+            v[i] = -t[i];
+            gamma += fabs(v[i]);
+            xi[i] = v[i] >= 0.0 ? 1.0 : -1.0;
+        }
+        solve_neg(xi, t);
+        for (int i = 0; i < n; ++i)
+            xv[i] = -t[i];
+        for (int k = 0; k < 5; ++k) {
+            int jmax = 0;
+            double amax = 0.0;
+            for (int i = 0; i < n; ++i)
+                if (fabs(xv[i]) > amax) {
+                    amax = fabs(xv[i]);
+                    jmax = i;
+                }
+            for (int i = 0; i < n; ++i)
+                xv[i] = (i == jmax) ? 1.0 : 0.0;
+            solve_neg(xv, t);
+            const double gamma_old = gamma;
+            gamma = 0.0;
+            bool same = true;
+            for (int i = 0; i < n; ++i) {
+                v[i] = -t[i];
+                gamma += fabs(v[i]);
+                same = same && ((v[i] >= 0.0 ? 1.0 : -1.0) == xi[i]);
+            }
+            if (same || gamma < gamma_old)
+                break;
+            for (int i = 0; i < n; ++i)
+                xi[i] = v[i] >= 0.0 ? 1.0 : -1.0;
+            solve_neg(xi, t);
+            for (int i = 0; i < n; ++i)
+                xv[i] = -t[i];
+        }
+        double sgn = 1.0;
+        for (int i = 0; i < n; ++i) {
+            xv[i] = sgn * (1.0 + (double)i / ((double)n - 1.0));
+            sgn = -sgn;
+        }
+        solve_neg(xv, t);
+        double alt = 0.0;
+        for (int i = 0; i < n; ++i)
+            alt += fabs(t[i]);
+        alt = 2.0 * alt / (3.0 * (double)n);
+        if (alt > gamma)
+            gamma = alt;
+        if (gamma == 0.0)
+            return HUGE_VAL;
+        return 1.0 / sqrt((1.0 / anorm) / gamma);
     }
 
     // ---------------------------------------------------------------- state record I/O

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
                                                  double *state, double *packet, double *req, double *partrace,
                                                  double *ssrtrace, double *condtrace, int *ndone,
                                                  volatile int *host_flags, double *host_state,
-                                                 unsigned long long watchdog_ns)
+                                                 unsigned long long watchdog_ns, unsigned long long handshake_ns)
 {
     extern __shared__ double trs_smem[];
     const int lane = threadIdx.x & 31;
@@ -82,33 +82,47 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
     const unsigned long long *flags = (const unsigned long long *)(channel + NLS_CH_FLAGS);
     const unsigned long long *abort_w = (const unsigned long long *)(channel + NLS_CH_ABORT);
     const double *mbox = (const double *)(channel + NLS_CH_DATA);
+    const unsigned long long *pass_seen = (const unsigned long long *)(channel + NLS_CH_PASS_SEEN);
     unsigned long long k = __ldcg((const unsigned long long *)(channel + NLS_CH_FIT_SEQ0));
+    // start-of-fit handshake: until the first pass kernel of this fit has been seen RUNNING next to this
+    // kernel, the wait below is bounded by handshake_ns, not by the watchdog.  Kernels are not guaranteed to
+    // run concurrently (ncu, compute-sanitizer, cuda-gdb and CUDA_LAUNCH_BLOCKING=1 serialise them): the
+    // server then leaves with host flag 3 and the host steps the fit launch-ordered (K1 -> K3 -> K1 ...).
+    bool partner_seen = false;
     trs::Solver<PMAX, trs::WarpLanes, FIXED> S(P, trs::WarpLanes(), trs_smem, trs_smem + P.p * P.p);
     if ((int)__ldcg(state + trs::S_PHASE) == trs::PH_DONE)
         return;
     for (;; ++k) {
         // ---- wait for pass k from every rank (lane r watches rank r) ----
         unsigned long long t0 = 0ull, spins = 0ull;
-        int why = 0; // 0 packet, 1 abort, 2 watchdog
+        int why = 0; // 0 packet, 1 abort, 2 watchdog, 3 no concurrent pass kernel (handshake)
         for (;;) {
             const bool have = lane >= nranks || ld_acquire_sys(flags + 16 * lane) >= k;
             if (__all_sync(0xffffffffu, have))
                 break;
             if ((++spins & 255ull) == 0ull) {
-                unsigned long long a = 0ull, t = 0ull;
+                unsigned long long a = 0ull, t = 0ull, seen = 0ull;
                 if (lane == 0) {
                     a = ld_acquire_sys(abort_w);
                     t = globaltimer_ns();
+                    if (!partner_seen)
+                        seen = ld_acquire_sys(pass_seen);
                 }
                 a = __shfl_sync(0xffffffffu, a, 0);
                 t = __shfl_sync(0xffffffffu, t, 0);
+                seen = __shfl_sync(0xffffffffu, seen, 0);
                 if (a) {
                     why = 1;
                     break;
                 }
+                if (!partner_seen && seen >= k)
+                    partner_seen = true;
                 if (t0 == 0ull)
                     t0 = t;
-                else if (t - t0 > watchdog_ns) {
+                else if (!partner_seen && t - t0 > handshake_ns) {
+                    why = 3;
+                    break;
+                } else if (t - t0 > watchdog_ns) {
                     why = 2;
                     break;
                 }
@@ -116,6 +130,19 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
         }
         if (why == 1)
             return; // fit_end before completion: state record is current, request k stays published
+        if (why == 3) {
+            // nothing has been consumed: the state record is still the start of the fit.  Queued pass
+            // launches fall through as idle no-ops (request mode IDLE, request sequence far ahead).
+            if (lane == 0) {
+                req[0] = (double)trs::MODE_IDLE;
+                __threadfence();
+                st_release_gpu(req_seq, k + NLS_CH_GONE_BUMP);
+                __threadfence_system();
+                host_flags[0] = 3;
+            }
+            return;
+        }
+        partner_seen = true; // a packet arrived: the kernels do run side by side
         if (why == 2) {
             // a peer never delivered: fail the fit instead of hanging the GPU
             if (lane == 0) {
@@ -176,6 +203,7 @@ __global__ void trs_channel_begin(char *channel)
         const unsigned long long done = *(unsigned long long *)(channel + NLS_CH_PASS_CTR);
         *(unsigned long long *)(channel + NLS_CH_FIT_SEQ0) = done + 1ull;
         *(unsigned long long *)(channel + NLS_CH_ABORT) = 0ull;
+        *(unsigned long long *)(channel + NLS_CH_PASS_SEEN) = 0ull; // idle launches behind the last fit wrote it
         __threadfence();
         *(unsigned long long *)(channel + NLS_CH_REQ_SEQ) = done + 1ull; // request 1 of this fit = trs_reset's
     }
@@ -235,12 +263,13 @@ cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream)
 cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
                               double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
                               int *ndone, int *host_flags_dev, double *host_state_dev, unsigned long long watchdog_ns,
-                              cudaStream_t stream)
+                              unsigned long long handshake_ns, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * 2 * (size_t)P.p * P.p;
 #define TRS_SERVER_LAUNCH(PM, FX)                                                                                  \
     trs_server<PM, FX><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace, \
-                                                condtrace, ndone, host_flags_dev, host_state_dev, watchdog_ns)
+                                                condtrace, ndone, host_flags_dev, host_state_dev, watchdog_ns, \
+                                                handshake_ns)
     if (P.p == 2)
         TRS_SERVER_LAUNCH(2, true);
     else if (P.p == 3)

@@ -22,7 +22,7 @@ cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream);
 cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
                               double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
                               int *ndone, int *host_flags_dev, double *host_state_dev, unsigned long long watchdog_ns,
-                              cudaStream_t stream);
+                              unsigned long long handshake_ns, cudaStream_t stream);
 cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int count, int nranks,
                                     cudaStream_t stream);
 } // namespace gslnls

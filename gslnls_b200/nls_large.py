@@ -15,6 +15,9 @@ from . import _lib
 from .control import ALGORITHMS, gsl_nls_control, pack_control
 
 JAC_MODES = {True: 0, "symbolic": 0, "forward": 1, "center": 2}
+# raw weights in the normal equations: "consistent" scales the rows of f and J by sqrt(w) (default);
+# "gsl" reproduces the reference -- libgsl scales f / fvv, gsl_df_large's J^T J stays unweighted
+WEIGHTS_MODES = {"consistent": 0, "gsl": 1}
 FVV_MODES = {None: 0, False: 0, True: 1, "symbolic": 1, "fd": 2}
 
 
@@ -102,6 +105,10 @@ class Problem:
         _lib.check(_lib.lib().gslnls_problem_bind_device(self.handle, arr, C.c_void_p(int(y_ptr)),
                                                          C.c_void_p(int(w_ptr)) if w_ptr else None))
         self._keep = list(keepalive)
+        return self
+
+    def set_weights_mode(self, mode):
+        _lib.check(_lib.lib().gslnls_problem_set_weights_mode(self.handle, WEIGHTS_MODES[mode]))
         return self
 
     def set_comm(self, comm):
@@ -359,7 +366,7 @@ class GslNls:
 
 
 def fit_large_multi(model, cols, y, weights, start, algorithm="lm", control=None, trace=False, devices=(0,),
-                    want_resid_grad=False):
+                    want_resid_grad=False, weights_mode="consistent"):
     """gslnls_fit_large_multi(): one call, host arrays in, the rows split over `devices` inside the library
     (one host thread and one PCIe link per GPU, packets over NVLink peer memory)"""
     ctrl = gsl_nls_control() if control is None else control
@@ -371,9 +378,14 @@ def fit_large_multi(model, cols, y, weights, start, algorithm="lm", control=None
     arr = (_lib.c_double_p * max(len(cols), 1))(*[_dptr(c) for c in cols])
     dev = np.ascontiguousarray(list(devices), dtype=np.int32)
     res = _lib.Result()
-    rc = _lib.lib().gslnls_fit_large_multi(model.handle, arr, _dptr(y), _dptr(w) if w is not None else None, y.size,
-                                           _dptr(st), ci.ctypes.data_as(_lib.c_int_p), _dptr(cd), dev.size,
-                                           dev.ctypes.data_as(_lib.c_int_p), int(want_resid_grad), C.byref(res))
+    _lib.check(_lib.lib().gslnls_set_weights_mode(WEIGHTS_MODES[weights_mode]))  # one-shot calls use the default
+    try:
+        rc = _lib.lib().gslnls_fit_large_multi(model.handle, arr, _dptr(y), _dptr(w) if w is not None else None,
+                                               y.size, _dptr(st), ci.ctypes.data_as(_lib.c_int_p), _dptr(cd),
+                                               dev.size, dev.ctypes.data_as(_lib.c_int_p), int(want_resid_grad),
+                                               C.byref(res))
+    finally:
+        _lib.lib().gslnls_set_weights_mode(0)
     _lib.check(rc)
     out = _result_to_dict(res, st.size, y.size, int(ci[0]), trace, want_resid_grad)
     _lib.lib().gslnls_result_free(C.byref(res))
@@ -381,7 +393,8 @@ def fit_large_multi(model, cols, y, weights, start, algorithm="lm", control=None
 
 
 def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=None, fvv=None, trace=False,
-                  weights=None, y=None, device=0, comm=None, model=None, devices=None, **kwargs):
+                  weights=None, y=None, device=0, comm=None, model=None, devices=None, weights_mode="consistent",
+                  **kwargs):
     """Fit a nonlinear least-squares model with the large-problem trust-region path on a B200.
 
     fn        two-sided formula text "y ~ A * exp(-lam * x) + b" (formula method, R/nls_large.R:135),
@@ -392,7 +405,11 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     jac       True: symbolic Jacobian as deriv() would give; "forward"/"center": finite differences
               with the step rule of src/fdjac.c.  Required, as in the reference (R/nls_large.R:319-321)
     fvv       for "lmaccel": True symbolic, "fd" finite difference (src/fdfvv.c); required (:354-356)
+    weights_mode  "consistent" (default): g = J^T W f, J^T W J; "gsl": exactly the reference's numbers for
+              non-unit weights (sqrt(w) on f only, unweighted J^T J -- what R/nls_large.R:587-600 + libgsl compute)
     """
+    if weights_mode not in WEIGHTS_MODES:
+        raise ValueError("'weights_mode' should be one of \"consistent\", \"gsl\"")
     if algorithm not in ALGORITHMS:
         raise ValueError("'arg' should be one of %s" % ", ".join('"%s"' % a for a in ALGORITHMS))
     if data is None:
@@ -461,12 +478,13 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     if devices is not None and len(devices) > 1:
         # several GPUs from this one process: the library splits the rows and runs one thread per GPU
         cfit = fit_large_multi(mdl, cols, lhs, weights, st, algorithm, ctrl, bool(trace), devices,
-                               want_resid_grad=True)
+                               want_resid_grad=True, weights_mode=weights_mode)
         obj = GslNls(fn, pnames, cfit, None, mdl, ctrl, algorithm, weights, lhs, bool(trace))
         obj._resid = -cfit["resid"]
         obj._device = int(devices[0])
         return obj
     pb = Problem(mdl, lhs.size, weights is not None, device)
+    pb.set_weights_mode(weights_mode)
     pb.upload(cols, lhs, weights)
     if comm is not None:
         pb.set_comm(comm)

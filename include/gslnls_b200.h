@@ -69,6 +69,18 @@ enum {
     GSLNLS_FVV_FD = 2        /* Transtrum-Sethna Eq. 19, src/fdfvv.c:35-77 */
 };
 
+/* how raw `weights` enter the normal equations */
+enum {
+    /* default: rows of f AND J are scaled by sqrt(w_i) (what src/fdf.c:135-177 does on the multifit path): the
+     * packet is that of the weighted problem, g = J^T W f and J^T W J, covar = (J^T W J)^-1 */
+    GSLNLS_WEIGHTS_CONSISTENT = 0,
+    /* reference-compatible: what gsl_nls_large() computes through gsl_multilarge_nlinear_winit
+     * (src/nls_large.c:216-222): libgsl scales f and fvv by sqrt(w_i) but never sees J, and the reference's
+     * callback gsl_df_large (:474-653) forms J^T u and J^T J from the UNWEIGHTED Jacobian.  Same inputs, same
+     * numbers as the reference for non-unit weights, including the returned `grad` (unweighted, :354-363). */
+    GSLNLS_WEIGHTS_GSL = 1
+};
+
 typedef struct gslnls_model gslnls_model;     /* compiled model: generated CUDA + cubin, opaque */
 typedef struct gslnls_problem gslnls_problem; /* device-resident data + solver workspace, opaque */
 typedef struct gslnls_comm gslnls_comm;       /* multi-GPU exchange context, opaque */
@@ -158,12 +170,19 @@ GSLNLS_API void gslnls_cache_clear(void);
 GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int has_weights, int device,
                                      gslnls_problem **out);
 GSLNLS_API void gslnls_problem_free(gslnls_problem *pb);
-/* copy host data into library-owned device buffers (pinned staging, async copy engine) */
+/* copy host data into library-owned device buffers.  Pageable host memory (what R passes) is pinned by the
+ * library: worker threads stage slices through pinned buffers while the copy engine drains them (upload.cpp);
+ * already pinned / registered memory goes to the copy engine directly.  The host arrays may be released as
+ * soon as the call returns. */
 GSLNLS_API int gslnls_problem_upload(gslnls_problem *pb, const double *const *vars, const double *y,
                                      const double *weights);
 /* use caller-owned device buffers (plain device pointers); they must outlive the problem */
 GSLNLS_API int gslnls_problem_bind_device(gslnls_problem *pb, const double *const *dev_vars,
                                           const double *dev_y, const double *dev_weights);
+/* weights mode (GSLNLS_WEIGHTS_*) of this problem; the process-wide default for problems created later and for
+ * the one-shot calls is set by gslnls_set_weights_mode() or the environment (GSLNLS_WEIGHTS_MODE=gsl) */
+GSLNLS_API int gslnls_problem_set_weights_mode(gslnls_problem *pb, int mode);
+GSLNLS_API int gslnls_set_weights_mode(int mode);
 /* attach an exchange context: this problem holds one shard of a global problem */
 GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm);
 GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const int *control_int,
@@ -225,6 +244,12 @@ GSLNLS_API void gslnls_comm_free(gslnls_comm *c);
 GSLNLS_API int gslnls_comm_has_peer_memory(const gslnls_comm *c);
 GSLNLS_API int gslnls_comm_rank(const gslnls_comm *c);
 GSLNLS_API int gslnls_comm_size(const gslnls_comm *c);
+
+/* ---- measurement hooks (bench.py roofline denominators; not on the product path) -------------- */
+/* FP64-pipe issue peak of the device in TFLOP/s: independent DFMA chains, and mma.sync.m8n8k4.f64 (DMMA) */
+GSLNLS_API int gslnls_measure_fp64_peak(int device, double *dfma_tflops, double *dmma_tflops);
+/* read bandwidth of a `bytes`-sized device buffer (16-byte streaming loads, best of 6), GB/s */
+GSLNLS_API int gslnls_measure_read_bandwidth(int device, size_t bytes, double *gb_per_s);
 
 /* ---- misc -------------------------------------------------------------------------------------- */
 GSLNLS_API const char *gslnls_strerror(int code);   /* gsl_strerror() strings + library errors */

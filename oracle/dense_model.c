@@ -306,7 +306,7 @@ int orc_dense_fvv(const double *x, const double *v, void *params, double *fvv)
 typedef struct {
     size_t p, nrow;
     double chisq;
-    double *partrace, *ssrtrace;
+    double *partrace, *ssrtrace, *condtrace;
 } trace_ctx;
 
 /* callback_large, src/nls_large.c:715-739 (printing dropped) */
@@ -319,13 +319,18 @@ static void trace_cb(size_t iter, void *params, const orc_workspace *w)
     t->ssrtrace[iter] = t->chisq;
     for (size_t k = 0; k < t->p; ++k)
         t->partrace[iter + t->nrow * k] = x[k];
+    if (t->condtrace) { /* :733-738: cond(J) = 1 / rcond as printed; a failed factorisation leaves rcond = 0 */
+        double rcond = 0.0;
+        orc_rcond(&rcond, (orc_workspace *)w);
+        t->condtrace[iter] = 1.0 / rcond;
+    }
 }
 
 void orc_fit_result_free(orc_fit_result *r)
 {
     if (!r)
         return;
-    free(r->par); free(r->covar); free(r->partrace); free(r->ssrtrace);
+    free(r->par); free(r->covar); free(r->partrace); free(r->ssrtrace); free(r->condtrace);
     memset(r, 0, sizeof(*r));
 }
 
@@ -424,7 +429,7 @@ int orc_nls_large(orc_rows_fn rows, void *data, const double *y, const double *w
     fdf.n = n; fdf.p = p; fdf.params = &m;
 
     w = orc_alloc(&P, n, p);
-    if (weights) {
+    if (weights && !(opts && opts->weights_gsl)) { /* reference mode: gsl_df_large never weights J */
         double *sw = (double *)malloc(n * sizeof(double));
         for (size_t i = 0; i < n; ++i)
             sw[i] = sqrt(weights[i]);
@@ -437,6 +442,7 @@ int orc_nls_large(orc_rows_fn rows, void *data, const double *y, const double *w
     if (verbose) {
         out->partrace = (double *)calloc((niter + 1) * p, sizeof(double));
         out->ssrtrace = (double *)calloc(niter + 1, sizeof(double));
+        out->condtrace = (double *)calloc(niter + 1, sizeof(double));
     }
 
     if (status == ORC_SUCCESS) {
@@ -447,7 +453,7 @@ int orc_nls_large(orc_rows_fn rows, void *data, const double *y, const double *w
             chisq_init += r[i] * r[i];
         chisq0 = chisq1 = chisq_init;
         tc.p = p; tc.nrow = niter + 1; tc.chisq = chisq_init;
-        tc.partrace = out->partrace; tc.ssrtrace = out->ssrtrace;
+        tc.partrace = out->partrace; tc.ssrtrace = out->ssrtrace; tc.condtrace = out->condtrace;
         if (verbose) {
             out->ssrtrace[0] = chisq_init;
             for (size_t k = 0; k < p; ++k)
@@ -528,7 +534,8 @@ int orc_eval_packet(orc_rows_fn rows, void *data, const double *y, const double 
         sw = (double *)malloc(n * sizeof(double));
         for (size_t i = 0; i < n; ++i)
             sw[i] = sqrt(weights[i]);
-        m.sqrt_wts = sw;
+        if (!(opts && opts->weights_gsl))
+            m.sqrt_wts = sw;
     }
     s = orc_dense_f(theta, &m, f);
     if (!s && sw)

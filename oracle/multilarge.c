@@ -1284,37 +1284,104 @@ int orc_covar(double *covar, orc_workspace *w)
     return ORC_SUCCESS;
 }
 
-/* reciprocal condition number of J: sqrt(rcond_1(J^T J)), exact 1-norms (GSL estimates them) */
+/* gsl_multilarge_nlinear_rcond (call site src/nls_large.c:735) -> the Cholesky solver's rcond (GSL
+ * multilarge_nlinear/cholesky.c): re-factor J^T J, gsl_linalg_cholesky_rcond, square root.  Third-party,
+ * restated from GSL 2.x linalg/cholesky.c + linalg/condest.c:
+ *   ||A||_1      cholesky_norm1: diagonal rebuilt from the factor (dot of row j of L with itself), off-diagonal
+ *                moduli from the original matrix that decomp1 keeps in the upper triangle;
+ *   ||A^-1||_1   gsl_linalg_invnorm1: Hager's estimator with Higham's refinements (Algorithm 4.1 of
+ *                "FORTRAN codes for estimating the one-norm of a real or complex matrix", ACM TOMS 14, 1988):
+ *                start x = 1/N, at most five sign-vector sweeps, then the alternating-sign safeguard vector. */
+static int sign_of(double v) { return v >= 0.0 ? 1 : -1; }
+
 int orc_rcond(double *rcond, orc_workspace *w)
 {
-    const size_t p = w->p;
-    double *A = (double *)malloc(p * p * sizeof(double));
-    double anorm = 0.0, ainvnorm = 0.0;
+    const size_t N = w->p;
+    double *L = (double *)malloc(N * N * sizeof(double));
+    double *work = (double *)calloc(4 * N, sizeof(double));
+    double *x = work, *v = work + N, *xi = work + 2 * N, *col = work + 3 * N;
+    double Anorm = 0.0, gamma, gamma_old, temp;
     int status;
-    for (size_t j = 0; j < p; ++j) {
-        double s = 0.0;
-        for (size_t i = 0; i < p; ++i)
-            s += fabs(i >= j ? w->JTJ[i * p + j] : w->JTJ[j * p + i]);
-        anorm = MAXV(anorm, s);
-    }
-    for (size_t i = 0; i < p; ++i)
-        for (size_t j = 0; j < p; ++j)
-            A[i * p + j] = (j <= i) ? w->JTJ[i * p + j] : 0.0;
-    status = cholesky_decomp1(p, A);
+    *rcond = 0.0;
+    for (size_t i = 0; i < N; ++i)
+        for (size_t j = 0; j < N; ++j)
+            L[i * N + j] = (j <= i) ? w->JTJ[i * N + j] : 0.0;
+    status = cholesky_decomp1(N, L);
     if (status) {
-        free(A);
-        *rcond = 0.0;
+        free(L);
+        free(work);
         return status;
     }
-    cholesky_invert(p, A);
-    for (size_t j = 0; j < p; ++j) {
-        double s = 0.0;
-        for (size_t i = 0; i < p; ++i)
-            s += fabs(A[i * p + j]);
-        ainvnorm = MAXV(ainvnorm, s);
+    /* cholesky_norm1 */
+    for (size_t j = 0; j < N; ++j) {
+        double sum = 0.0, Ajj = 0.0;
+        for (size_t k = 0; k <= j; ++k)
+            Ajj += L[j * N + k] * L[j * N + k];
+        for (size_t i = 0; i < j; ++i) {
+            const double absAij = fabs(w->JTJ[j * N + i]);
+            sum += absAij;
+            col[i] += absAij;
+        }
+        col[j] = sum + fabs(Ajj);
     }
-    free(A);
-    *rcond = sqrt(1.0 / (anorm * ainvnorm));
+    for (size_t i = 0; i < N; ++i)
+        Anorm = MAXV(Anorm, col[i]);
+    if (Anorm == 0.0) {
+        free(L);
+        free(work);
+        return ORC_SUCCESS;
+    }
+    /* gsl_linalg_invnorm1 with Ainvx = two triangular solves on L */
+    for (size_t i = 0; i < N; ++i)
+        x[i] = 1.0 / (double)N;
+    cholesky_solve(N, L, x, v);
+    gamma = 0.0;
+    for (size_t i = 0; i < N; ++i) {
+        gamma += fabs(v[i]);
+        xi[i] = (double)sign_of(v[i]);
+    }
+    cholesky_solve(N, L, xi, x);
+    for (size_t k = 0; k < 5; ++k) {
+        size_t jmax = 0;
+        double amax = 0.0;
+        int same = 1;
+        for (size_t i = 0; i < N; ++i) /* idamax: first index of the largest modulus */
+            if (fabs(x[i]) > amax) {
+                amax = fabs(x[i]);
+                jmax = i;
+            }
+        for (size_t i = 0; i < N; ++i)
+            v[i] = (i == jmax) ? 1.0 : 0.0;
+        cholesky_solve(N, L, v, v);
+        gamma_old = gamma;
+        gamma = 0.0;
+        for (size_t i = 0; i < N; ++i) {
+            gamma += fabs(v[i]);
+            if ((double)sign_of(v[i]) != xi[i])
+                same = 0;
+        }
+        if (same || gamma < gamma_old)
+            break;
+        for (size_t i = 0; i < N; ++i)
+            xi[i] = (double)sign_of(v[i]);
+        cholesky_solve(N, L, xi, x);
+    }
+    temp = 1.0;
+    for (size_t i = 0; i < N; ++i) {
+        x[i] = temp * (1.0 + (double)i / ((double)N - 1.0));
+        temp = -temp;
+    }
+    cholesky_solve(N, L, x, x);
+    temp = 0.0;
+    for (size_t i = 0; i < N; ++i)
+        temp += fabs(x[i]);
+    temp = 2.0 * temp / (3.0 * (double)N);
+    if (temp > gamma)
+        gamma = temp;
+    if (gamma != 0.0)
+        *rcond = sqrt((1.0 / Anorm) / gamma);
+    free(L);
+    free(work);
     return ORC_SUCCESS;
 }
 

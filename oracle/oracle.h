@@ -148,6 +148,7 @@ typedef struct {
     double *partrace; /* (maxiter+1)*p column-major, row = iteration (only if trace) */
     double *ssrtrace; /* maxiter+1 */
     double chisq_init;
+    double *condtrace; /* maxiter+1: cond(J) = 1/rcond as callback_large prints it (:733-738); row 0 unused */
 } orc_fit_result;
 
 /* C_nls_large_internal restated.  control_int[7], control_dbl[8] exactly as packed by
@@ -157,6 +158,9 @@ typedef struct {
     int threads;    /* OpenMP threads for the O(n) work (baseline timing); 0/1 = sequential */
     int fd_jac;     /* 0 analytic / 1 forward / 2 centre; step h_df = control_dbl[3] */
     int fd_fvv;     /* lmaccel without analytic fvv: FD rule with h_fvv = control_dbl[4] */
+    int weights_gsl; /* 1: weights exactly as the reference applies them -- gsl_multilarge_nlinear_winit scales f
+                        (and fvv) by sqrt(w), gsl_df_large (src/nls_large.c:474-653) leaves J unweighted;
+                        0: rows of J scaled too (the repo's default mode) */
 } orc_opts;
 
 int orc_nls_large(orc_rows_fn rows, void *data, const double *y, const double *weights, size_t n,

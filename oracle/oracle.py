@@ -30,14 +30,16 @@ class _XData(C.Structure):
 
 
 class _Opts(C.Structure):
-    _fields_ = [("longdouble", C.c_int), ("threads", C.c_int), ("fd_jac", C.c_int), ("fd_fvv", C.c_int)]
+    _fields_ = [("longdouble", C.c_int), ("threads", C.c_int), ("fd_jac", C.c_int), ("fd_fvv", C.c_int),
+                ("weights_gsl", C.c_int)]
 
 
 class _FitResult(C.Structure):
     _fields_ = [("par", C.POINTER(C.c_double)), ("covar", C.POINTER(C.c_double)), ("ssr", C.c_double),
                 ("ssrtol", C.c_double), ("niter", C.c_int), ("conv", C.c_int), ("info", C.c_int),
                 ("neval", C.c_size_t * 4), ("partrace", C.POINTER(C.c_double)),
-                ("ssrtrace", C.POINTER(C.c_double)), ("chisq_init", C.c_double)]
+                ("ssrtrace", C.POINTER(C.c_double)), ("chisq_init", C.c_double),
+                ("condtrace", C.POINTER(C.c_double))]
 
 
 def build(force=False):
@@ -119,8 +121,10 @@ class _Model:
 
 
 def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=None, longdouble=False,
-              threads=0, fd_jac=0, fd_fvv=0, want_resid_grad=False, **control):
-    """C_nls_large restated; returns a dict with the fields of the reference's result list."""
+              threads=0, fd_jac=0, fd_fvv=0, want_resid_grad=False, weights_gsl=False, **control):
+    """C_nls_large restated; returns a dict with the fields of the reference's result list.
+    weights_gsl=True applies raw weights exactly as the reference does (sqrt(w) on f and fvv inside libgsl,
+    J^T J from the unweighted Jacobian); False scales the rows of J too (the product's default mode)."""
     L = lib()
     y = np.ascontiguousarray(y, dtype=np.float64)
     start = np.ascontiguousarray(start, dtype=np.float64)
@@ -130,7 +134,7 @@ def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=No
     m = _Model(model, x=x, p=p)
     if have_fvv is None:
         have_fvv = (algorithm == "lmaccel") and not fd_fvv
-    opts = _Opts(int(longdouble), int(threads), int(fd_jac), int(fd_fvv))
+    opts = _Opts(int(longdouble), int(threads), int(fd_jac), int(fd_fvv), int(bool(weights_gsl)))
     res = _FitResult()
     resid = np.empty(n) if want_resid_grad else None
     grad = np.empty(n * p) if want_resid_grad else None
@@ -148,6 +152,7 @@ def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=No
     if ci[1]:
         out["partrace"] = np.ctypeslib.as_array(res.partrace, shape=(p, maxiter + 1)).copy().T[: res.niter + 1]
         out["ssrtrace"] = np.ctypeslib.as_array(res.ssrtrace, shape=(maxiter + 1,)).copy()[: res.niter + 1]
+        out["condtrace"] = np.ctypeslib.as_array(res.condtrace, shape=(maxiter + 1,)).copy()[: res.niter + 1]
     if want_resid_grad:
         out["resid"] = resid
         out["grad"] = grad.reshape(p, n).T.copy()
@@ -155,7 +160,7 @@ def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=No
     return out
 
 
-def eval_packet(model, y, theta, x=None, weights=None, longdouble=False, threads=0, fd_jac=0):
+def eval_packet(model, y, theta, x=None, weights=None, longdouble=False, threads=0, fd_jac=0, weights_gsl=False):
     """[J^T J lower packed (row-major (0,0),(1,0),(1,1),..) | J^T f | f^T f] in reference order."""
     L = lib()
     y = np.ascontiguousarray(y, dtype=np.float64)
@@ -163,7 +168,7 @@ def eval_packet(model, y, theta, x=None, weights=None, longdouble=False, threads
     n, p = y.size, theta.size
     w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
     m = _Model(model, x=x, p=p)
-    opts = _Opts(int(longdouble), int(threads), int(fd_jac), 0)
+    opts = _Opts(int(longdouble), int(threads), int(fd_jac), 0, int(bool(weights_gsl)))
     pk = np.zeros(p * (p + 1) // 2 + p + 1)
     s = L.orc_eval_packet(m.fnptr, m.data, _dptr(y), _dptr(w), n, p, _dptr(theta), C.byref(opts), _dptr(pk))
     if s:

@@ -7,6 +7,9 @@ import pytest
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
+import os  # noqa: E402
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 ALGS = ["lm", "lmaccel", "dogleg", "ddogleg", "subspace2D", "cgst"]
 
@@ -435,4 +438,175 @@ def test_tma_ring_shrinks_to_fit_many_columns(G, monkeypatch):
     assert rel_packet_err(got, ref, 3) < 1e-10  # numpy double sums here, not the long-double oracle
     fit = pb.fit([1.0, 1.0, 0.0])
     assert fit["conv"] == 0 and np.allclose(fit["par"], [2.0, 0.7, 0.5], rtol=2e-2)
+    pb.close()
+
+
+# ---------------------------------------------------------------- round-2 additions
+def test_center_difference_jacobian_on_gpu(G, readme_examples):
+    """jac="center": src/fdjac.c:81-128 (+-delta/2, delta = h |x_j| or h) inside the pass kernel, against the
+    oracle's restatement of the same rule -- packet at 1e-9 of the centred-difference oracle (differences of
+    nearly equal numbers: the FD noise floor, not a summation error) and the full fit at 1e-8"""
+    e = readme_examples["example2"]
+    x, y = np.array(e["x"]), np.array(e["y"])
+    m = G.Model("a * exp(-(x - b)^2 / (2 * c^2))", ["a", "b", "c"], ["x"], jac="center")
+    pb = G.Problem(m, x.size).upload([x], y)
+    for theta in ([1.0, 0.0, 1.0], [4.5, 0.45, 0.15]):
+        got = pb.eval_packet(theta)
+        ref = O.eval_packet("gauss", y, theta, x=x, fd_jac=2, longdouble=True)
+        assert rel_packet_err(got, ref, 3) < 1e-9, theta
+        ana = O.eval_packet("gauss", y, theta, x=x, longdouble=True)
+        assert rel_packet_err(got, ana, 3) < 1e-6   # and close to the analytic Jacobian's packet
+    for alg in ("lm", "dogleg"):
+        fit = pb.fit(e["start"], algorithm=alg, control=dict(G.gsl_nls_control(), fdtype="center"))
+        ref = O.nls_large("gauss", y, e["start"], x=x, algorithm=alg, fd_jac=2, fdtype="center")
+        _fit_cmp(fit, ref)
+    pb.close()
+    # tiled kernel (p > 8) with centred differences
+    rng = np.random.Generator(np.random.Philox(key=21))
+    n, K = 5000, 3
+    xx = np.linspace(0, 30, n)
+    th = np.array([5.0, 5.0, 2.0, 7.0, 15.0, 2.5, 4.0, 25.0, 2.0])
+    yy = sum(th[3 * k] * np.exp(-((xx - th[3 * k + 1]) ** 2) / th[3 * k + 2] ** 2) for k in range(K))
+    yy = yy + 0.1 * rng.standard_normal(n)
+    rhs = " + ".join("a%d * exp(-(x - m%d)^2 / s%d^2)" % (k, k, k) for k in range(1, K + 1))
+    names = [s % k for k in range(1, K + 1) for s in ("a%d", "m%d", "s%d")]
+    m9 = G.Model(rhs, names, ["x"], jac="center")
+    pb = G.Problem(m9, n).upload([xx], yy)
+    st = th * 1.02
+    got = pb.eval_packet(st)
+    ref = O.eval_packet("gaussmix", yy, st, x=xx, fd_jac=2, longdouble=True)
+    assert rel_packet_err(got, ref, 9) < 1e-8
+    pb.close()
+
+
+@pytest.mark.parametrize("alg", ["lm", "dogleg"])
+def test_condtrace_matches_oracle_on_gpu(G, nist_problems, alg):
+    """cond(J) column of the trace (callback_large, src/nls_large.c:733-738): GSL's cholesky_rcond estimator on
+    the device against the oracle's restatement, p = 3 (resident server) and p = 7 / 8 (cooperative solves)"""
+    for name in ("Misra1a", "Thurber", "Gauss3"):
+        pr = nist_problems[name]
+        data = {k: np.array(v) for k, v in pr["data"].items()}
+        rows = O.sympy_rows(O.split_formula(pr["formula"])[1], pr["param_names"], {"x": data["x"]})
+        ref = O.nls_large(rows, data["y"], pr["start"], algorithm=alg, maxiter=8, trace=True)
+        m = G.Model(O.split_formula(pr["formula"])[1], pr["param_names"], ["x"], jac=True)
+        pb = G.Problem(m, data["y"].size).upload([data["x"]], data["y"])
+        fit = pb.fit(pr["start"], algorithm=alg, control=dict(G.gsl_nls_control(), maxiter=8), trace=True)
+        k = min(fit["niter"], ref["niter"]) + 1
+        assert k >= 3, name
+        assert np.allclose(fit["condtrace"][1:k], ref["condtrace"][1:k], rtol=1e-5), (name, alg)
+        pb.close()
+
+
+def test_weights_mode_gsl_matches_reference_semantics(G, readme_examples):
+    """weights_mode="gsl": sqrt(w) on f only, J^T J unweighted -- what the reference computes for non-unit
+    weights (libgsl's winit never sees J; gsl_df_large, src/nls_large.c:474-653, does not weight it)"""
+    e = readme_examples["example1"]
+    x, y = np.array(e["x"]), np.array(e["y"])
+    w = 1.0 + (np.arange(x.size) % 3)
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    pb = G.Problem(m, x.size, has_weights=True).set_weights_mode("gsl").upload([x], y, w)
+    theta = [4.0, 1.2, 0.8]
+    got = pb.eval_packet(theta)
+    ref = O.eval_packet("exp3", y, theta, x=x, weights=w, longdouble=True, weights_gsl=True)
+    assert rel_packet_err(got, ref, 3) < 1e-12
+    other = O.eval_packet("exp3", y, theta, x=x, weights=w, longdouble=True)
+    assert rel_packet_err(got, other, 3) > 1e-3   # the two semantics really differ
+    for alg in ("lm", "lmaccel", "dogleg"):
+        fit = pb.fit([1.0, 1.0, 0.0], algorithm=alg, want_resid_grad=True)
+        ref = O.nls_large("exp3", y, [1.0, 1.0, 0.0], x=x, weights=w, algorithm=alg, weights_gsl=True,
+                          want_resid_grad=True)
+        _fit_cmp(fit, ref)
+        assert np.allclose(fit["covar"], ref["covar"], rtol=1e-7)
+        assert np.allclose(fit["resid"], ref["resid"], rtol=1e-6, atol=1e-9)   # weighted residuals
+        assert np.allclose(fit["grad"], ref["grad"], rtol=1e-6, atol=1e-9)     # unweighted Jacobian (:354-363)
+    pb.close()
+    hi = G.gsl_nls_large("y ~ A * exp(-lam * x) + b", data={"x": x, "y": y}, start={"A": 1, "lam": 1, "b": 0},
+                         jac=True, weights=w, weights_mode="gsl")
+    ref = O.nls_large("exp3", y, [1, 1, 0], x=x, weights=w, weights_gsl=True)
+    assert hi.convInfo["finIter"] == ref["niter"] and np.allclose(list(hi.coef().values()), ref["par"], rtol=1e-8)
+
+
+def test_inf_residual_finite_jacobian_on_gpu(G):
+    """model value overflows while the Jacobian stays finite: the reference's NaN scan covers J only
+    (src/nls_large.c:515-522), so the fit iterates on with residual +Inf (16 rejected trials -> ENOPROG in the
+    first iteration, par = start) instead of stopping with EBADFUNC"""
+    x = np.linspace(0.0, 1.0, 64)
+    y = 1.0 + 2.0 * x
+
+    def rows(theta, v, wf, wJ, wh):
+        A, b = theta
+        with np.errstate(all="ignore"):
+            f = A * x + b + 1e308 * (1.0 + np.sign(A - 5.0))
+        return f, np.stack([x, np.ones_like(x)], axis=1), np.zeros_like(x)
+    m = G.Model("A * x + b + 1e308 * (1 + sign(A - 5))", ["A", "b"], ["x"], jac=True, fvv=True)
+    pb = G.Problem(m, x.size).upload([x], y)
+    for alg in ALGS:
+        for st in ([10.0, 0.0], [4.9, 0.0]):
+            fit = pb.fit(st, algorithm=alg)
+            ref = O.nls_large(rows, y, st, algorithm=alg)
+            assert fit["conv"] == ref["conv"] == (27 if st[0] > 5 else 0), (alg, st, fit["status"])
+            assert fit["niter"] == ref["niter"], (alg, st)
+            assert np.allclose(fit["par"], ref["par"], rtol=1e-8), (alg, st)
+    pb.close()
+
+
+def test_serialised_execution_falls_back_to_launch_ordered(tmp_path):
+    """CUDA_LAUNCH_BLOCKING=1 (and ncu / compute-sanitizer) serialise kernels: the resident trust-region
+    server cannot run next to the pass kernel.  The library must notice -- by environment, or through the
+    server's start-of-fit handshake when told to try anyway (GSLNLS_SERVER=1) -- and step launch-ordered."""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, time
+import numpy as np
+sys.path.insert(0, %r)
+import gslnls_b200 as G
+rng = np.random.Generator(np.random.Philox(key=1))
+n = 200001
+x = 3.0 * np.arange(n) / (n - 1)
+y = 5.0 * np.exp(-1.5 * x) + 1.0 + 0.25 * rng.standard_normal(n)
+m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+pb = G.Problem(m, n).upload([x], y)
+out = {}
+for alg in ("lm", "lmaccel"):
+    t0 = time.time()
+    f = pb.fit([1.0, 1.0, 0.0], algorithm=alg)
+    out[alg] = {"par": list(f["par"]), "niter": f["niter"], "conv": f["conv"], "ssr": f["ssr"], "s": time.time() - t0}
+print(json.dumps(out))
+''' % ROOT_DIR
+    results = {}
+    for tag, env_extra in (("plain", {}), ("blocking", {"CUDA_LAUNCH_BLOCKING": "1"}),
+                           ("blocking_forced_server", {"CUDA_LAUNCH_BLOCKING": "1", "GSLNLS_SERVER": "1",
+                                                       "GSLNLS_WATCHDOG_S": "20"})):
+        env = dict(os.environ, **env_extra)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, (tag, r.stderr[-2000:])
+        results[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    for tag in ("blocking", "blocking_forced_server"):
+        for alg in ("lm", "lmaccel"):
+            a, b = results[tag][alg], results["plain"][alg]
+            assert a["conv"] == b["conv"] == 0 and a["niter"] == b["niter"], (tag, alg)
+            assert np.allclose(a["par"], b["par"], rtol=1e-12) and a["ssr"] == pytest.approx(b["ssr"], rel=1e-12)
+            assert a["s"] < 10.0, (tag, alg, a["s"])   # a handshake period, not a 60 s watchdog
+
+
+def test_upload_from_pageable_memory_is_exact_and_fast(G):
+    """gslnls_problem_upload stages pageable host arrays through the library's pinned ring (upload.cpp): the
+    device copy must be bit-exact at sizes that are not multiples of the slice, and repeatable"""
+    import time
+    n = 6_000_011
+    x, y = synth_exp(n)
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True)
+    pb = G.Problem(m, n)
+    t0 = time.perf_counter()
+    pb.upload([x], y)
+    r = pb.residuals([0.0, 0.0, 1.0])   # A = 0: residual = 1 - y, i.e. the uploaded y column itself
+    dt = time.perf_counter() - t0
+    assert np.array_equal(r, 1.0 - y)
+    r2 = pb.residuals([1.0, 0.0, 0.0])  # lam = 0: residual = 1 - y as well; x enters through J only
+    assert np.array_equal(r2, 1.0 - y)
+    _, J = pb.residuals([1.0, 1.0, 0.0], want_grad=True)
+    assert np.allclose(J[:, 0], np.exp(-x), rtol=1e-14)   # the uploaded x column, through the model
+    assert dt < 5.0
     pb.close()

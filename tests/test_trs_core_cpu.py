@@ -80,6 +80,30 @@ def test_failure_paths():
     assert int(r["status"]) == 27 and int(r["niter"]) == 1 and int(r["neval_f"]) == 17
 
 
+def test_infinite_residual_with_finite_jacobian_iterates_like_the_reference():
+    """The reference's NaN/Inf scan covers the Jacobian only (src/nls_large.c:515-522); a model value that
+    overflows next to a finite Jacobian row gives residual +Inf (:464-467), an infinite / NaN gradient, and the
+    solver iterates on (here: 16 rejected trials -> ENOPROG in the first iteration), it does not stop with
+    EBADFUNC.  The device state machine scans J^T J only and must walk the oracle's path."""
+    x = np.linspace(0, 1, 20)
+    y = 1 + 2 * x
+
+    def rows(theta, v, wf, wJ, wh):
+        A, b = theta
+        with np.errstate(all="ignore"):
+            f = A * x + b + np.where((x > 0.5) & (A > 5.0), np.inf, 0.0)
+        return f, np.stack([x, np.ones_like(x)], axis=1), np.zeros_like(x)
+    prov = T.packet_from_rows(rows, y)
+    for alg in ALGS:
+        for st in ([10.0, 0.0], [4.9, 0.0]):
+            o = O.nls_large(rows, y, st, algorithm=alg)
+            r = T.fit(prov, st, algorithm=alg)
+            assert int(r["status"]) == o["conv"] and int(r["niter"]) == o["niter"], (alg, st)
+            assert o["conv"] == (27 if st[0] > 5 else 0)
+            if o["conv"] == 0:
+                assert np.allclose(r["par"], o["par"], rtol=1e-8)
+
+
 def test_maxiter_and_trace_layout(readme_examples):
     e = readme_examples["example2"]
     x, y = np.array(e["x"]), np.array(e["y"])
@@ -89,7 +113,25 @@ def test_maxiter_and_trace_layout(readme_examples):
     assert int(r["status"]) == o["conv"] == 11 and int(r["niter"]) == 5
     assert np.allclose(r["partrace"], o["partrace"], rtol=1e-9)
     assert r["partrace"].shape == (6, 3) and np.allclose(r["partrace"][0], e["start"])
-    assert r["condtrace"][1] > 1.0
+    # cond(J) column of the trace (callback_large, src/nls_large.c:733-738): GSL's cholesky_rcond estimator,
+    # restated independently in the oracle (orc_rcond) and in the device state machine (cond_J)
+    assert np.allclose(r["condtrace"][1:], o["condtrace"][1:], rtol=1e-9)
+    JTJ = r["jtj"] + np.tril(r["jtj"], -1).T
+    exact = np.sqrt(np.linalg.cond(JTJ, 1))
+    assert 0.3 * exact <= r["condtrace"][-1] <= 1.0000001 * exact  # an estimate from below of the exact 1-norm value
+
+
+def test_condtrace_estimator_matches_oracle_larger_p(nist_problems):
+    for name, alg in (("Thurber", "lm"), ("Gauss3", "dogleg"), ("Hahn1", "lm")):
+        pr = nist_problems[name]
+        data = {k: np.array(v) for k, v in pr["data"].items()}
+        rows = O.sympy_rows(O.split_formula(pr["formula"])[1], pr["param_names"], {"x": data["x"]})
+        prov = T.packet_from_rows(rows, data["y"])
+        r = T.fit(prov, pr["start"], algorithm=alg, maxiter=6)
+        o = O.nls_large(rows, data["y"], pr["start"], algorithm=alg, maxiter=6, trace=True)
+        k = min(len(r["condtrace"]), len(o["condtrace"]))
+        assert k >= 3
+        assert np.allclose(r["condtrace"][1:k], o["condtrace"][1:k], rtol=1e-5), (name, r["condtrace"], o["condtrace"])
 
 
 def test_boxbod_reproduces_reference_nan_norm_quirk(nist_problems):

@@ -34,9 +34,11 @@ def lib():
     return _LIB
 
 
-def packet_from_rows(rows, y, weights=None):
-    """packet provider implementing the pass kernel's contract with numpy"""
+def packet_from_rows(rows, y, weights=None, weights_gsl=False):
+    """packet provider implementing the pass kernel's contract with numpy; weights_gsl=True leaves the rows of
+    J unweighted (GSLNLS_WEIGHTS_GSL: only f and fvv carry sqrt(w))"""
     sw = None if weights is None else np.sqrt(np.asarray(weights, dtype=float))
+    swJ = None if weights_gsl else sw
 
     def provider(mode, theta, v):
         p = theta.size
@@ -45,7 +47,8 @@ def packet_from_rows(rows, y, weights=None):
             r = np.where(np.isfinite(f), f - y, np.inf)
             if sw is not None:
                 r = r * sw
-                J = J * sw[:, None]
+            if swJ is not None:
+                J = J * swJ[:, None]
             with np.errstate(all="ignore"):
                 JTJ = J.T @ J
                 pk = np.concatenate([JTJ[np.tril_indices(p)], J.T @ r, [r @ r], [np.sum(~np.isfinite(r))]])
@@ -53,8 +56,9 @@ def packet_from_rows(rows, y, weights=None):
         if mode == 2:
             _, J, h = rows(theta, v, False, True, True)
             if sw is not None:
-                J = J * sw[:, None]
                 h = h * sw
+            if swJ is not None:
+                J = J * swJ[:, None]
             with np.errstate(all="ignore"):
                 return np.concatenate([J.T @ h, [h @ h]])
         raise ValueError(mode)
