@@ -42,6 +42,13 @@ SIGNATURES = {
                                          c_double_p, c_int_p, c_double_p, C.c_int, c_int_p, C.c_int,
                                          C.POINTER(Result)]),
     "gslnls_result_free": (None, [C.POINTER(Result)]),
+    "gslnls_session_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_int_p, C.POINTER(C.c_void_p)]),
+    "gslnls_session_free": (None, [C.c_void_p]),
+    "gslnls_session_ngpu": (C.c_int, [C.c_void_p]),
+    "gslnls_session_set_weights_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "gslnls_session_upload": (C.c_int, [C.c_void_p, C.POINTER(c_double_p), c_double_p, c_double_p]),
+    "gslnls_session_fit": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, C.c_int, C.POINTER(Result)]),
+    "gslnls_session_residuals": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
     "gslnls_cache_clear": (None, []),
     "gslnls_problem_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gslnls_problem_free": (None, [C.c_void_p]),

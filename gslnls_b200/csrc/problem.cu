@@ -398,10 +398,13 @@ static void cache_put(gslnls_problem *pb)
         gslnls_problem_free(e);
 }
 
+static void multi_cache_drop(const gslnls_model *m);
+
 namespace gslnls {
 // a model is going away (gslnls_model_free) or the user asked for the memory back (m == nullptr: all)
 void cache_drop(const gslnls_model *m)
 {
+    multi_cache_drop(m);
     std::vector<gslnls_problem *> evict;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -753,7 +756,16 @@ GSLNLS_API int gslnls_problem_time_passes(gslnls_problem *pb, const double *thet
     return GSLNLS_SUCCESS;
 }
 
+static int problem_residuals_ld(gslnls_problem *pb, const double *theta, double *resid, double *grad, int64_t ld);
+
 GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta, double *resid, double *grad)
+{
+    return problem_residuals_ld(pb, theta, resid, grad, pb ? pb->n : 0);
+}
+
+// K4 with the host Jacobian's leading dimension given: a shard of a multi-GPU session writes its rows into
+// the caller's n x p column-major array directly (column j of this shard starts at grad + j * ld)
+static int problem_residuals_ld(gslnls_problem *pb, const double *theta, double *resid, double *grad, int64_t ld)
 {
     if (!pb || !theta)
         return GSLNLS_EINVAL;
@@ -789,8 +801,15 @@ GSLNLS_API int gslnls_problem_residuals(gslnls_problem *pb, const double *theta,
     ++pb->launches;
     if (resid)
         CK(cudaMemcpyAsync(resid, d_resid, sizeof(double) * pb->n, cudaMemcpyDeviceToHost, pb->stream));
-    if (grad)
-        CK(cudaMemcpyAsync(grad, d_grad, sizeof(double) * pb->n * p, cudaMemcpyDeviceToHost, pb->stream));
+    if (grad) {
+        if (ld == pb->n) {
+            CK(cudaMemcpyAsync(grad, d_grad, sizeof(double) * pb->n * p, cudaMemcpyDeviceToHost, pb->stream));
+        } else {
+            for (int j = 0; j < p; ++j)
+                CK(cudaMemcpyAsync(grad + (size_t)j * ld, d_grad + (size_t)j * pb->n, sizeof(double) * pb->n,
+                                   cudaMemcpyDeviceToHost, pb->stream));
+        }
+    }
     CK(cudaStreamSynchronize(pb->stream));
     return GSLNLS_SUCCESS;
 }
@@ -1308,16 +1327,217 @@ GSLNLS_API int gslnls_fit_large(const gslnls_model *m, const double *const *vars
                                     want_resid_grad, out);
 }
 
-// ---- one call, several GPUs, one process -------------------------------------------------------
-namespace {
-struct LocalGroup {
-    std::vector<int> devices;
-    std::vector<gslnls_comm *> comms;
+} // extern "C"
+
+// ---- sessions: one handle for "the data of a fit, resident on 1..R GPUs of this process" ------------
+// What the R shim keeps behind an external pointer: the rows are split into contiguous, 2-aligned shards,
+// one gslnls_problem per GPU, each driven by its own host thread (upload over that GPU's PCIe link, sharded
+// fit with packets crossing NVLink peer memory).  resid / grad of src/nls_large.c:339-385 are produced on
+// demand from the resident shards (lazy post-fit accessors), not by the fit.
+struct gslnls_session {
+    const gslnls_model *model = nullptr;
+    int64_t n = 0, per = 0;
+    int has_w = 0;
+    std::vector<int> dev;
+    std::vector<gslnls_problem *> pb;
+    std::vector<gslnls_comm *> comm; // empty for one GPU
+    int R() const { return (int)pb.size(); }
+    int64_t lo(int r) const { return std::min<int64_t>(n, (int64_t)r * per); }
+    int64_t hi(int r) const { return std::min<int64_t>(n, lo(r) + per); }
 };
-std::mutex g_group_mu;
-LocalGroup g_group; // the last device group, kept for the next call (NCCL and peer-access setup are slow)
+
+namespace {
+template <class F>
+int on_every_rank(gslnls_session *s, F f)
+{
+    const int R = s->R();
+    if (R == 1)
+        return f(0);
+    std::vector<int> rcs(R, GSLNLS_SUCCESS);
+    std::vector<std::string> errs(R);
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r)
+        th.emplace_back([&, r] {
+            rcs[r] = f(r);
+            errs[r] = g_last_error;
+        });
+    for (std::thread &t : th)
+        t.join();
+    for (int r = 0; r < R; ++r)
+        if (rcs[r] >= 1000 || rcs[r] == GSLNLS_EINVAL) {
+            set_error(errs[r]);
+            return rcs[r];
+        }
+    return rcs[0];
+}
+
+// the session of the last gslnls_fit_large_multi call, kept for the next one (peer-access setup, the n-sized
+// device buffers, streams and loaded kernels are all slow to create)
+std::mutex g_multi_mu;
+gslnls_session *g_multi = nullptr;
 } // namespace
 
+extern "C" GSLNLS_API void gslnls_session_free(gslnls_session *s);
+static void multi_cache_drop(const gslnls_model *m)
+{
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    if (g_multi && (!m || g_multi->model == m)) {
+        gslnls_session_free(g_multi);
+        g_multi = nullptr;
+    }
+}
+
+extern "C" {
+
+GSLNLS_API void gslnls_session_free(gslnls_session *s)
+{
+    if (!s)
+        return;
+    for (gslnls_problem *pb : s->pb)
+        gslnls_problem_free(pb);
+    for (gslnls_comm *c : s->comm)
+        gslnls_comm_free(c);
+    delete s;
+}
+
+GSLNLS_API int gslnls_session_create(const gslnls_model *m, int64_t n, int has_weights, int ngpu, const int *devices,
+                                     gslnls_session **out)
+{
+    if (!m || !out || n < 0 || ngpu < 1 || ngpu > NLS_MAX_RANKS)
+        return GSLNLS_EINVAL;
+    *out = nullptr;
+    // contiguous, 2-aligned row ranges (keeps every shard's columns 16-byte aligned); no empty shards
+    int R = (int)std::min<int64_t>(ngpu, std::max<int64_t>(1, n / 2));
+    auto rows_per = [&](int r) {
+        int64_t q = (n + r - 1) / r;
+        return q + (q & 1);
+    };
+    while (R > 1 && (int64_t)(R - 1) * rows_per(R) >= n) // rounding the shard length up to even can empty the last shard
+        --R;
+    gslnls_session *s = new gslnls_session();
+    s->model = m;
+    s->n = n;
+    s->has_w = has_weights ? 1 : 0;
+    s->per = R > 1 ? rows_per(R) : n;
+    for (int r = 0; r < R; ++r)
+        s->dev.push_back(devices ? devices[r] : r);
+    if (R > 1) {
+        s->comm.assign(R, nullptr);
+        int rc = gslnls_comm_create_local(R, s->dev.data(), s->comm.data());
+        if (rc) {
+            s->comm.clear();
+            gslnls_session_free(s);
+            return rc;
+        }
+    }
+    for (int r = 0; r < R; ++r) {
+        gslnls_problem *pb = nullptr;
+        int rc = gslnls_problem_create(m, s->hi(r) - s->lo(r), s->has_w, s->dev[r], &pb);
+        if (rc) {
+            gslnls_session_free(s);
+            return rc;
+        }
+        pb->upload_sharing = R;
+        s->pb.push_back(pb);
+    }
+    *out = s;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_session_ngpu(const gslnls_session *s) { return s ? s->R() : 0; }
+
+GSLNLS_API int gslnls_session_set_weights_mode(gslnls_session *s, int mode)
+{
+    if (!s)
+        return GSLNLS_EINVAL;
+    for (gslnls_problem *pb : s->pb) {
+        int rc = gslnls_problem_set_weights_mode(pb, mode);
+        if (rc)
+            return rc;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_session_upload(gslnls_session *s, const double *const *vars, const double *y, const double *weights)
+{
+    if (!s || !y || (s->model->nvar > 0 && !vars) || (s->has_w && !weights))
+        return GSLNLS_EINVAL;
+    const int nvar = s->model->nvar;
+    return on_every_rank(s, [&](int r) {
+        const int64_t lo = s->lo(r);
+        std::vector<const double *> v(std::max(nvar, 1), nullptr);
+        for (int k = 0; k < nvar; ++k)
+            v[k] = vars[k] + lo;
+        int rc = gslnls_problem_upload(s->pb[r], v.data(), y + lo, weights ? weights + lo : nullptr);
+        if (rc == GSLNLS_SUCCESS && s->R() > 1) {
+            s->comm[r]->n_total_hint = s->n;
+            rc = gslnls_problem_set_comm(s->pb[r], s->comm[r]);
+        }
+        return rc;
+    });
+}
+
+GSLNLS_API int gslnls_session_residuals(gslnls_session *s, const double *theta, double *resid, double *grad)
+{
+    if (!s || !theta)
+        return GSLNLS_EINVAL;
+    // every rank writes its rows straight into the caller's n-row arrays (grad is n x p column-major)
+    return on_every_rank(s, [&](int r) {
+        const int64_t lo = s->lo(r);
+        return problem_residuals_ld(s->pb[r], theta, resid ? resid + lo : nullptr, grad ? grad + lo : nullptr, s->n);
+    });
+}
+
+GSLNLS_API int gslnls_session_fit(gslnls_session *s, const double *start, const int *control_int,
+                                  const double *control_dbl, int want_resid_grad, gslnls_result *out)
+{
+    if (!s || !start || !control_int || !control_dbl || !out)
+        return GSLNLS_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    if (s->n < s->model->p) {
+        // R/nls_large.R:286-288
+        set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
+        return GSLNLS_EINVAL;
+    }
+    const int R = s->R();
+    std::vector<gslnls_result> res(R);
+    for (gslnls_result &q : res)
+        std::memset(&q, 0, sizeof(q));
+    int rc = on_every_rank(s, [&](int r) {
+        return gslnls_problem_fit(s->pb[r], start, control_int, control_dbl, 0, &res[r]);
+    });
+    if (rc >= 1000 || rc == GSLNLS_EINVAL) {
+        for (gslnls_result &q : res)
+            gslnls_result_free(&q);
+        return rc;
+    }
+    *out = res[0]; // every rank holds bitwise the same result
+    out->n = s->n;
+    out->n_local = s->n;
+    for (int r = 1; r < R; ++r)
+        gslnls_result_free(&res[r]);
+    if (want_resid_grad) {
+        // src/nls_large.c:339-385; NaN-filled on failure (:345-349, :371-376)
+        const int p = s->model->p;
+        out->resid = (double *)std::malloc(sizeof(double) * (size_t)std::max<int64_t>(s->n, 1));
+        out->grad = (double *)std::malloc(sizeof(double) * (size_t)std::max<int64_t>(s->n, 1) * p);
+        if (rc == GSLNLS_SUCCESS || rc == GSLNLS_EMAXITER) {
+            int r2 = gslnls_session_residuals(s, out->par, out->resid, out->grad);
+            if (r2) {
+                gslnls_result_free(out);
+                return r2;
+            }
+        } else {
+            for (int64_t i = 0; i < s->n; ++i)
+                out->resid[i] = NAN;
+            for (int64_t i = 0; i < s->n * p; ++i)
+                out->grad[i] = NAN;
+        }
+    }
+    return rc;
+}
+
+// ---- one call, several GPUs, one process: the `int ngpu, const int *devices` form of src/nls_large.c:66 ----
 GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const *vars, const double *y,
                                       const double *weights, int64_t n, const double *start,
                                       const int *control_int, const double *control_dbl, int ngpu,
@@ -1330,87 +1550,56 @@ GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const
         set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
         return GSLNLS_EINVAL;
     }
+    if (ngpu == 1)
+        return gslnls_fit_large_sharded(m, vars, y, weights, n, start, control_int, control_dbl,
+                                        devices ? devices[0] : 0, nullptr, want_resid_grad, out);
+    std::lock_guard<std::mutex> lk(g_multi_mu); // one multi-GPU one-shot fit at a time per process
     std::vector<int> dev(ngpu);
     for (int r = 0; r < ngpu; ++r)
         dev[r] = devices ? devices[r] : r;
-    // contiguous, 2-aligned row ranges (keeps every shard's columns 16-byte aligned); no empty shards
-    int R = (int)std::min<int64_t>(ngpu, std::max<int64_t>(1, n / 2));
-    auto rows_per = [&](int r) {
-        int64_t q = (n + r - 1) / r;
-        return q + (q & 1);
-    };
-    while (R > 1 && (int64_t)(R - 1) * rows_per(R) >= n) // rounding the shard length up to even can empty the last shard
-        --R;
-    if (R == 1)
-        return gslnls_fit_large_sharded(m, vars, y, weights, n, start, control_int, control_dbl, dev[0], nullptr,
-                                        want_resid_grad, out);
-    dev.resize(R);
-    const int64_t per = rows_per(R);
-    std::lock_guard<std::mutex> lk(g_group_mu); // one multi-GPU fit at a time per process
-    if (g_group.devices != dev) {
-        for (gslnls_comm *c : g_group.comms)
-            gslnls_comm_free(c);
-        g_group.comms.assign(R, nullptr);
-        g_group.devices.clear();
-        int rc = gslnls_comm_create_local(R, dev.data(), g_group.comms.data());
-        if (rc) {
-            g_group.comms.clear();
+    gslnls_session *s = g_multi;
+    bool reuse = s && s->model == m && s->has_w == (weights ? 1 : 0) && (int)s->dev.size() <= ngpu &&
+                 std::equal(s->dev.begin(), s->dev.end(), dev.begin());
+    if (reuse && s->n != n) {
+        // same devices, another row count: keep the peer-access group and the streams, re-split the rows (the
+        // column buffers grow on demand in upload())
+        int R = (int)std::min<int64_t>(ngpu, std::max<int64_t>(1, n / 2));
+        auto rows_per = [&](int r) {
+            int64_t q = (n + r - 1) / r;
+            return q + (q & 1);
+        };
+        while (R > 1 && (int64_t)(R - 1) * rows_per(R) >= n)
+            --R;
+        if (R != s->R()) {
+            reuse = false;
+        } else {
+            s->n = n;
+            s->per = R > 1 ? rows_per(R) : n;
+            for (int r = 0; r < R; ++r) {
+                s->pb[r]->n = s->hi(r) - s->lo(r);
+                s->pb[r]->n_total = n;
+            }
+        }
+    }
+    if (!reuse) {
+        gslnls_session_free(g_multi);
+        g_multi = nullptr;
+        int rc = gslnls_session_create(m, n, weights != nullptr, ngpu, dev.data(), &s);
+        if (rc)
             return rc;
-        }
-        g_group.devices = dev;
+        if (cache_enabled())
+            g_multi = s;
     }
-    std::vector<gslnls_result> res(R);
-    std::vector<int> rcs(R, GSLNLS_SUCCESS);
-    std::vector<std::string> errs(R);
-    std::vector<std::thread> th;
-    const int nvar = m->nvar;
-    for (int r = 0; r < R; ++r) {
-        g_group.comms[r]->n_total_hint = n;
-        th.emplace_back([&, r] {
-            const int64_t lo = std::min<int64_t>(n, (int64_t)r * per), hi = std::min<int64_t>(n, lo + per);
-            std::vector<const double *> v(std::max(nvar, 1), nullptr);
-            for (int k = 0; k < nvar; ++k)
-                v[k] = vars[k] + lo;
-            rcs[r] = gslnls_fit_large_sharded(m, v.data(), y + lo, weights ? weights + lo : nullptr, hi - lo, start,
-                                              control_int, control_dbl, dev[r], g_group.comms[r], want_resid_grad,
-                                              &res[r]);
-            errs[r] = g_last_error;
-        });
+    gslnls_session_set_weights_mode(s, default_weights_mode());
+    int rc = gslnls_session_upload(s, vars, y, weights);
+    if (rc == GSLNLS_SUCCESS)
+        rc = gslnls_session_fit(s, start, control_int, control_dbl, want_resid_grad, out);
+    if (s != g_multi)
+        gslnls_session_free(s);
+    else if (rc >= 1000) { // do not keep a session that failed at the library level
+        gslnls_session_free(g_multi);
+        g_multi = nullptr;
     }
-    for (std::thread &t : th)
-        t.join();
-    int rc = rcs[0];
-    for (int r = 0; r < R; ++r)
-        if (rcs[r] >= 1000 || rcs[r] == GSLNLS_EINVAL) {
-            rc = rcs[r];
-            set_error(errs[r]);
-            break;
-        }
-    if (rc >= 1000 || rc == GSLNLS_EINVAL) {
-        for (int r = 0; r < R; ++r)
-            gslnls_result_free(&res[r]);
-        return rc;
-    }
-    *out = res[0];
-    out->n_local = n;
-    if (want_resid_grad) {
-        // stitch the per-rank pieces: resid is n, grad is n x p column-major (src/nls_large.c:339-385)
-        const int p = m->p;
-        double *resid = (double *)std::malloc(sizeof(double) * (size_t)n);
-        double *grad = (double *)std::malloc(sizeof(double) * (size_t)n * p);
-        for (int r = 0; r < R; ++r) {
-            const int64_t lo = std::min<int64_t>(n, (int64_t)r * per), nl = res[r].n_local;
-            std::memcpy(resid + lo, res[r].resid, sizeof(double) * (size_t)nl);
-            for (int j = 0; j < p; ++j)
-                std::memcpy(grad + (size_t)j * n + lo, res[r].grad + (size_t)j * nl, sizeof(double) * (size_t)nl);
-        }
-        std::free(res[0].resid);
-        std::free(res[0].grad);
-        out->resid = resid;
-        out->grad = grad;
-    }
-    for (int r = 1; r < R; ++r)
-        gslnls_result_free(&res[r]);
     return rc;
 }
 
@@ -1418,11 +1607,6 @@ GSLNLS_API void gslnls_cache_clear(void)
 {
     cache_drop(nullptr);
     upload_pools_release();
-    std::lock_guard<std::mutex> lk(g_group_mu);
-    for (gslnls_comm *c : g_group.comms)
-        gslnls_comm_free(c);
-    g_group.comms.clear();
-    g_group.devices.clear();
 }
 
 GSLNLS_API void gslnls_result_free(gslnls_result *r)

@@ -234,6 +234,66 @@ class Problem:
             pass
 
 
+class Session:
+    """gslnls_session: the data of a fit resident on one or several GPUs of this process.  What the fitted
+    object keeps so that residuals / gradient (src/nls_large.c:339-385) are produced only when asked for."""
+
+    def __init__(self, model, n, has_weights=False, devices=(0,)):
+        self.model, self.n, self.has_weights = model, int(n), bool(has_weights)
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().gslnls_session_create(model.handle, self.n, int(self.has_weights), dev.size,
+                                                    dev.ctypes.data_as(_lib.c_int_p), C.byref(h)))
+        self.handle = h
+        self.device = int(dev[0])
+
+    @property
+    def ngpu(self):
+        return _lib.lib().gslnls_session_ngpu(self.handle)
+
+    def set_weights_mode(self, mode):
+        _lib.check(_lib.lib().gslnls_session_set_weights_mode(self.handle, WEIGHTS_MODES[mode]))
+        return self
+
+    def upload(self, vars_, y, weights=None):
+        cols = [np.ascontiguousarray(v, dtype=np.float64) for v in vars_]
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        arr = (_lib.c_double_p * max(1, len(cols)))(*[_dptr(c) for c in cols])
+        _lib.check(_lib.lib().gslnls_session_upload(self.handle, arr, _dptr(y), _dptr(w)))
+        return self
+
+    def fit(self, start, algorithm="lm", control=None, trace=False, want_resid_grad=False):
+        ctrl = gsl_nls_control() if control is None else control
+        ci, cd = pack_control(ctrl, algorithm, trace)
+        st = np.ascontiguousarray(start, dtype=np.float64)
+        res = _lib.Result()
+        rc = _lib.lib().gslnls_session_fit(self.handle, _dptr(st), ci.ctypes.data_as(_lib.c_int_p), _dptr(cd),
+                                           int(want_resid_grad), C.byref(res))
+        _lib.check(rc)
+        out = _result_to_dict(res, st.size, self.n, int(ci[0]), trace, want_resid_grad)
+        _lib.lib().gslnls_result_free(C.byref(res))
+        return out
+
+    def residuals(self, theta, want_grad=False):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        r = np.empty(self.n)
+        g = np.empty(self.n * th.size) if want_grad else None
+        _lib.check(_lib.lib().gslnls_session_residuals(self.handle, _dptr(th), _dptr(r), _dptr(g)))
+        return (r, g.reshape(th.size, self.n).T.copy()) if want_grad else r
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().gslnls_session_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 # formula handling (R/nls_large.R:141-283)
 # ------------------------------------------------------------------------------------------------
@@ -313,10 +373,15 @@ class GslNls:
         return np.linalg.cholesky(self.cfit["jtj"]).T
 
     def residuals(self):
-        """response residuals y - fitted, weighted like m$resid() = -cFit$resid (R/nls.R:1255)"""
+        """response residuals y - fitted, weighted like m$resid() = -cFit$resid (R/nls.R:1255); computed from
+        the device-resident data on first use, never by the fit itself"""
         if self._resid is None:
             self._resid = -self._problem.residuals(self.cfit["par"])
         return self._resid
+
+    def gradient(self):
+        """m$gradient(): the n x p (weighted) Jacobian at the estimates, on demand"""
+        return self._problem.residuals(self.cfit["par"], want_grad=True)[1]
 
     def fitted(self):
         r = self.residuals()
@@ -349,7 +414,7 @@ class GslNls:
         """evaluate the fitted curve on new predictor values (on the device, like everything O(n))"""
         cols = [np.ascontiguousarray(newdata[v], dtype=np.float64) for v in self._model.var_names]
         n = cols[0].size if cols else 1
-        pb = Problem(self._model, n, False, self._problem.device if self._problem is not None else self._device)
+        pb = Problem(self._model, n, False, self._problem.device)
         pb.upload(cols, np.zeros(n))
         out = pb.residuals(self.cfit["par"])
         pb.close()
@@ -476,13 +541,12 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
 
     mdl = model if model is not None else Model(rhs, pnames, var_names, jac=jac, fvv=fvv)
     if devices is not None and len(devices) > 1:
-        # several GPUs from this one process: the library splits the rows and runs one thread per GPU
-        cfit = fit_large_multi(mdl, cols, lhs, weights, st, algorithm, ctrl, bool(trace), devices,
-                               want_resid_grad=True, weights_mode=weights_mode)
-        obj = GslNls(fn, pnames, cfit, None, mdl, ctrl, algorithm, weights, lhs, bool(trace))
-        obj._resid = -cfit["resid"]
-        obj._device = int(devices[0])
-        return obj
+        # several GPUs from this one process: the library splits the rows and runs one thread per GPU; the
+        # session stays behind the fitted object, residuals / gradient are lazy (no O(n) arrays from the fit)
+        ses = Session(mdl, lhs.size, weights is not None, devices).set_weights_mode(weights_mode)
+        ses.upload(cols, lhs, weights)
+        cfit = ses.fit(st, algorithm=algorithm, control=ctrl, trace=bool(trace))
+        return GslNls(fn, pnames, cfit, ses, mdl, ctrl, algorithm, weights, lhs, bool(trace))
     pb = Problem(mdl, lhs.size, weights is not None, device)
     pb.set_weights_mode(weights_mode)
     pb.upload(cols, lhs, weights)

@@ -84,6 +84,7 @@ enum {
 typedef struct gslnls_model gslnls_model;     /* compiled model: generated CUDA + cubin, opaque */
 typedef struct gslnls_problem gslnls_problem; /* device-resident data + solver workspace, opaque */
 typedef struct gslnls_comm gslnls_comm;       /* multi-GPU exchange context, opaque */
+typedef struct gslnls_session gslnls_session; /* the data of a fit resident on 1..8 GPUs of this process, opaque */
 
 /* The list returned by C_nls_large (src/nls_large.c:279-288), as a C struct.
  * All pointers are owned by the struct; release with gslnls_result_free. */
@@ -160,6 +161,27 @@ GSLNLS_API int gslnls_fit_large_multi(const gslnls_model *m, const double *const
                                       const int *control_int, const double *control_dbl, int ngpu,
                                       const int *devices, int want_resid_grad, gslnls_result *out);
 GSLNLS_API void gslnls_result_free(gslnls_result *r);
+
+/* ---- sessions: what the host language keeps behind its fitted-model object ------------------------
+ * A session is the data of one fit resident on ngpu GPUs of this process (rows split into contiguous shards,
+ * one host thread and one PCIe link per GPU, packets over NVLink peer memory).  gslnls_fit_large_multi is
+ * create + upload + fit + free; a host object that keeps the session can fit again from other start values
+ * or methods without a new upload, and obtains the O(n) outputs of C_nls_large -- `resid` and `grad`,
+ * src/nls_large.c:339-385 -- lazily, only when residuals() / the gradient are actually asked for
+ * (R/nls.R:1231-1484 builds them eagerly: 3.2 GB of host arrays at n = 1e8, p = 3). */
+GSLNLS_API int gslnls_session_create(const gslnls_model *m, int64_t n, int has_weights, int ngpu, const int *devices,
+                                     gslnls_session **out);
+GSLNLS_API void gslnls_session_free(gslnls_session *s);
+GSLNLS_API int gslnls_session_ngpu(const gslnls_session *s); /* GPUs actually used (tiny n uses fewer) */
+GSLNLS_API int gslnls_session_set_weights_mode(gslnls_session *s, int mode);
+GSLNLS_API int gslnls_session_upload(gslnls_session *s, const double *const *vars, const double *y,
+                                     const double *weights);
+GSLNLS_API int gslnls_session_fit(gslnls_session *s, const double *start, const int *control_int,
+                                  const double *control_dbl, int want_resid_grad, gslnls_result *out);
+/* weighted residuals f - y (n) and Jacobian (n x p column-major) at theta from the resident shards; either
+ * output may be NULL */
+GSLNLS_API int gslnls_session_residuals(gslnls_session *s, const double *theta, double *resid, double *grad_colmajor);
+
 /* gslnls_fit_large[_sharded] keeps the device buffers, workspace and streams of the last call per device
  * for the next one (same model); this returns them (also done for a model by gslnls_model_free).
  * GSLNLS_CACHE=0 in the environment disables the cache. */

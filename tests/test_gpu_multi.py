@@ -82,3 +82,38 @@ def test_single_process_multi_gpu_call(ngpu, alg):
     # twice in a row: the device group and the per-device buffers are reused
     again = gsl_nls_large("y ~ A * exp(-lam * x) + b", devices=list(range(ngpu)), **kw)
     assert list(again.coef().values()) == list(multi.coef().values())
+
+
+@pytest.mark.parametrize("ngpu", [1, 2, 4, 8])
+def test_session_lazy_residuals_and_gradient(ngpu):
+    """gslnls_session_*: the handle a host object keeps.  The fit returns no O(n) arrays; residuals and the
+    n x p gradient (src/nls_large.c:339-385) come from the resident shards when asked, stitched to n rows."""
+    if _ngpu() < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    import bench
+    import gslnls_b200 as G
+    from oracle import oracle as O
+    n = 300_007
+    x, y = bench.synth_rows(0, n, n)
+    w = 0.5 + (np.arange(n) % 5) / 4.0
+    m = G.Model(bench.FORMULA_RHS, ["A", "lam", "b"], ["x"], jac=True, fvv=True)
+    for weights in (None, w):
+        ses = G.Session(m, n, weights is not None, list(range(ngpu))).upload([x], y, weights)
+        assert ses.ngpu == ngpu
+        for alg in ("lm", "lmaccel"):
+            fit = ses.fit(list(bench.START), algorithm=alg)
+            ref = O.nls_large("exp3", y, list(bench.START), x=x, algorithm=alg, weights=weights, want_resid_grad=True)
+            assert fit["conv"] == ref["conv"] == 0 and fit["niter"] == ref["niter"], alg
+            assert np.allclose(fit["par"], ref["par"], rtol=1e-8) and fit["n"] == n
+            assert "resid" not in fit
+        r, J = ses.residuals(fit["par"], want_grad=True)
+        assert np.allclose(r, ref["resid"], rtol=1e-6, atol=1e-8)
+        assert np.allclose(J, ref["grad"], rtol=1e-6, atol=1e-8)
+        assert abs(r @ r - fit["ssr"]) <= 1e-9 * fit["ssr"]
+        ses.close()
+    # the high-level call keeps the session behind the fitted object
+    obj = G.gsl_nls_large("y ~ A * exp(-lam * x) + b", data={"x": x, "y": y}, start={"A": 1, "lam": 1, "b": 0},
+                          jac=True, devices=list(range(max(ngpu, 2))) if ngpu > 1 else None)
+    assert obj._resid is None                       # nothing O(n) was materialised by the fit
+    assert abs(np.sum(obj.residuals() ** 2) - obj.deviance()) <= 1e-9 * obj.deviance()
+    assert obj.gradient().shape == (n, 3)
