@@ -25,6 +25,13 @@ class Result(C.Structure):
     ]
 
 
+class MstartResult(C.Structure):
+    """struct gslnls_mstart_result"""
+    _fields_ = [("p", C.c_int), ("par", c_double_p), ("range", c_double_p), ("ssr", C.c_double),
+                ("ssrconv", C.c_double), ("nsp", C.c_int), ("nwsp", C.c_int), ("mstarts", C.c_int),
+                ("status", C.c_int), ("searches", C.c_int64)]
+
+
 # every symbol include/gslnls_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gslnls_model_compile": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
@@ -73,6 +80,10 @@ SIGNATURES = {
     "gslnls_problem_channel_stats": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.POINTER(C.c_int64)]),
     "gslnls_problem_fit_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p,
                                            c_double_p, c_double_p, c_int_p, c_int_p]),
+    "gslnls_problem_multistart": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_int_p, c_double_p, c_int_p, c_double_p,
+                                            C.POINTER(MstartResult)]),
+    "gslnls_mstart_result_free": (None, [C.POINTER(MstartResult)]),
+    "gslnls_qrng_points": (C.c_int, [C.c_int, C.c_int, c_double_p]),
     "gslnls_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "gslnls_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gslnls_comm_create_local": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_void_p)]),

@@ -46,6 +46,8 @@ struct NlsPassParams {
     int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
     unsigned long long watchdog_ns;   // server mode: longest in-kernel wait for a request (GSLNLS_WATCHDOG_S)
+    long long keep_rows;              // rows [0, keep_rows) of every column are loaded with an L2 evict_last policy,
+                                      // the rest evict_first: the head of the shard stays L2-resident from pass to pass
     // two-level grid reduction (single-candidate launches): CTAs in groups of NLS_RED_GROUP, the last
     // arriver of a group sums the group's partials, the last group sums the group sums
     double *group_partials;           // [ceil(gridDim.x / NLS_RED_GROUP)][pk_stride] or nullptr (flat reduction)

@@ -66,17 +66,34 @@
 enum { NLS_MODE_IDLE = 0, NLS_MODE_FJ = 1, NLS_MODE_FVV = 2, NLS_MODE_JVP = 3 };
 
 // ------------------------------------------------------------------------------------ loads
-static __device__ __forceinline__ double2 nls_ld2(const double *p)
+// Every streaming load carries an L2 eviction policy.  A pass reads each byte once, but the NEXT pass reads
+// the same bytes again, and 126 MB of L2 sit in front of HBM: rows below prm.keep_rows are loaded evict_last
+// (they stay resident from pass to pass and are served at L2 rate), the rest evict_first (they cycle through
+// what is left and never push the kept lines, or the trust-region server's state, out).
+struct NlsPolicy {
+    unsigned long long keep, stream;
+    long long keep_rows;
+};
+static __device__ __forceinline__ NlsPolicy nls_policy(long long keep_rows)
+{
+    NlsPolicy P;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(P.keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(P.stream));
+    P.keep_rows = keep_rows;
+    return P;
+}
+static __device__ __forceinline__ double2 nls_ld2(const double *p, unsigned long long pol)
 {
     double2 r;
 #if NLS_STREAM
-    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
 #else
+    (void)pol;
     asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
 #endif
     return r;
 }
-#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o))
+#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o), ((o) < PL.keep_rows) ? PL.keep : PL.stream)
 static __device__ __forceinline__ double nls_ld1(const double *p)
 {
     double r;
@@ -257,6 +274,8 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     const long long n = prm.n;
     const long long stride = (long long)gridDim.x * NLS_BLOCK;
     long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
+    const NlsPolicy PL = nls_policy(prm.keep_rows);
+    (void)PL;
 #if NLS_VEC == 2
     const long long nv = n >> 1;
     i += lo >> 1;
@@ -544,8 +563,7 @@ static __device__ __forceinline__ void nls_stream_tma(const NlsPassParams &prm, 
     int nbad = 0;
     if (warp == NLS_NCW) {
         if (lane == 0) {
-            unsigned long long policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            const NlsPolicy PL = nls_policy(prm.keep_rows);
             int s = 0;
             unsigned ph = 1u; // a fresh barrier lets a wait on the "previous" phase through
             for (long long t = blockIdx.x; t < ntile; t += gridDim.x) {
@@ -553,6 +571,7 @@ static __device__ __forceinline__ void nls_stream_tma(const NlsPassParams &prm, 
                 nls_bar_expect_tx(full + s, (unsigned)(NLS_STAGE_DOUBLES * sizeof(double)));
                 double *dst = buf + (size_t)s * NLS_STAGE_DOUBLES;
                 const long long o = t * NLS_TILE;
+                const unsigned long long policy = (o < PL.keep_rows) ? PL.keep : PL.stream;
 #pragma unroll
                 for (int k = 0; k < GSLNLS_NVAR; ++k)
                     nls_bulk_g2s(dst + k * NLS_TILE, prm.vars[k] + o, NLS_TILE * 8u, full + s, policy);

@@ -23,6 +23,7 @@
 #include "../../include/gslnls_b200.h"
 #include "comm.hpp"
 #include "model.hpp"
+#include "mstart.hpp"
 #include "nls_abi.h"
 #include "trs_launch.hpp"
 #include "upload.hpp"
@@ -62,6 +63,7 @@ struct gslnls_problem {
     const double *dvars[NLS_MAX_VARS] = {nullptr};
     const double *dy = nullptr, *dw = nullptr;
     bool bound = false;
+    double keep_mb = -1.0; // L2-resident head of the shard in MB (GSLNLS_L2_KEEP_MB; < 0: automatic)
     int wgsl = 0; // weights mode: 0 rows of J weighted too (default), 1 GSL multilarge's (f, fvv only)
     int upload_sharing = 1; // uploads running side by side in this process (one per GPU of a multi-GPU call)
     // kernels
@@ -233,6 +235,13 @@ static int ensure_workspace(gslnls_problem *pb, int ncand, int grid_x, int ntrac
     return GSLNLS_SUCCESS;
 }
 
+// how much of a shard to hold in L2 across passes: nothing is gained once the pass is many times the cache
+static double default_keep_mb(double pass_bytes)
+{
+    (void)pass_bytes;
+    return 0.0; // set from measurements, see DESIGN.md
+}
+
 static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
 {
     NlsPassParams prm;
@@ -252,6 +261,12 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
     prm.watchdog_ns = pb->watchdog_ns;
+    {
+        // L2 residency: the first keep_mb of the pass's bytes are loaded evict_last (nls_pass_kernel.cuh)
+        const double row_bytes = 8.0 * (pb->nvar + 1 + pb->has_w);
+        const double keep = pb->keep_mb >= 0.0 ? pb->keep_mb : default_keep_mb(row_bytes * (double)pb->n);
+        prm.keep_rows = ncand == 1 ? (long long)std::min((double)pb->n, keep * 1048576.0 / row_bytes) : 0;
+    }
     static const bool flat_red = std::getenv("GSLNLS_FLAT_RED") != nullptr; // developer aid
     // two-level grid reduction for long packets (p > 8); a short packet is summed faster by one CTA
     if (ncand == 1 && pb->grid_x > NLS_RED_GROUP && pb->pk_stride >= 48 && !flat_red) {
@@ -529,6 +544,8 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
         pb->watchdog_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000000ull;
     pb->wgsl = default_weights_mode();
+    if (const char *c = std::getenv("GSLNLS_L2_KEEP_MB"))
+        pb->keep_mb = std::atof(c);
     if (const char *c = std::getenv("GSLNLS_HANDSHAKE_MS"))
         pb->handshake_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000ull;
     CK(cudaStreamCreateWithFlags(&pb->srv_stream, cudaStreamNonBlocking));
@@ -1619,12 +1636,11 @@ GSLNLS_API void gslnls_result_free(gslnls_result *r)
 }
 
 // ---- batched multi-start inner kernels ------------------------------------------------------
-GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts, int S, const int *control_int,
-                                        const double *control_dbl, double *par_out, double *ssr_out,
-                                        double *logdet_out, int *conv_out, int *niter_out)
+// S candidates side by side: candidates ride blockIdx.y of the pass kernel and one thread each of the batched
+// trust-region step; `iters` outer iterations per candidate.  Leaves the S state records in `states`.
+static int batch_run(gslnls_problem *pb, const double *starts, int S, const int *control_int,
+                     const double *control_dbl, std::vector<double> &states)
 {
-    if (!pb || !starts || S < 1 || !control_int || !control_dbl)
-        return GSLNLS_EINVAL;
     if (pb->p > 8) {
         set_error("batched multi-start supports p <= 8");
         return GSLNLS_EINVAL;
@@ -1637,6 +1653,7 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
     if (rc)
         return rc;
     pb->P.trace = 0;
+    stop_server(pb);
     rc = prepare(pb, S, 0, true);
     if (rc)
         return rc;
@@ -1665,8 +1682,22 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
         CK(cudaStreamSynchronize(pb->stream));
         fin = pb->h_ndone[0] >= S;
     }
-    std::vector<double> St((size_t)S * pb->state_stride);
-    CK(cudaMemcpy(St.data(), pb->d_state, sizeof(double) * St.size(), cudaMemcpyDeviceToHost));
+    states.resize((size_t)S * pb->state_stride);
+    CK(cudaMemcpy(states.data(), pb->d_state, sizeof(double) * states.size(), cudaMemcpyDeviceToHost));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts, int S, const int *control_int,
+                                        const double *control_dbl, double *par_out, double *ssr_out,
+                                        double *logdet_out, int *conv_out, int *niter_out)
+{
+    if (!pb || !starts || S < 1 || !control_int || !control_dbl)
+        return GSLNLS_EINVAL;
+    std::vector<double> St;
+    int rc = batch_run(pb, starts, S, control_int, control_dbl, St);
+    if (rc)
+        return rc;
+    const int p = pb->p;
     for (int c = 0; c < S; ++c) {
         const double *s = St.data() + (size_t)c * pb->state_stride;
         if (par_out)
@@ -1679,6 +1710,117 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
             conv_out[c] = (int)s[trs::S_PHASE] == trs::PH_DONE ? (int)s[trs::S_STATUS] : GSLNLS_CONTINUE;
         if (niter_out)
             niter_out[c] = (int)s[trs::S_NITER];
+    }
+    return GSLNLS_SUCCESS;
+}
+
+} // extern "C"
+
+// ---- multi-start global search (control logic: mstart.hpp; local searches: the batched kernels) ----
+namespace {
+struct GpuBatchEvaluator {
+    gslnls_problem *pb;
+    const int *ci;
+    const double *cd;
+    int rc = GSLNLS_SUCCESS;
+    void operator()(const std::vector<double> &starts, int S, int iters, std::vector<mstart::BatchResult> &out)
+    {
+        out.assign(S, mstart::BatchResult());
+        const int p = pb->p;
+        int c_int[7];
+        double c_dbl[8];
+        std::memcpy(c_int, ci, sizeof(c_int));
+        std::memcpy(c_dbl, cd, sizeof(c_dbl));
+        c_int[0] = iters;
+        c_int[1] = 0;
+        c_dbl[7] = 1.0e-3; // gtol of the inner searches, src/nls_mstart.c:90, :250
+        std::vector<double> St;
+        if (rc == GSLNLS_SUCCESS)
+            rc = batch_run(pb, starts.data(), S, c_int, c_dbl, St);
+        for (int c = 0; c < S; ++c) {
+            mstart::BatchResult &b = out[c];
+            b.par.assign(starts.begin() + (size_t)c * p, starts.begin() + (size_t)(c + 1) * p);
+            b.diag.assign(p, 1.0);
+            b.ssr = b.ssr_prev = b.ssr_start = std::numeric_limits<double>::infinity();
+            b.logdet_start = b.logdet_end = -std::numeric_limits<double>::infinity();
+            b.status = GSLNLS_FAILURE;
+            if (rc != GSLNLS_SUCCESS)
+                continue;
+            const double *s = St.data() + (size_t)c * pb->state_stride;
+            const double *v = s + trs::S_COUNT;
+            b.par.assign(v, v + p);
+            b.diag.assign(v + 3 * p, v + 4 * p);
+            b.ssr = s[trs::S_CHISQ1];
+            b.ssr_prev = s[trs::S_CHISQ0];
+            b.ssr_start = s[trs::S_CHISQ_INIT];
+            b.logdet_start = s[trs::S_LOGDET0];
+            b.logdet_end = s[trs::S_LOGDET1];
+            b.status = (int)s[trs::S_STATUS];
+        }
+    }
+};
+} // namespace
+
+extern "C" {
+
+GSLNLS_API int gslnls_problem_multistart(gslnls_problem *pb, const double *range, const int *has_range,
+                                         const int *control_int, const double *control_dbl, const int *mstart_int,
+                                         const double *mstart_dbl, gslnls_mstart_result *out)
+{
+    if (!pb || !range || !has_range || !control_int || !control_dbl || !mstart_int || !mstart_dbl || !out)
+        return GSLNLS_EINVAL;
+    std::memset(out, 0, sizeof(*out));
+    mstart::Control c;
+    c.n = mstart_int[0]; c.p = mstart_int[1]; c.q = mstart_int[2]; c.s = mstart_int[3];
+    c.niter = mstart_int[4]; c.max = mstart_int[5]; c.minsp = mstart_int[6];
+    c.r = mstart_dbl[0]; c.tol = mstart_dbl[1];
+    if (c.n < 1 || c.p < 1 || c.q < 1 || c.s < 1 || c.niter < 1 || c.max < 1 || c.minsp < 1 || !(c.r > 1.0) || !(c.tol > 0.0)) {
+        set_error("invalid multi-start control values"); // R/nls.R:681-689
+        return GSLNLS_EINVAL;
+    }
+    GpuBatchEvaluator ev{pb, control_int, control_dbl};
+    mstart::Driver<GpuBatchEvaluator> drv(pb->p, c, range, has_range, control_dbl[5], control_dbl[6], ev);
+    const mstart::Outcome o = drv.run();
+    if (ev.rc)
+        return ev.rc;
+    const int p = pb->p;
+    out->p = p;
+    out->par = dup(o.par.data(), p);
+    out->range = dup(o.range.data(), 2 * (size_t)p);
+    out->ssr = o.ssr;
+    out->ssrconv = o.ssrconv;
+    out->nsp = o.nsp;
+    out->nwsp = o.nwsp;
+    out->mstarts = o.mstarts;
+    out->status = o.status;
+    out->searches = o.searches;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API void gslnls_mstart_result_free(gslnls_mstart_result *r)
+{
+    if (!r)
+        return;
+    std::free(r->par);
+    std::free(r->range);
+    std::memset(r, 0, sizeof(*r));
+}
+
+/* test hook: the first `count` points of the quasi-random generator the multi-start sampler uses for `dim`
+ * parameters (Sobol below 41 dimensions, Halton above), row-major count x dim */
+GSLNLS_API int gslnls_qrng_points(int dim, int count, double *out)
+{
+    if (dim < 1 || count < 0 || !out)
+        return GSLNLS_EINVAL;
+    if (dim < 41) {
+        mstart::Sobol g(dim);
+        for (int i = 0; i < count; ++i)
+            if (!g.next(out + (size_t)i * dim))
+                return GSLNLS_FAILURE;
+    } else {
+        mstart::Halton g(dim);
+        for (int i = 0; i < count; ++i)
+            g.next(out + (size_t)i * dim);
     }
     return GSLNLS_SUCCESS;
 }

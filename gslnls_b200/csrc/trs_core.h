@@ -42,7 +42,7 @@ enum { E_SUCCESS = 0, E_FAILURE = -1, E_CONTINUE = -2, E_EDOM = 1, E_EBADFUNC = 
 enum {
     S_PHASE = 0, S_STATUS, S_INFO, S_NITER, S_ITER, S_BAD, S_NU, S_NEVAL_F, S_NEVAL_DFU, S_NEVAL_DF2,
     S_NEVAL_FVV, S_MU, S_DELTA, S_AVRATIO, S_CHISQ0, S_CHISQ1, S_F2, S_CHISQ_INIT, S_NPASS, S_RHO,
-    S_LOGDET0, S_NBAD, S_COUNT = 24
+    S_LOGDET0, S_NBAD, S_LOGDET1, S_COUNT = 24
 };
 
 struct Params {
@@ -111,7 +111,7 @@ struct Solver {
     int phase, status, info, niter, iter, bad;
     double nu;
     double nf, ndfu, ndf2, nfvv, npass;
-    double mu, delta, avratio, chisq0, chisq1, f2, chisq_init, rho, logdet0;
+    double mu, delta, avratio, chisq0, chisq1, f2, chisq_init, rho, logdet0, logdet1;
     double nbad; // number of non-finite residuals in the current f
     // per-iteration subproblem products (recomputed from g, JTJ, diag on every call)
     double norm_Dgn, norm_Dsd, norm_Dinvg, norm_JDinv2g;
@@ -1006,7 +1006,7 @@ struct Solver {
         nf = S[S_NEVAL_F]; ndfu = S[S_NEVAL_DFU]; ndf2 = S[S_NEVAL_DF2]; nfvv = S[S_NEVAL_FVV];
         mu = S[S_MU]; delta = S[S_DELTA]; avratio = S[S_AVRATIO]; chisq0 = S[S_CHISQ0];
         chisq1 = S[S_CHISQ1]; f2 = S[S_F2]; chisq_init = S[S_CHISQ_INIT]; npass = S[S_NPASS];
-        rho = S[S_RHO]; logdet0 = S[S_LOGDET0]; nbad = S[S_NBAD];
+        rho = S[S_RHO]; logdet0 = S[S_LOGDET0]; nbad = S[S_NBAD]; logdet1 = S[S_LOGDET1];
         const double *v = S + S_COUNT;
         for (int i = 0; i < p; ++i) {
             x[i] = v[i]; dx[i] = v[p + i]; g[i] = v[2 * p + i]; diag[i] = v[3 * p + i];
@@ -1032,6 +1032,7 @@ struct Solver {
             S[S_NEVAL_DF2] = ndf2; S[S_NEVAL_FVV] = nfvv; S[S_MU] = mu; S[S_DELTA] = delta;
             S[S_AVRATIO] = avratio; S[S_CHISQ0] = chisq0; S[S_CHISQ1] = chisq1; S[S_F2] = f2;
             S[S_CHISQ_INIT] = chisq_init; S[S_NPASS] = npass; S[S_RHO] = rho; S[S_LOGDET0] = logdet0; S[S_NBAD] = nbad;
+            S[S_LOGDET1] = logdet1;
             double *v = S + S_COUNT;
             for (int i = 0; i < p; ++i) {
                 v[i] = x[i]; v[p + i] = dx[i]; v[2 * p + i] = g[i]; v[3 * p + i] = diag[i];
@@ -1103,6 +1104,17 @@ struct Solver {
         phase = PH_DONE;
         if (L.lane() == 0)
             req[0] = (double)MODE_IDLE;
+        if (P.batch_iters > 0) {
+            // multi-start screen after the search: log det(J^T J) at the final point (det_cholesky_jtj,
+            // src/nls_mstart.c:93, :251); -inf when the factorisation fails
+            logdet1 = -HUGE_VAL;
+            if (factor(0.0) == E_SUCCESS) {
+                double s = 0.0;
+                for (int i = 0; i < p; ++i)
+                    s += 2.0 * log(A[i * p + i]);
+                logdet1 = s;
+            }
+        }
         store(S, true);
         if (st == E_SUCCESS || st == E_EMAXITER)
             write_covar(S);

@@ -250,6 +250,32 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
                                         double *logdet_out /* S: log det(J^T J) at start, or NULL */,
                                         int *conv_out /* S */, int *niter_out /* S */);
 
+/* ---- multi-start global search: the control logic of gsl_multistart_driver (src/nls_mstart.c:24-349) and its
+ *      outer loop (src/nls.c:274-399) over the batched kernels above --------------------------------
+ * range       2p doubles (lower, upper) per parameter: the sampling ranges (`start` given as ranges)
+ * has_range   2p flags: 0 where the user gave no (finite) limit -> that side adapts dynamically; the caller
+ *             substitutes the reference's defaults -0.1 / 0.75 there (R/nls.R:412-422)
+ * mstart_int  {mstart_n, mstart_p, mstart_q, mstart_s, mstart_maxiter, mstart_maxstart, mstart_minsp}
+ *             = control_int[6..12] of the reference's gsl_nls() call (src/nls.c:300-306)
+ * mstart_dbl  {mstart_r, mstart_tol} = control_dbl[8..9] (:308-309)
+ * The result is the start vector the final fit is launched from (src/nls.c:518-541). */
+typedef struct gslnls_mstart_result {
+    int p;
+    double *par;     /* [p]  best stationary point found (or the fall-back sample) */
+    double *range;   /* [2p] sampling ranges at the end */
+    double ssr, ssrconv;
+    int nsp, nwsp, mstarts; /* stationary points, worse stationary points since the last one, major iterations */
+    int status;      /* 0: stopping rule nsp >= minsp && nwsp > r + sqrt(r) nsp met; 11: mstart_maxstart reached */
+    int64_t searches; /* local searches run */
+} gslnls_mstart_result;
+GSLNLS_API int gslnls_problem_multistart(gslnls_problem *pb, const double *range, const int *has_range,
+                                         const int *control_int, const double *control_dbl, const int *mstart_int,
+                                         const double *mstart_dbl, gslnls_mstart_result *out);
+GSLNLS_API void gslnls_mstart_result_free(gslnls_mstart_result *r);
+/* test hook: first `count` points (row-major count x dim) of the quasi-random generator behind the sampler:
+ * restatements of gsl_qrng_sobol (dim < 41) / gsl_qrng_halton (src/nls.c:277-280) */
+GSLNLS_API int gslnls_qrng_points(int dim, int count, double *out);
+
 /* ---- multi-GPU exchange (one process per GPU) ------------------------------------------------ */
 #define GSLNLS_COMM_ID_BYTES 128
 /* rank 0 creates an id and ships it to the other ranks by any means (MPI, files, a process-group broadcast) */

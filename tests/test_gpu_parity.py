@@ -444,8 +444,10 @@ def test_tma_ring_shrinks_to_fit_many_columns(G, monkeypatch):
 # ---------------------------------------------------------------- round-2 additions
 def test_center_difference_jacobian_on_gpu(G, readme_examples):
     """jac="center": src/fdjac.c:81-128 (+-delta/2, delta = h |x_j| or h) inside the pass kernel, against the
-    oracle's restatement of the same rule -- packet at 1e-9 of the centred-difference oracle (differences of
-    nearly equal numbers: the FD noise floor, not a summation error) and the full fit at 1e-8"""
+    oracle's restatement of the same rule.  A difference quotient with step delta ~ 1.5e-8 amplifies the last-ulp
+    differences between the device exp() and libm's by 1/delta: J entries agree to ~eps/h ~ 1e-8 by
+    construction, so the gates here are 5e-8 on the packet (not 1e-12, which is a summation gate) and 1e-6 on
+    the fitted parameters, with equal iteration counts."""
     e = readme_examples["example2"]
     x, y = np.array(e["x"]), np.array(e["y"])
     m = G.Model("a * exp(-(x - b)^2 / (2 * c^2))", ["a", "b", "c"], ["x"], jac="center")
@@ -453,13 +455,13 @@ def test_center_difference_jacobian_on_gpu(G, readme_examples):
     for theta in ([1.0, 0.0, 1.0], [4.5, 0.45, 0.15]):
         got = pb.eval_packet(theta)
         ref = O.eval_packet("gauss", y, theta, x=x, fd_jac=2, longdouble=True)
-        assert rel_packet_err(got, ref, 3) < 1e-9, theta
+        assert rel_packet_err(got, ref, 3) < 5e-8, theta
         ana = O.eval_packet("gauss", y, theta, x=x, longdouble=True)
         assert rel_packet_err(got, ana, 3) < 1e-6   # and close to the analytic Jacobian's packet
     for alg in ("lm", "dogleg"):
         fit = pb.fit(e["start"], algorithm=alg, control=dict(G.gsl_nls_control(), fdtype="center"))
         ref = O.nls_large("gauss", y, e["start"], x=x, algorithm=alg, fd_jac=2, fdtype="center")
-        _fit_cmp(fit, ref)
+        _fit_cmp(fit, ref, tol=1e-6)
     pb.close()
     # tiled kernel (p > 8) with centred differences
     rng = np.random.Generator(np.random.Philox(key=21))
@@ -475,7 +477,7 @@ def test_center_difference_jacobian_on_gpu(G, readme_examples):
     st = th * 1.02
     got = pb.eval_packet(st)
     ref = O.eval_packet("gaussmix", yy, st, x=xx, fd_jac=2, longdouble=True)
-    assert rel_packet_err(got, ref, 9) < 1e-8
+    assert rel_packet_err(got, ref, 9) < 5e-7
     pb.close()
 
 
