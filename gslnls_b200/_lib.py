@@ -73,6 +73,7 @@ SIGNATURES = {
     "gslnls_problem_fit_run": (C.c_int, [C.c_void_p, C.c_int, c_int_p, C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     "gslnls_problem_fit_end": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Result)]),
     "gslnls_problem_launch_count": (C.c_int64, [C.c_void_p]),
+    "gslnls_problem_trace": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.c_int, c_int_p]),
     "gslnls_problem_timer_start": (C.c_int, [C.c_void_p]),
     "gslnls_problem_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gslnls_problem_set_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -34,6 +34,7 @@ struct Variant {
     std::string log;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t pass = nullptr, materialise = nullptr;
+    cudaKernel_t persistent = nullptr; // nls_pass_persistent (TMA-ring variants only): one launch per fit
     bool loaded = false;
     size_t pass_smem = 0; // dynamic shared memory of one nls_pass CTA (tiled variant)
     std::vector<int> smem_devices; // devices on which the dynamic shared-memory limit has been raised
@@ -57,7 +58,8 @@ struct gslnls_model {
 
 namespace gslnls {
 // shard_bytes: bytes one pass reads on this GPU (0 = unknown / small); picks the load path of the p <= 4 kernel
-KernelTune default_tune(int p, double shard_bytes = 0.0);
+// persistent: the fit will run the one-launch-per-fit kernel, which exists for the TMA-ring variant only
+KernelTune default_tune(int p, double shard_bytes = 0.0, bool persistent = false);
 size_t tiled_smem_bytes(int p, int block, int nprod, int nconst); // dynamic shared memory of the tiled pass kernel
 size_t tma_smem_bytes(int narr, int block, int unroll, int stages); // dynamic shared memory of the TMA-staged pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture

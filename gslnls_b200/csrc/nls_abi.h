@@ -46,6 +46,10 @@ struct NlsPassParams {
     int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
     unsigned long long watchdog_ns;   // server mode: longest in-kernel wait for a request (GSLNLS_WATCHDOG_S)
+    int max_passes;                   // persistent kernel: leave after this many passes even if the fit goes on
+    int pad2_;
+    volatile int *host_passes;        // persistent kernel: passes executed, written at exit (mapped host memory) or nullptr
+    unsigned long long *trace;        // developer hook: [gridDim.x][8] globaltimer stamps of each CTA's phases, or nullptr
     long long keep_rows;              // rows [0, keep_rows) of every column are loaded with an L2 evict_last policy,
                                       // the rest evict_first: the head of the shard stays L2-resident from pass to pass
     // two-level grid reduction (single-candidate launches): CTAs in groups of NLS_RED_GROUP, the last

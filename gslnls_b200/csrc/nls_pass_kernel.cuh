@@ -132,6 +132,19 @@ static __device__ __forceinline__ unsigned long long nls_globaltimer()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// developer hook (gslnls_problem_trace): phase stamps of every CTA -- 0 entry, 1 request seen, 2 thread 0 done
+// streaming, 3 whole CTA done streaming, 4 CTA partial written, 5 (last CTA only) packet published
+static __device__ __forceinline__ void nls_trace(const NlsPassParams &prm, int slot)
+{
+    if (prm.trace && threadIdx.x == 0 && blockIdx.y == 0)
+        prm.trace[(size_t)blockIdx.x * 32 + slot] = nls_globaltimer();
+}
+// slots 8 + w: warp w is done streaming (stamped by its lane 0)
+static __device__ __forceinline__ void nls_trace_warp(const NlsPassParams &prm)
+{
+    if (prm.trace && (threadIdx.x & 31) == 0 && blockIdx.y == 0 && (threadIdx.x >> 5) < 24)
+        prm.trace[(size_t)blockIdx.x * 32 + 8 + (threadIdx.x >> 5)] = nls_globaltimer();
+}
 #define NLS_WATCHDOG_NS 60000000000ull /* default when the host passes no period (prm.watchdog_ns == 0) */
 
 // ------------------------------------------------------------------------------------ model glue
@@ -714,6 +727,7 @@ static __device__ __forceinline__ void nls_packet_out(const NlsPassParams &prm, 
 }
 static __device__ __forceinline__ void nls_packet_publish(const NlsPassParams &prm, int cand, unsigned long long seq)
 {
+    nls_trace(prm, 5);
     if (prm.channel) {
         if (prm.nranks > 1)
             __threadfence_system();
@@ -829,9 +843,11 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
 {
     const int cand = blockIdx.y;
     const double *req = prm.req + (size_t)cand * prm.req_stride;
+    nls_trace(prm, 0);
     const int mode = nls_begin(prm, req);
     if (mode == NLS_MODE_IDLE)
         return; // this candidate has finished; uniform for the whole CTA
+    nls_trace(prm, 1);
     nls_exp_init();
 
     NlsThread T;
@@ -861,6 +877,8 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     // ---- CTA reduction: fixed shuffle tree, then warps summed in warp order ----
     __shared__ double sred[NLS_NW][NLS_PK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    nls_trace(prm, 2);
+    nls_trace_warp(prm);
 #pragma unroll
     for (int e = 0; e < NLS_PK; ++e) {
         double v = acc[e];
@@ -873,6 +891,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
             sred[warp][e] = v;
     }
     __syncthreads();
+    nls_trace(prm, 3);
     double *part = prm.partials + ((size_t)cand * gridDim.x + blockIdx.x) * prm.pk_stride;
     for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK) {
         double s = 0.0;
@@ -881,9 +900,303 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
             s += sred[w][e];
         part[e] = s;
     }
+    nls_trace(prm, 4);
     nls_grid_finish(prm, cand);
 }
 #endif // NLS_TILED == 1
+
+#if NLS_TILED == 2
+// ------------------------------------------------------------------------------------ K1, persistent
+// One launch per FIT instead of one per pass (resident-server mode, TMA ring).  The grid stays on the SMs and
+// every CTA loops over the passes of the fit: wait for request k from the trust-region server, stream the
+// shard, reduce, the last CTA to arrive deposits the packet; the server steps and publishes request k + 1.
+// What this removes from every pass of a small shard (200 MB = 31 us of HBM time on an 8-GPU split):
+//   * the launch and its dispatch, and the cold instruction / constant lines of the epilogue: code that ran
+//     35 us ago is still in the SM's instruction cache, code of a fresh launch is fetched from DRAM behind
+//     20 MB of queued streaming requests (measured: 11 us between "all warps done" and "partial written");
+//   * the empty ring at the start of a pass: x and y do not depend on theta, so the producer lane does not
+//     stop at the end of a pass -- it refills the ring with the FIRST tiles of the next pass while the
+//     consumers reduce and the server steps (4 stages x 36 KB x 148 SMs = 21 MB are in shared memory when
+//     request k + 1 lands).
+// Consumers synchronise among themselves on named barrier 1 (the producer warp never joins a CTA barrier
+// after the set-up).  Same arithmetic per observation as nls_pass; the thread -> row mapping of the ragged
+// tail differs, so packets agree with the per-launch kernels to rounding, not bitwise.
+static __device__ __forceinline__ void nls_cons_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NLS_NCONS) : "memory");
+}
+static __device__ __forceinline__ bool nls_bar_try(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}" : "=r"(ok) : "r"(nls_saddr(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+
+template <int MODE>
+static __device__ __forceinline__ void nls_persistent_stream(const NlsPassParams &prm, const NlsThread &T, double *acc,
+                                                             int &nbad, const double *buf, unsigned long long *full,
+                                                             unsigned long long *empty, long long my_tiles,
+                                                             unsigned long long &gc)
+{
+    const int lane = threadIdx.x & 31;
+    for (long long i = 0; i < my_tiles; ++i, ++gc) {
+        const int s = (int)(gc % NLS_STAGES);
+        nls_bar_wait(full + s, (unsigned)((gc / NLS_STAGES) & 1ull));
+        const double *b = buf + (size_t)s * NLS_STAGE_DOUBLES;
+        double2 xv[NLS_UNROLL][NLS_NV], yv[NLS_UNROLL], wv[NLS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            const int o = 2 * (u * NLS_NCONS + (int)threadIdx.x);
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k)
+                xv[u][k] = *reinterpret_cast<const double2 *>(b + k * NLS_TILE + o);
+            yv[u] = *reinterpret_cast<const double2 *>(b + GSLNLS_NVAR * NLS_TILE + o);
+#if NLS_HAS_W
+            wv[u] = *reinterpret_cast<const double2 *>(b + (GSLNLS_NVAR + 1) * NLS_TILE + o);
+#else
+            wv[u] = make_double2(1.0, 1.0);
+#endif
+        }
+        __syncwarp();
+        if (lane == 0)
+            nls_bar_arrive(empty + s); // the slot can be refilled while we compute
+#pragma unroll
+        for (int u = 0; u < NLS_UNROLL; ++u) {
+            double xa[NLS_NV], xb[NLS_NV];
+#pragma unroll
+            for (int k = 0; k < GSLNLS_NVAR; ++k) {
+                xa[k] = xv[u][k].x;
+                xb[k] = xv[u][k].y;
+            }
+            nls_observe<MODE>(T, xa, yv[u].x, wv[u].x, acc, nbad);
+            nls_observe<MODE>(T, xb, yv[u].y, wv[u].y, acc, nbad);
+        }
+    }
+    // rows past the last full tile: one scalar load per consumer thread and grid stride
+    for (long long r = (prm.n / NLS_TILE) * NLS_TILE + (long long)blockIdx.x * NLS_NCONS + threadIdx.x; r < prm.n;
+         r += (long long)gridDim.x * NLS_NCONS) {
+        double xa[NLS_NV];
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = nls_ld1(prm.vars[k] + r);
+#if NLS_HAS_W
+        const double ww = nls_ld1(prm.w + r);
+#else
+        const double ww = 1.0;
+#endif
+        nls_observe<MODE>(T, xa, nls_ld1(prm.y + r), ww, acc, nbad);
+    }
+    if (MODE == NLS_MODE_FJ)
+        acc[NLS_NPK + NLS_P + 1] = (double)nbad;
+}
+
+extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(const NlsPassParams prm)
+{
+    extern __shared__ __align__(128) unsigned char nls_dyn[];
+    double *buf = reinterpret_cast<double *>(nls_dyn); // [NLS_STAGES][NLS_NARR][NLS_TILE]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(buf + (size_t)NLS_STAGES * NLS_STAGE_DOUBLES);
+    unsigned long long *empty = full + NLS_STAGES;
+    __shared__ double sred[NLS_NCW][NLS_PK];
+    __shared__ unsigned long long s_seq, s_consumed;
+    __shared__ int s_mode, s_last;
+    __shared__ volatile int s_stop;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntile = prm.n / NLS_TILE;
+    const long long my_tiles = ntile > (long long)blockIdx.x ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NLS_STAGES; ++s) {
+            nls_bar_init(full + s, 1);
+            nls_bar_init(empty + s, NLS_NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_stop = 0;
+        s_consumed = 0ull;
+    }
+    nls_exp_init(); // contains a CTA-wide barrier: the last one the producer warp takes part in
+    __syncthreads();
+
+    if (warp == NLS_NCW) {
+        // ---- producer lane: keeps the ring full, across pass boundaries ----
+        if (lane == 0 && my_tiles > 0) {
+            const NlsPolicy PL = nls_policy(prm.keep_rows);
+            unsigned long long g = 0ull; // tiles issued since the kernel started
+            bool stop = false;
+            while (!stop) {
+                for (long long i = 0; i < my_tiles && !stop; ++i) {
+                    const int s = (int)(g % NLS_STAGES);
+                    const unsigned ph = (unsigned)(((g / NLS_STAGES) & 1ull) ^ 1ull);
+                    while (!nls_bar_try(empty + s, ph)) {
+                        if (s_stop) {
+                            stop = true;
+                            break;
+                        }
+                    }
+                    if (stop)
+                        break;
+                    nls_bar_expect_tx(full + s, (unsigned)(NLS_STAGE_DOUBLES * sizeof(double)));
+                    double *dst = buf + (size_t)s * NLS_STAGE_DOUBLES;
+                    const long long o = ((long long)blockIdx.x + i * gridDim.x) * NLS_TILE;
+                    const unsigned long long policy = (o < PL.keep_rows) ? PL.keep : PL.stream;
+#pragma unroll
+                    for (int k = 0; k < GSLNLS_NVAR; ++k)
+                        nls_bulk_g2s(dst + k * NLS_TILE, prm.vars[k] + o, NLS_TILE * 8u, full + s, policy);
+                    nls_bulk_g2s(dst + GSLNLS_NVAR * NLS_TILE, prm.y + o, NLS_TILE * 8u, full + s, policy);
+#if NLS_HAS_W
+                    nls_bulk_g2s(dst + (GSLNLS_NVAR + 1) * NLS_TILE, prm.w + o, NLS_TILE * 8u, full + s, policy);
+#endif
+                    ++g;
+                }
+            }
+            // tiles requested for a pass that will not happen: their bytes must land before the CTA may go
+            __threadfence_block();
+            for (unsigned long long j = s_consumed; j < g; ++j)
+                nls_bar_wait(full + (int)(j % NLS_STAGES), (unsigned)((j / NLS_STAGES) & 1ull));
+        }
+        return;
+    }
+
+    // ---- consumers ----
+    unsigned long long gc = 0ull; // tiles consumed since the kernel started
+    int done_passes = 0;
+    unsigned long long k = 0ull;
+    for (int pass = 0; pass < prm.max_passes; ++pass) {
+        // wait for this pass's request (published by the resident trust-region server)
+        if (threadIdx.x == 0) {
+            if (pass == 0)
+                k = __ldcg((const unsigned long long *)(prm.channel + NLS_CH_PASS_CTR)) + 1ull;
+            else
+                ++k;
+            const unsigned long long *rs = (const unsigned long long *)(prm.channel + NLS_CH_REQ_SEQ);
+            const unsigned long long *ab = (const unsigned long long *)(prm.channel + NLS_CH_ABORT);
+            if (pass == 0 && blockIdx.x == 0) // start-of-fit handshake, see nls_begin
+                nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_PASS_SEEN), k);
+            const unsigned long long wd = prm.watchdog_ns ? prm.watchdog_ns : NLS_WATCHDOG_NS;
+            unsigned long long t0 = 0ull, spins = 0ull;
+            int mode = -1;
+            while (nls_ld_acquire_gpu(rs) < k) {
+                if ((++spins & 1023ull) == 0ull) {
+                    const unsigned long long t = nls_globaltimer();
+                    if (t0 == 0ull)
+                        t0 = t;
+                    else if (t - t0 > wd || nls_ld_acquire_gpu(ab) != 0ull) {
+                        mode = NLS_MODE_IDLE; // give up (watchdog), or the host ended the fit early
+                        break;
+                    }
+                }
+            }
+            if (mode < 0)
+                mode = (int)__ldcg(prm.req);
+            s_mode = mode;
+            s_seq = k;
+            if (blockIdx.x == 0 && mode != NLS_MODE_IDLE)
+                *(unsigned long long *)(prm.channel + NLS_CH_TIMER) = nls_globaltimer();
+        }
+        nls_cons_sync();
+        const int mode = s_mode;
+        if (mode == NLS_MODE_IDLE)
+            break;
+        nls_trace(prm, 1);
+        NlsThread T;
+        nls_load_request(prm, prm.req, T);
+        double acc[NLS_PK];
+#pragma unroll
+        for (int e = 0; e < NLS_PK; ++e)
+            acc[e] = 0.0;
+        int nbad = 0;
+        if (mode == NLS_MODE_FJ)
+            nls_persistent_stream<NLS_MODE_FJ>(prm, T, acc, nbad, buf, full, empty, my_tiles, gc);
+        else if (mode == NLS_MODE_FVV)
+            nls_persistent_stream<NLS_MODE_FVV>(prm, T, acc, nbad, buf, full, empty, my_tiles, gc);
+        else
+            nls_persistent_stream<NLS_MODE_JVP>(prm, T, acc, nbad, buf, full, empty, my_tiles, gc);
+        nls_trace(prm, 2);
+        nls_trace_warp(prm);
+
+        // ---- CTA reduction among the consumer warps: fixed shuffle tree, warps summed in warp order ----
+#pragma unroll
+        for (int e = 0; e < NLS_PK; ++e) {
+            double v = acc[e];
+            v += __shfl_down_sync(0xffffffffu, v, 16);
+            v += __shfl_down_sync(0xffffffffu, v, 8);
+            v += __shfl_down_sync(0xffffffffu, v, 4);
+            v += __shfl_down_sync(0xffffffffu, v, 2);
+            v += __shfl_down_sync(0xffffffffu, v, 1);
+            if (lane == 0)
+                sred[warp][e] = v;
+        }
+        nls_cons_sync();
+        nls_trace(prm, 3);
+        double *part = prm.partials + (size_t)blockIdx.x * prm.pk_stride;
+        for (int e = threadIdx.x; e < NLS_PK; e += NLS_NCONS) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NLS_NCW; ++w)
+                s += sred[w][e];
+            part[e] = s;
+        }
+        nls_trace(prm, 4);
+        // ---- grid: the last CTA to arrive sums the CTA partials in CTA order and hands the packet on ----
+        __threadfence();
+        nls_cons_sync();
+        if (threadIdx.x == 0)
+            s_last = (atomicAdd(prm.ticket, 1u) == gridDim.x - 1);
+        nls_cons_sync();
+        if (s_last) {
+            __threadfence();
+            const unsigned long long seq = s_seq;
+            for (int e = warp; e < NLS_PK; e += NLS_NCW) {
+                double s = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32)
+                    s += __ldcg(prm.partials + (size_t)b * prm.pk_stride + e);
+                s += __shfl_down_sync(0xffffffffu, s, 16);
+                s += __shfl_down_sync(0xffffffffu, s, 8);
+                s += __shfl_down_sync(0xffffffffu, s, 4);
+                s += __shfl_down_sync(0xffffffffu, s, 2);
+                s += __shfl_down_sync(0xffffffffu, s, 1);
+                if (lane == 0)
+                    nls_packet_out(prm, 0, seq, e, s);
+            }
+            if (prm.nranks > 1)
+                __threadfence_system();
+            else
+                __threadfence();
+            nls_cons_sync();
+            nls_trace(prm, 5);
+            if (threadIdx.x == 0) {
+                prm.ticket[0] = 0u;
+                unsigned long long *tm = (unsigned long long *)(prm.channel + NLS_CH_TIMER);
+                tm[1] = __ldcg(tm + 1) + (nls_globaltimer() - __ldcg(tm));
+                tm[2] = __ldcg(tm + 2) + 1ull;
+                *(unsigned long long *)(prm.channel + NLS_CH_PASS_CTR) = seq;
+                if (prm.prof_flag)
+                    *prm.prof_flag += 1;
+            }
+            if (prm.nranks > 1) {
+                if ((int)threadIdx.x < prm.nranks)
+                    nls_st_release_sys((unsigned long long *)(prm.peer_channel[threadIdx.x] + NLS_CH_FLAGS + 128 * prm.rank), seq);
+            } else if (threadIdx.x == 0) {
+                nls_st_release_gpu((unsigned long long *)(prm.channel + NLS_CH_FLAGS + 128 * prm.rank), seq);
+            }
+        }
+        ++done_passes;
+    }
+    // ---- leave: tell the producer how far the ring was drained ----
+    if (threadIdx.x == 0) {
+        s_consumed = gc;
+        __threadfence_block();
+        s_stop = 1;
+        if (blockIdx.x == 0 && prm.host_passes) {
+            *prm.host_passes = done_passes;
+            __threadfence_system();
+        }
+    }
+}
+#endif // NLS_TILED == 2 (persistent)
 
 // ------------------------------------------------------------------------------------ K4
 // resid_i = sqrt(w_i) (fn_i - y_i) and grad[i + n j] = sqrt(w_i) J_ij at the final parameters:

@@ -63,6 +63,8 @@ struct gslnls_problem {
     const double *dvars[NLS_MAX_VARS] = {nullptr};
     const double *dy = nullptr, *dw = nullptr;
     bool bound = false;
+    unsigned long long *d_trace = nullptr; // developer hook: per-CTA phase stamps of the last pass
+    int trace_cap = 0;
     double keep_mb = -1.0; // L2-resident head of the shard in MB (GSLNLS_L2_KEEP_MB; < 0: automatic)
     int wgsl = 0; // weights mode: 0 rows of J weighted too (default), 1 GSL multilarge's (f, fvv only)
     int upload_sharing = 1; // uploads running side by side in this process (one per GPU of a multi-GPU call)
@@ -95,6 +97,7 @@ struct gslnls_problem {
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
     bool allow_server = true, server_on = false;
+    bool allow_persistent = true, persistent_on = false; // one pass-kernel launch per fit (GSLNLS_PERSISTENT=0 disables)
     bool server_pending = false; // fit_begin chose the server; it is launched with the first pass (fit_run)
     unsigned long long handshake_ns = 100000000ull; // start-of-fit handshake period (GSLNLS_HANDSHAKE_MS)
     char *own_channel = nullptr; // single-GPU problems own their channel; sharded ones use the comm's
@@ -122,7 +125,7 @@ static void free_workspace(gslnls_problem *pb)
     pb->cap = 0;
 }
 
-static int ensure_kernels(gslnls_problem *pb, bool batch)
+static int ensure_kernels(gslnls_problem *pb, bool batch, bool persistent = false)
 {
     int vec = 2;
     for (int k = 0; k < pb->nvar; ++k)
@@ -130,7 +133,8 @@ static int ensure_kernels(gslnls_problem *pb, bool batch)
             vec = 1;
     if ((reinterpret_cast<uintptr_t>(pb->dy) & 15u) || (pb->dw && (reinterpret_cast<uintptr_t>(pb->dw) & 15u)))
         vec = 1;
-    KernelTune t = default_tune(pb->p, batch ? 0.0 : 8.0 * (pb->nvar + 1 + pb->has_w) * (double)pb->n);
+    KernelTune t = default_tune(pb->p, batch ? 0.0 : 8.0 * (pb->nvar + 1 + pb->has_w) * (double)pb->n,
+                                persistent && !batch && vec == 2);
     if (t.tiled == 2 && (vec != 2 || batch)) { // bulk copies need 16-byte aligned columns; fall back to LDG
         t = default_tune(pb->p, 0.0);
         if (t.tiled == 2) { // forced through GSLNLS_TUNE
@@ -242,9 +246,61 @@ static double default_keep_mb(double pass_bytes)
     return 0.0; // set from measurements, see DESIGN.md
 }
 
+static void fill_pass_params(gslnls_problem *pb, int ncand, int force_mode, NlsPassParams &prm);
+
 static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
 {
     NlsPassParams prm;
+    fill_pass_params(pb, ncand, force_mode, prm);
+    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size() &&
+                       (pb->prof_seen++ % std::max(pb->prof_stride, 1)) == 0;
+    if (timed)
+        prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
+    void *args[] = {&prm};
+    if (timed)
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
+    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
+                        pb->var->pass_smem, pb->stream));
+    if (timed) {
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
+        pb->prof_used += 2;
+    }
+    ++pb->launches;
+    ++pb->passes;
+    return GSLNLS_SUCCESS;
+}
+
+// one launch for (up to) max_passes passes of the current fit: the persistent pass kernel (resident-server
+// mode, TMA-ring variant).  Profiling: one event pair around the launch, the kernel counts its real passes.
+static int launch_persistent(gslnls_problem *pb, int max_passes)
+{
+    NlsPassParams prm;
+    fill_pass_params(pb, 1, 0, prm);
+    prm.max_passes = max_passes;
+    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size();
+    if (timed)
+        prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
+    void *args[] = {&prm};
+    if (timed)
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)pb->var->persistent, dim3(pb->grid_x, 1, 1),
+                                                dim3(pb->vkey.block, 1, 1), args, pb->var->pass_smem, pb->stream);
+    if (e != cudaSuccess) { // every CTA of this grid must be resident at once; plain launch relies on the grid size
+        cudaGetLastError();
+        CK(cudaLaunchKernel((const void *)pb->var->persistent, dim3(pb->grid_x, 1, 1), dim3(pb->vkey.block, 1, 1), args,
+                            pb->var->pass_smem, pb->stream));
+    }
+    if (timed) {
+        CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
+        pb->prof_used += 2;
+    }
+    ++pb->launches;
+    pb->passes += max_passes;
+    return GSLNLS_SUCCESS;
+}
+
+static void fill_pass_params(gslnls_problem *pb, int ncand, int force_mode, NlsPassParams &prm)
+{
     std::memset(&prm, 0, sizeof(prm));
     for (int k = 0; k < pb->nvar; ++k)
         prm.vars[k] = pb->dvars[k];
@@ -261,6 +317,7 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
     prm.pk_stride = pb->pk_stride;
     prm.force_mode = force_mode;
     prm.watchdog_ns = pb->watchdog_ns;
+    prm.trace = (pb->d_trace && pb->grid_x <= pb->trace_cap) ? pb->d_trace : nullptr;
     {
         // L2 residency: the first keep_mb of the pass's bytes are loaded evict_last (nls_pass_kernel.cuh)
         const double row_bytes = 8.0 * (pb->nvar + 1 + pb->has_w);
@@ -284,22 +341,6 @@ static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
                 prm.peer_channel[r] = pb->comm->peer_channel[r];
         }
     }
-    const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size() &&
-                       (pb->prof_seen++ % std::max(pb->prof_stride, 1)) == 0;
-    if (timed)
-        prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
-    void *args[] = {&prm};
-    if (timed)
-        CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
-    CK(cudaLaunchKernel((const void *)pb->var->pass, dim3(pb->grid_x, ncand, 1), dim3(pb->vkey.block, 1, 1), args,
-                        pb->var->pass_smem, pb->stream));
-    if (timed) {
-        CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
-        pb->prof_used += 2;
-    }
-    ++pb->launches;
-    ++pb->passes;
-    return GSLNLS_SUCCESS;
 }
 
 static int exchange_packet(gslnls_problem *pb, size_t count)
@@ -541,6 +582,8 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
         pb->allow_server = std::atoi(c) != 0;
     else if (serialising_environment())
         pb->allow_server = false;
+    if (const char *c = std::getenv("GSLNLS_PERSISTENT"))
+        pb->allow_persistent = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
         pb->watchdog_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000000ull;
     pb->wgsl = default_weights_mode();
@@ -568,6 +611,7 @@ GSLNLS_API void gslnls_problem_free(gslnls_problem *pb)
     stop_server(pb);
     cudaStreamSynchronize(pb->stream);
     cudaFree(pb->own_channel);
+    cudaFree(pb->d_trace);
     cudaFree(pb->d_prof_flags);
     cudaFreeHost(pb->h_flags);
     cudaFreeHost(pb->h_state);
@@ -686,17 +730,21 @@ GSLNLS_API int gslnls_problem_set_comm(gslnls_problem *pb, gslnls_comm *comm)
     return GSLNLS_SUCCESS;
 }
 
-static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch, bool reserve_slot = false)
+static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch, bool reserve_slot = false,
+                   bool persistent = false)
 {
     if (!pb->dy) {
         set_error("no data: call gslnls_problem_upload or gslnls_problem_bind_device first");
         return GSLNLS_EINVAL;
     }
     CK(cudaSetDevice(pb->device));
-    int rc = ensure_kernels(pb, batch);
+    int rc = ensure_kernels(pb, batch, persistent);
     if (rc)
         return rc;
-    pb->grid_x = pick_grid(pb, ncand, reserve_slot);
+    pb->persistent_on = persistent && pb->vkey.tiled == 2 && pb->var->persistent != nullptr;
+    // the TMA-ring CTA (416 threads, ~150 KB of shared memory, one per SM) leaves room for the resident
+    // trust-region warp on the same SM; the LDG variants fill the register file and give it a slot of its own
+    pb->grid_x = pick_grid(pb, ncand, reserve_slot && !pb->persistent_on);
     rc = ensure_workspace(pb, ncand, pb->grid_x, ntrace);
     return rc;
 }
@@ -872,7 +920,8 @@ static int fit_setup(gslnls_problem *pb)
     const bool sharded = pb->comm && pb->comm->nranks > 1;
     const bool use_server = pb->allow_server && !g_server_unsafe.load() && pb->p <= trs_server_max_p() &&
                             trs::packet_doubles(pb->p) + 1 <= NLS_CH_MAXPK && (!sharded || pb->comm->p2p);
-    int rc = prepare(pb, 1, ntrace, false, use_server);
+    const bool want_persistent = use_server && pb->allow_persistent && pb->p <= 4;
+    int rc = prepare(pb, 1, ntrace, false, use_server, want_persistent);
     if (rc)
         return rc;
     if (use_server && pb->h_state_cap < pb->state_stride) {
@@ -960,7 +1009,24 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
         // older chunk's event and looking at the done word the server writes into mapped host memory
         int slot = 0, inflight = 0;
         fin = pb->h_flags[0] != 0;
-        while (!fin && (max_passes <= 0 || run < max_passes)) {
+        if (pb->persistent_on && !fin) {
+            // one launch for the rest of the fit (or for max_passes of it): the grid stays resident, every CTA
+            // loops over the passes; the host only watches the done word and the end of the kernel
+            const int64_t cap = (int64_t)pb->P.maxiter * 34 + 8;
+            const int budget = (int)(max_passes > 0 ? std::min<int64_t>(max_passes, cap) : cap);
+            int rc = launch_persistent(pb, budget);
+            if (rc)
+                return rc;
+            run = budget;
+            CK(cudaEventRecord(pb->ev_chunk[0], pb->stream));
+            cudaError_t q;
+            while ((q = cudaEventQuery(pb->ev_chunk[0])) == cudaErrorNotReady && pb->h_flags[0] == 0) {
+            }
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                CK(q);
+            fin = pb->h_flags[0] != 0;
+        }
+        while (!pb->persistent_on && !fin && (max_passes <= 0 || run < max_passes)) {
             int todo = pb->chunk;
             if (max_passes > 0)
                 todo = (int)std::min<int64_t>(todo, max_passes - run);
@@ -1183,6 +1249,33 @@ GSLNLS_API int gslnls_problem_fit(gslnls_problem *pb, const double *start, const
     return gslnls_problem_fit_end(pb, want_resid_grad, out);
 }
 
+/* developer hook: record globaltimer stamps of every CTA's phases in the pass kernel (0 entry, 1 request seen,
+ * 2 thread 0 done streaming, 3 CTA done streaming, 4 partial written, 5 packet published by the last CTA);
+ * read returns the stamps of the LAST pass launched, [ctas][8] nanoseconds, and the number of CTAs */
+GSLNLS_API int gslnls_problem_trace(gslnls_problem *pb, int enable, unsigned long long *out, int cap_ctas, int *nctas)
+{
+    if (!pb)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    if (enable && !pb->d_trace) {
+        pb->trace_cap = 1024;
+        CK(cudaMalloc(&pb->d_trace, sizeof(unsigned long long) * 32 * pb->trace_cap));
+        CK(cudaMemset(pb->d_trace, 0, sizeof(unsigned long long) * 32 * pb->trace_cap));
+    }
+    if (out && pb->d_trace) {
+        CK(cudaStreamSynchronize(pb->stream));
+        const int n = std::min(std::min(cap_ctas, pb->trace_cap), pb->grid_x);
+        CK(cudaMemcpy(out, pb->d_trace, sizeof(unsigned long long) * 32 * n, cudaMemcpyDeviceToHost));
+        if (nctas)
+            *nctas = n;
+    }
+    if (!enable && pb->d_trace) {
+        cudaFree(pb->d_trace);
+        pb->d_trace = nullptr;
+    }
+    return GSLNLS_SUCCESS;
+}
+
 GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb) { return pb ? pb->launches : 0; }
 
 GSLNLS_API int gslnls_problem_timer_start(gslnls_problem *pb)
@@ -1245,7 +1338,7 @@ GSLNLS_API int gslnls_problem_profile(gslnls_problem *pb, float *avg_pass_ms, in
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, pb->prof_ev[i], pb->prof_ev[i + 1]));
         tot += ms;
-        ++cnt;
+        cnt += real[i / 2]; // 1 for a per-pass launch; the persistent kernel counts the passes it ran
     }
     *npasses_timed = cnt;
     *avg_pass_ms = *npasses_timed ? (float)(tot / (double)*npasses_timed) : 0.f;

@@ -196,6 +196,31 @@ class Problem:
                                                        nit.ctypes.data_as(_lib.c_int_p)))
         return {"par": par, "ssr": ssr, "logdet": ld, "conv": conv, "niter": nit}
 
+    def multistart(self, start_range, has_range=None, algorithm="lm", control=None):
+        """multi-start global search (gsl_multistart_driver, src/nls_mstart.c + src/nls.c:274-399) over batched
+        local searches: returns the start vector for the final fit plus the search statistics.
+        start_range  p pairs (lower, upper); has_range  p pairs of flags, False = side adapts dynamically"""
+        ctrl = gsl_nls_control() if control is None else gsl_nls_control(**dict(control))
+        ci, cd = pack_control(ctrl, algorithm, False)
+        rng = np.ascontiguousarray(start_range, dtype=np.float64).reshape(-1)
+        p = rng.size // 2
+        has = np.ones(2 * p, dtype=np.int32) if has_range is None else \
+            np.ascontiguousarray(np.asarray(has_range, dtype=np.int32).reshape(-1))
+        r = ctrl["mstart_r"] * (10 if not has.all() else 1)     # R/nls.R:711-713
+        mi = np.array([ctrl[k] for k in ("mstart_n", "mstart_p", "mstart_q", "mstart_s", "mstart_maxiter",
+                                         "mstart_maxstart", "mstart_minsp")], dtype=np.int32)
+        md = np.array([r, ctrl["mstart_tol"]], dtype=np.float64)
+        res = _lib.MstartResult()
+        _lib.check(_lib.lib().gslnls_problem_multistart(self.handle, _dptr(rng), has.ctypes.data_as(_lib.c_int_p),
+                                                        ci.ctypes.data_as(_lib.c_int_p), _dptr(cd),
+                                                        mi.ctypes.data_as(_lib.c_int_p), _dptr(md), C.byref(res)))
+        out = {"par": np.ctypeslib.as_array(res.par, shape=(p,)).copy(),
+               "range": np.ctypeslib.as_array(res.range, shape=(p, 2)).copy(), "ssr": res.ssr,
+               "ssrconv": res.ssrconv, "nsp": res.nsp, "nwsp": res.nwsp, "mstarts": res.mstarts,
+               "status": res.status, "searches": res.searches}
+        _lib.lib().gslnls_mstart_result_free(C.byref(res))
+        return out
+
     def timer_start(self):
         _lib.check(_lib.lib().gslnls_problem_timer_start(self.handle))
 
@@ -485,6 +510,17 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
         raise ValueError("starting values need to be provided")       # :468-470 (no selfStart on the device)
     start = dict(start)
     pnames = list(start)
+    # start values given as ranges (lower, upper) or missing (None / NaN): multi-start, as gsl_nls() does for
+    # `start` lists with length-2 elements / NA (R/nls.R:398-424); missing sides default to (-0.1, 0.75)
+    ranges, has_range = None, None
+    if any(v is None or isinstance(v, (tuple, list)) or (isinstance(v, float) and v != v) for v in start.values()):
+        ranges, has_range = [], []
+        for v in start.values():
+            lo, hi = (v if isinstance(v, (tuple, list)) else (v, v))
+            miss = [b is None or b != b or math.isinf(b) for b in (lo, hi)]
+            ranges.append([-0.1 if miss[0] else float(lo), 0.75 if miss[1] else float(hi)])
+            has_range.append([not miss[0], not miss[1]])
+        start = {k: r[0] for k, r in zip(pnames, ranges)}
     two_sided = "~" in fn
     lhs_txt, rhs = (s.strip() for s in fn.split("~", 1)) if two_sided else (None, fn.strip())
     if two_sided and not lhs_txt:
@@ -552,5 +588,11 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     pb.upload(cols, lhs, weights)
     if comm is not None:
         pb.set_comm(comm)
+    ms = None
+    if ranges is not None:
+        ms = pb.multistart(ranges, has_range, algorithm=algorithm, control=ctrl)
+        st = ms["par"]                                          # src/nls.c:534-541: the fit restarts from mpopt
     cfit = pb.fit(st, algorithm=algorithm, control=ctrl, trace=bool(trace))
-    return GslNls(fn, pnames, cfit, pb, mdl, ctrl, algorithm, weights, lhs, bool(trace))
+    obj = GslNls(fn, pnames, cfit, pb, mdl, ctrl, algorithm, weights, lhs, bool(trace))
+    obj.mstart = ms
+    return obj

@@ -228,6 +228,10 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
                                       float *device_ms);
 GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, gslnls_result *out);
 GSLNLS_API int64_t gslnls_problem_launch_count(const gslnls_problem *pb);
+/* developer hook: per-CTA phase stamps (globaltimer ns) of the last pass kernel launch, [ctas][32]:
+ * 0 entry, 1 request seen, 2 thread 0 done streaming, 3 CTA done streaming, 4 partial written, 5 packet published,
+ * 8 + w: warp w done streaming */
+GSLNLS_API int gslnls_problem_trace(gslnls_problem *pb, int enable, unsigned long long *out, int cap_ctas, int *nctas);
 /* device timers on the solver's own stream (CUDA events): a region timer, and optional event
  * pairs around each fused-pass launch so a benchmark can report the pass kernel's mean duration
  * inside its timed region (roofline) */

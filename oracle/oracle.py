@@ -39,7 +39,8 @@ class _FitResult(C.Structure):
                 ("ssrtol", C.c_double), ("niter", C.c_int), ("conv", C.c_int), ("info", C.c_int),
                 ("neval", C.c_size_t * 4), ("partrace", C.POINTER(C.c_double)),
                 ("ssrtrace", C.POINTER(C.c_double)), ("chisq_init", C.c_double),
-                ("condtrace", C.POINTER(C.c_double))]
+                ("condtrace", C.POINTER(C.c_double)), ("diag", C.POINTER(C.c_double)),
+                ("jtj", C.POINTER(C.c_double))]
 
 
 def build(force=False):
@@ -148,6 +149,8 @@ def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=No
         "niter": res.niter, "conv": res.conv, "info": res.info, "status": L.orc_strerror(status).decode(),
         "ssr": res.ssr, "ssrtol": res.ssrtol, "chisq_init": res.chisq_init,
         "neval": {"f": res.neval[0], "dfu": res.neval[1], "df2": res.neval[2], "fvv": res.neval[3]},
+        "diag": np.ctypeslib.as_array(res.diag, shape=(p,)).copy(),
+        "jtj": np.tril(np.ctypeslib.as_array(res.jtj, shape=(p, p)).copy()),
     }
     if ci[1]:
         out["partrace"] = np.ctypeslib.as_array(res.partrace, shape=(p, maxiter + 1)).copy().T[: res.niter + 1]

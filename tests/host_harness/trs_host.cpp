@@ -130,3 +130,95 @@ long trs_host_fit_lanes(const trs_host_params *hp, const double *start, packet_c
     return n;
 }
 }
+
+// ---- multi-start control logic (gslnls_b200/csrc/mstart.hpp) on the host ------------------------------
+// The evaluator runs every candidate of a batch through the one-lane host build of the trust-region core
+// (the arithmetic of the device's trs_step_batch), packets supplied by the caller's callback.
+#include "../../gslnls_b200/csrc/mstart.hpp"
+
+namespace {
+struct HostBatchEvaluator {
+    trs::Params P;
+    packet_cb cb;
+    void *ctx;
+    void operator()(const std::vector<double> &starts, int S, int iters,
+                    std::vector<gslnls::mstart::BatchResult> &out)
+    {
+        const int p = P.p;
+        trs::Params Q = P;
+        Q.maxiter = iters;
+        Q.batch_iters = iters;
+        Q.trace = 0;
+        Q.gtol = 1.0e-3;
+        out.assign(S, gslnls::mstart::BatchResult());
+        std::vector<double> state(trs::state_doubles(p)), req(trs::request_doubles(p)), pk(trs::packet_doubles(p) + 2);
+        std::vector<double> jtj(p * p), work(p * p);
+        typedef trs::Solver<128, trs::SingleLane> S1;
+        std::unique_ptr<S1> solver(new S1(Q, trs::SingleLane(), jtj.data(), work.data()));
+        for (int c = 0; c < S; ++c) {
+            trs::state_reset(state.data(), req.data(), starts.data() + (size_t)c * p, p);
+            long guard = 0;
+            while ((int)state[trs::S_PHASE] != trs::PH_DONE && guard++ < 100000) {
+                const int mode = (int)req[0];
+                if (mode == trs::MODE_IDLE || cb(ctx, mode, req.data() + 1, req.data() + 1 + p, pk.data()))
+                    break;
+                solver->advance(state.data(), pk.data(), req.data(), nullptr, nullptr, nullptr);
+            }
+            gslnls::mstart::BatchResult &b = out[c];
+            const double *v = state.data() + trs::S_COUNT;
+            b.par.assign(v, v + p);
+            b.diag.assign(v + 3 * p, v + 4 * p);
+            b.ssr = state[trs::S_CHISQ1];
+            b.ssr_prev = state[trs::S_CHISQ0];
+            b.ssr_start = state[trs::S_CHISQ_INIT];
+            b.logdet_start = state[trs::S_LOGDET0];
+            b.logdet_end = state[trs::S_LOGDET1];
+            b.status = (int)state[trs::S_STATUS];
+        }
+    }
+};
+} // namespace
+
+extern "C" {
+// out: [p par | 2p range | ssr ssrconv nsp nwsp mstarts status searches]
+int trs_host_multistart(const trs_host_params *hp, const double *range, const int *has_range, const int *mstart_int,
+                        const double *mstart_dbl, packet_cb cb, void *ctx, double *out)
+{
+    HostBatchEvaluator ev;
+    trs::Params &P = ev.P;
+    P.p = hp->p; P.maxiter = hp->maxiter; P.trs = hp->trs; P.scale = hp->scale; P.trace = 0;
+    P.batch_iters = hp->batch_iters; P.cg_maxit = hp->cg_maxit; P.factor_up = hp->factor_up;
+    P.factor_down = hp->factor_down; P.avmax = hp->avmax; P.h_df = hp->h_df; P.h_fvv = hp->h_fvv;
+    P.xtol = hp->xtol; P.ftol = hp->ftol; P.gtol = hp->gtol; P.cg_tol = hp->cg_tol;
+    ev.cb = cb;
+    ev.ctx = ctx;
+    gslnls::mstart::Control c;
+    c.n = mstart_int[0]; c.p = mstart_int[1]; c.q = mstart_int[2]; c.s = mstart_int[3];
+    c.niter = mstart_int[4]; c.max = mstart_int[5]; c.minsp = mstart_int[6];
+    c.r = mstart_dbl[0]; c.tol = mstart_dbl[1];
+    gslnls::mstart::Driver<HostBatchEvaluator> drv(P.p, c, range, has_range, P.xtol, P.ftol, ev);
+    const gslnls::mstart::Outcome o = drv.run();
+    const int p = P.p;
+    for (int k = 0; k < p; ++k)
+        out[k] = o.par[k];
+    for (int k = 0; k < 2 * p; ++k)
+        out[p + k] = o.range[k];
+    double *s = out + 3 * p;
+    s[0] = o.ssr; s[1] = o.ssrconv; s[2] = o.nsp; s[3] = o.nwsp; s[4] = o.mstarts; s[5] = o.status; s[6] = (double)o.searches;
+    return 0;
+}
+
+int trs_host_qrng(int dim, int count, double *out)
+{
+    if (dim < 41) {
+        gslnls::mstart::Sobol g(dim);
+        for (int i = 0; i < count; ++i)
+            g.next(out + (size_t)i * dim);
+    } else {
+        gslnls::mstart::Halton g(dim);
+        for (int i = 0; i < count; ++i)
+            g.next(out + (size_t)i * dim);
+    }
+    return 0;
+}
+}

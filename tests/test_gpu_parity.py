@@ -612,3 +612,52 @@ def test_upload_from_pageable_memory_is_exact_and_fast(G):
     assert np.allclose(J[:, 0], np.exp(-x), rtol=1e-14)   # the uploaded x column, through the model
     assert dt < 5.0
     pb.close()
+
+
+# ---------------------------------------------------------------- multi-start
+def test_multistart_boxbod_madsen_on_gpu(G, nist_problems):
+    """gslnls_problem_multistart: control logic of gsl_multistart_driver over the batched kernels, against the
+    oracle's restatement on the reference's fixtures (inst/unit_tests/unit_tests_gslnls.R:137-176)"""
+    from oracle import mstart as OM
+    pr = nist_problems["BoxBOD"]
+    data = {k: np.array(v) for k, v in pr["data"].items()}
+    rhs = O.split_formula(pr["formula"])[1]
+    rows = O.sympy_rows(rhs, pr["param_names"], {"x": data["x"]})
+    m = G.Model(rhs, pr["param_names"], ["x"], jac=True)
+    pb = G.Problem(m, data["y"].size).upload([data["x"]], data["y"])
+    ctl = dict(mstart_n=5, mstart_q=1, mstart_r=1.1)
+    for rng, has in (([[200.0, 250.0], [0.0, 1.0]], [[1, 1], [1, 1]]),
+                     ([[-0.1, 0.75], [0.0, 1.0]], [[0, 0], [1, 1]])):
+        got = pb.multistart(rng, has, control=ctl)
+        ref = OM.multistart(rows, data["y"], rng, has, mstart_n=5, mstart_q=1,
+                            mstart_r=1.1 * (10 if not np.all(has) else 1))
+        assert got["status"] == ref["status"] and got["mstarts"] == ref["mstarts"], (got, ref)
+        assert got["nsp"] == ref["nsp"] and np.allclose(got["par"], ref["par"], rtol=1e-6)
+        fit = pb.fit(got["par"])
+        assert fit["conv"] == 0 and np.max(np.abs(fit["par"] / np.array(pr["target"]) - 1)) < 1e-6
+    pb.close()
+    # the high-level call: ranges in `start` trigger the search, the final fit starts from its optimum
+    obj = G.gsl_nls_large(pr["formula"], data=data, start={"b1": (200, 250), "b2": (0, 1)}, jac=True, control=ctl)
+    assert obj.mstart["nsp"] >= 1 and obj.convInfo["isConv"]
+    assert np.max(np.abs(np.array(list(obj.coef().values())) / np.array(pr["target"]) - 1)) < 1e-6
+    obj = G.gsl_nls_large(pr["formula"], data=data, start={"b1": None, "b2": (0, 1)}, jac=True, control=ctl)
+    assert np.max(np.abs(np.array(list(obj.coef().values())) / np.array(pr["target"]) - 1)) < 1e-6
+
+
+def test_multistart_config5_shape_finds_the_global_minimum(G):
+    """BASELINE configs[4] as a search: 8192 start points per major iteration batched per kernel, exponential
+    mixture with known truth (3, 0.5, 2, 3); the search must end on the global minimiser (or its label swap)"""
+    import bench
+    x, y = bench.mstart_problem()
+    m = G.Model("A1*exp(-l1*x)+A2*exp(-l2*x)", ["A1", "l1", "A2", "l2"], ["x"], jac=True)
+    pb = G.Problem(m, x.size).upload([x], y)
+    got = pb.multistart([[0.0, 10.0]] * 4, control=dict(mstart_n=8192, mstart_q=819, mstart_maxstart=8))
+    fit = pb.fit(got["par"])
+    assert fit["conv"] == 0
+    par = fit["par"]
+    if par[1] > par[3]:
+        par = par[[2, 3, 0, 1]]
+    assert np.allclose(par, [3.0, 0.5, 2.0, 3.0], rtol=0.05)
+    assert fit["ssr"] < 1.02 * np.sum((3 * np.exp(-0.5 * x) + 2 * np.exp(-3 * x) - y) ** 2)
+    assert got["searches"] >= 8192
+    pb.close()

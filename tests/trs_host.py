@@ -107,3 +107,41 @@ def fit(provider, start, algorithm="lm", maxiter=100, scale="more", trace=True, 
     out["ssrtrace"] = ssrtrace[: nit + 1].copy()
     out["condtrace"] = condtrace[: nit + 1].copy()
     return out
+
+
+def multistart(provider, start_range, has_range, algorithm="lm", mstart_n=30, mstart_p=5, mstart_q=None, mstart_r=4.0,
+               mstart_s=2, mstart_tol=0.25, mstart_maxiter=10, mstart_maxstart=250, mstart_minsp=1, n=1000):
+    """the product's multi-start control logic (gslnls_b200/csrc/mstart.hpp) over the host build of the
+    trust-region core; packets for every candidate come from `provider`"""
+    from oracle.oracle import SCALE, SQRT_EPS, TRS
+    L = lib()
+    rng = np.ascontiguousarray(start_range, dtype=float).reshape(-1)
+    has = np.ascontiguousarray(np.asarray(has_range, dtype=np.int32).reshape(-1))
+    p = rng.size // 2
+    hp = HostParams(p, 100, TRS[algorithm], SCALE["more"], 0, 0, n, 2.0, 3.0, 0.75, SQRT_EPS, 0.02, SQRT_EPS,
+                    SQRT_EPS, SQRT_EPS, 1e-6)
+    npk = p * (p + 1) // 2 + p + 2
+
+    def cb(ctx, mode, th, v, out):
+        theta = np.ctypeslib.as_array(th, shape=(p,)).copy()
+        vel = np.ctypeslib.as_array(v, shape=(p,)).copy()
+        pk = provider(mode, theta, vel)
+        np.ctypeslib.as_array(out, shape=(npk,))[:] = 0.0
+        np.ctypeslib.as_array(out, shape=(npk,))[: pk.size] = pk
+        return 0
+    mi = np.array([mstart_n, mstart_p, mstart_q if mstart_q is not None else mstart_n // 10, mstart_s, mstart_maxiter,
+                   mstart_maxstart, mstart_minsp], dtype=np.int32)
+    md = np.array([mstart_r, mstart_tol], dtype=float)
+    out = np.zeros(3 * p + 7)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))  # noqa: E731
+    L.trs_host_multistart(C.byref(hp), dp(rng), ip(has), ip(mi), dp(md), _CB(cb), None, dp(out))
+    s = out[3 * p:]
+    return {"par": out[:p].copy(), "range": out[p:3 * p].reshape(p, 2).copy(), "ssr": s[0], "ssrconv": s[1],
+            "nsp": int(s[2]), "nwsp": int(s[3]), "mstarts": int(s[4]), "status": int(s[5]), "searches": int(s[6])}
+
+
+def qrng(dim, count):
+    out = np.zeros((count, dim))
+    lib().trs_host_qrng(dim, count, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
