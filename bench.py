@@ -323,19 +323,21 @@ def run_fit_config(args):
     start = wl.start
     host_us = [0.0, 0.0, 0.0, 0]
 
+    packed = pack_control(ctrl, wl.algorithm, False) + (np.ascontiguousarray(start, dtype=np.float64),)
+
     def run_steps(k):
         """exactly k trial steps as back-to-back fits; returns (outer iterations, fits, last complete result)"""
         left, iters, fits, last, complete = k, 0, 0, None, None
         while left > 0:
             t0 = time.perf_counter()
-            pb.fit_begin(start, algorithm=wl.algorithm, control=ctrl)
+            pb.fit_begin(start, packed=packed)
             t1 = time.perf_counter()
             done, run = False, 0
             while not done and run < left:
                 done, r, _ = pb.fit_run(left - run)
                 run += r
             t2 = time.perf_counter()
-            last = pb.fit_end()
+            last = pb.fit_end(light=True)
             t3 = time.perf_counter()
             host_us[0] += (t1 - t0) * 1e6
             host_us[1] += (t2 - t1) * 1e6

@@ -18,6 +18,8 @@
 #define NLS_CH_PASS_SEEN 640  /* u64: sequence number of the latest pass kernel that has STARTED running (K1 ->
                                  server): the start-of-fit handshake that proves pass and server kernels execute
                                  concurrently (they do not under ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING) */
+#define NLS_CH_CTA_COUNT 768  /* u64: partial packets deposited by the CTAs of the persistent pass kernel since the
+                                 fit began (K1 -> server): pass j of the fit is complete at j x gridDim.x */
 #define NLS_CH_GONE_BUMP (1ull << 40) /* added to REQ_SEQ by a server that gives up: every queued pass falls through idle */
 #define NLS_CH_FLAGS 1024     /* u64 x NLS_MAX_RANKS, 128 B apart: latest sequence deposited by rank r */
 #define NLS_CH_DATA 2048      /* double [2 parities][NLS_MAX_RANKS][NLS_CH_MAXPK]               */
@@ -46,8 +48,11 @@ struct NlsPassParams {
     int pad_;
     int *prof_flag;                   // benchmark hook: set to 1 by a launch that really streamed (not idle)
     unsigned long long watchdog_ns;   // server mode: longest in-kernel wait for a request (GSLNLS_WATCHDOG_S)
+    int server_reduce;                // persistent kernel: 1 = the CTAs only deposit partials and count themselves in
+                                      // on NLS_CH_CTA_COUNT; the resident server sums them (no last-CTA stage)
+    int pad3_;
     int max_passes;                   // persistent kernel: leave after this many passes even if the fit goes on
-    int pad2_;
+    int l2_ahead;                     // persistent kernel: tiles per CTA requested into L2 ahead of the ring
     volatile int *host_passes;        // persistent kernel: passes executed, written at exit (mapped host memory) or nullptr
     unsigned long long *trace;        // developer hook: [gridDim.x][8] globaltimer stamps of each CTA's phases, or nullptr
     long long keep_rows;              // rows [0, keep_rows) of every column are loaded with an L2 evict_last policy,

@@ -925,6 +925,10 @@ static __device__ __forceinline__ void nls_cons_sync()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(NLS_NCONS) : "memory");
 }
+static __device__ __forceinline__ void nls_l2_prefetch(const double *src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 static __device__ __forceinline__ bool nls_bar_try(unsigned long long *bar, unsigned parity)
 {
     unsigned ok;
@@ -1025,9 +1029,28 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(c
         if (lane == 0 && my_tiles > 0) {
             const NlsPolicy PL = nls_policy(prm.keep_rows);
             unsigned long long g = 0ull; // tiles issued since the kernel started
+            // L2 run-ahead: beyond the ring, the next prm.l2_ahead tiles of this CTA are requested into L2.
+            // Inside a pass that only moves HBM reads a few microseconds earlier; between passes -- while
+            // the consumers reduce, the packet travels and the server steps, 9 us with the ring already full
+            // -- it keeps HBM busy: 8 tiles x 36 KB x 147 SMs = 43 MB of the next pass are L2 hits.
+            unsigned long long pf = NLS_STAGES; // tiles covered so far (the ring itself needs no prefetch)
+            long long pfi = NLS_STAGES % my_tiles;
             bool stop = false;
             while (!stop) {
                 for (long long i = 0; i < my_tiles && !stop; ++i) {
+                    while (pf < g + NLS_STAGES + (unsigned long long)prm.l2_ahead) {
+                        const long long po = ((long long)blockIdx.x + pfi * gridDim.x) * NLS_TILE;
+#pragma unroll
+                        for (int k = 0; k < GSLNLS_NVAR; ++k)
+                            nls_l2_prefetch(prm.vars[k] + po, NLS_TILE * 8u);
+                        nls_l2_prefetch(prm.y + po, NLS_TILE * 8u);
+#if NLS_HAS_W
+                        nls_l2_prefetch(prm.w + po, NLS_TILE * 8u);
+#endif
+                        ++pf;
+                        if (++pfi == my_tiles)
+                            pfi = 0;
+                    }
                     const int s = (int)(g % NLS_STAGES);
                     const unsigned ph = (unsigned)(((g / NLS_STAGES) & 1ull) ^ 1ull);
                     while (!nls_bar_try(empty + s, ph)) {
@@ -1140,6 +1163,31 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(c
             part[e] = s;
         }
         nls_trace(prm, 4);
+        if (prm.server_reduce) {
+            // ---- grid: the resident server sums the CTA partials itself.  A CTA only counts itself in: no
+            // ticket round trip, no last-CTA stage, no second hop for the packet (3.3 us -> ~1 us measured) ----
+#if NLS_PK <= 32
+            if (warp == 0) { // every partial entry was written by this warp
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(prm.channel + NLS_CH_CTA_COUNT) : "memory");
+                    if (prm.prof_flag && blockIdx.x == 0)
+                        *prm.prof_flag += 1;
+                }
+            }
+#else
+            __threadfence();
+            nls_cons_sync();
+            if (threadIdx.x == 0) {
+                asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(prm.channel + NLS_CH_CTA_COUNT) : "memory");
+                if (prm.prof_flag && blockIdx.x == 0)
+                    *prm.prof_flag += 1;
+            }
+#endif
+            ++done_passes;
+            continue;
+        }
         // ---- grid: the last CTA to arrive sums the CTA partials in CTA order and hands the packet on ----
         __threadfence();
         nls_cons_sync();

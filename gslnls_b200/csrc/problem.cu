@@ -97,6 +97,7 @@ struct gslnls_problem {
     // resident-server mode: the trust-region warp lives on its own stream for the whole fit and the
     // pass launches are sequenced on the device through the channel (nls_abi.h NLS_CH_*)
     bool allow_server = true, server_on = false;
+    bool server_reduce = true; // persistent mode: the server sums the CTA partials (GSLNLS_SERVER_REDUCE=0: last CTA does)
     bool allow_persistent = true, persistent_on = false; // one pass-kernel launch per fit (GSLNLS_PERSISTENT=0 disables)
     bool server_pending = false; // fit_begin chose the server; it is launched with the first pass (fit_run)
     unsigned long long handshake_ns = 100000000ull; // start-of-fit handshake period (GSLNLS_HANDSHAKE_MS)
@@ -248,6 +249,12 @@ static double default_keep_mb(double pass_bytes)
 
 static void fill_pass_params(gslnls_problem *pb, int ncand, int force_mode, NlsPassParams &prm);
 
+// persistent mode: does the resident server sum the CTA partials itself?  (its lanes hold a 16 x 5 block each)
+static bool use_server_reduce(const gslnls_problem *pb)
+{
+    return pb->persistent_on && pb->server_reduce && pb->grid_x <= 160 && pb->pk_stride - 1 <= 16;
+}
+
 static int launch_pass(gslnls_problem *pb, int ncand, int force_mode)
 {
     NlsPassParams prm;
@@ -277,19 +284,22 @@ static int launch_persistent(gslnls_problem *pb, int max_passes)
     NlsPassParams prm;
     fill_pass_params(pb, 1, 0, prm);
     prm.max_passes = max_passes;
+    prm.server_reduce = use_server_reduce(pb) ? 1 : 0;
+    static const int l2_ahead = std::getenv("GSLNLS_L2_AHEAD") ? std::atoi(std::getenv("GSLNLS_L2_AHEAD")) : 8;
+    prm.l2_ahead = std::max(0, l2_ahead);
     const bool timed = pb->profile && pb->prof_used + 2 <= pb->prof_ev.size();
     if (timed)
         prm.prof_flag = pb->d_prof_flags + pb->prof_used / 2;
     void *args[] = {&prm};
     if (timed)
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used], pb->stream));
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)pb->var->persistent, dim3(pb->grid_x, 1, 1),
-                                                dim3(pb->vkey.block, 1, 1), args, pb->var->pass_smem, pb->stream);
-    if (e != cudaSuccess) { // every CTA of this grid must be resident at once; plain launch relies on the grid size
-        cudaGetLastError();
-        CK(cudaLaunchKernel((const void *)pb->var->persistent, dim3(pb->grid_x, 1, 1), dim3(pb->vkey.block, 1, 1), args,
-                            pb->var->pass_smem, pb->stream));
-    }
+    // Every CTA of this grid has to be resident at once (the last CTA to arrive reduces, all wait for the next
+    // request): the grid is sized to one CTA per SM, which the occupancy query of prepare() guarantees to fit.
+    // A cooperative launch would assert the same, but the driver does not run a cooperative grid next to the
+    // resident trust-region kernel (measured on B200: it waits for the server to leave -- the start-of-fit
+    // handshake then times out and the fit falls back to launch-ordered stepping).
+    CK(cudaLaunchKernel((const void *)pb->var->persistent, dim3(pb->grid_x, 1, 1), dim3(pb->vkey.block, 1, 1), args,
+                        pb->var->pass_smem, pb->stream));
     if (timed) {
         CK(cudaEventRecord(pb->prof_ev[pb->prof_used + 1], pb->stream));
         pb->prof_used += 2;
@@ -391,11 +401,17 @@ static int wait_server_caught_up(gslnls_problem *pb)
         return GSLNLS_SUCCESS; // never launched: nothing to catch up with
     const auto t0 = std::chrono::steady_clock::now();
     const double limit_s = 1e-9 * (double)pb->watchdog_ns + 1.0;
+    const bool counted = use_server_reduce(pb); // the server, not the pass kernel, advances PASS_CTR
     while (pb->h_flags[0] == 0) {
         CK(cudaMemcpyAsync(&w[0], ch + NLS_CH_REQ_SEQ, sizeof(w[0]), cudaMemcpyDeviceToHost, pb->ctl_stream));
-        CK(cudaMemcpyAsync(&w[1], ch + NLS_CH_PASS_CTR, sizeof(w[1]), cudaMemcpyDeviceToHost, pb->ctl_stream));
+        CK(cudaMemcpyAsync(&w[1], ch + (counted ? NLS_CH_CTA_COUNT : NLS_CH_PASS_CTR), sizeof(w[1]),
+                           cudaMemcpyDeviceToHost, pb->ctl_stream));
+        if (counted)
+            CK(cudaMemcpyAsync(&w[2], ch + NLS_CH_FIT_SEQ0, sizeof(w[2]), cudaMemcpyDeviceToHost, pb->ctl_stream));
         CK(cudaStreamSynchronize(pb->ctl_stream));
-        if (w[0] >= w[1] + 1ull)
+        // passes whose partials are all in: the request that follows the last of them must be out
+        const unsigned long long need = counted ? w[2] + w[1] / (unsigned long long)std::max(pb->grid_x, 1) : w[1] + 1ull;
+        if (w[0] >= need)
             return GSLNLS_SUCCESS;
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit_s) {
             set_error("the resident trust-region server did not digest the last pass within the watchdog period");
@@ -573,7 +589,7 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     CK(cudaEventCreate(&pb->ev1));
     CK(cudaEventCreate(&pb->ev2));
     CK(cudaEventCreate(&pb->ev3));
-    CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 4));
+    CK(cudaMallocHost(&pb->h_ndone, sizeof(int) * 8));
     if (const char *c = std::getenv("GSLNLS_CHUNK"))
         pb->chunk = std::max(1, std::atoi(c));
     if (const char *c = std::getenv("GSLNLS_PROF_STRIDE"))
@@ -582,6 +598,8 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
         pb->allow_server = std::atoi(c) != 0;
     else if (serialising_environment())
         pb->allow_server = false;
+    if (const char *c = std::getenv("GSLNLS_SERVER_REDUCE"))
+        pb->server_reduce = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_PERSISTENT"))
         pb->allow_persistent = std::atoi(c) != 0;
     if (const char *c = std::getenv("GSLNLS_WATCHDOG_S"))
@@ -742,9 +760,12 @@ static int prepare(gslnls_problem *pb, int ncand, int ntrace, bool batch, bool r
     if (rc)
         return rc;
     pb->persistent_on = persistent && pb->vkey.tiled == 2 && pb->var->persistent != nullptr;
-    // the TMA-ring CTA (416 threads, ~150 KB of shared memory, one per SM) leaves room for the resident
-    // trust-region warp on the same SM; the LDG variants fill the register file and give it a slot of its own
-    pb->grid_x = pick_grid(pb, ncand, reserve_slot && !pb->persistent_on);
+    // The resident trust-region warp gets an SM slot of its own.  Registers and shared memory of a TMA-ring CTA
+    // would leave room for it on the same SM, but an SM that is running the server (tiny shared-memory carve-out)
+    // cannot be re-configured for a 150 KB CTA until it drains, which the server never does: a 148-CTA
+    // persistent grid then waits forever for its last CTA (measured: watchdog).  The pass is HBM-bound; 147
+    // streaming SMs lose nothing.
+    pb->grid_x = pick_grid(pb, ncand, reserve_slot);
     rc = ensure_workspace(pb, ncand, pb->grid_x, ntrace);
     return rc;
 }
@@ -937,24 +958,26 @@ static int fit_setup(gslnls_problem *pb)
     }
     const int p = pb->p;
     pb->ncand = 1;
-    CK(cudaMemcpyAsync(pb->d_starts, pb->start.data(), sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
     if (ntrace) {
         CK(cudaMemsetAsync(pb->d_partrace, 0, sizeof(double) * (size_t)ntrace * p, pb->stream));
         CK(cudaMemsetAsync(pb->d_ssrtrace, 0, sizeof(double) * ntrace, pb->stream));
         CK(cudaMemsetAsync(pb->d_condtrace, 0, sizeof(double) * ntrace, pb->stream));
     }
-    CK(trs_launch_reset(pb->d_state, pb->state_stride, pb->d_req, pb->req_stride, pb->d_starts, p, 1, pb->d_ndone,
-                        pb->stream));
-    ++pb->launches;
     if (use_server) {
-        // the pass launches that follow on the main stream find their request through the channel, not
-        // through stream order; the server kernel itself goes out with the first pass (fit_run)
-        CK(trs_launch_channel_begin(channel_of(pb), pb->stream));
+        // one launch writes the records (start values travel as kernel arguments) and opens the channel; the
+        // pass launches that follow on the main stream find their request through the channel, not through
+        // stream order; the server kernel itself goes out with the first pass (fit_run)
+        CK(trs_launch_fit_begin(pb->d_state, pb->d_req, pb->start.data(), p, pb->d_ndone, channel_of(pb), pb->stream));
         CK(cudaEventRecord(pb->ev_reset, pb->stream));
         ++pb->launches;
         pb->h_flags[0] = 0;
         pb->server_on = true;
         pb->server_pending = true;
+    } else {
+        CK(cudaMemcpyAsync(pb->d_starts, pb->start.data(), sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+        CK(trs_launch_reset(pb->d_state, pb->state_stride, pb->d_req, pb->req_stride, pb->d_starts, p, 1, pb->d_ndone,
+                            pb->stream));
+        ++pb->launches;
     }
     pb->active = true;
     pb->passes = 0;
@@ -970,10 +993,21 @@ static int launch_pending_server(gslnls_problem *pb)
     const bool sharded = pb->comm && pb->comm->nranks > 1;
     const bool tr = pb->P.trace != 0;
     CK(cudaStreamWaitEvent(pb->srv_stream, pb->ev_reset, 0));
+    TrsLinks links;
+    if (use_server_reduce(pb)) {
+        links.partials = pb->d_partials;
+        links.nctas = pb->grid_x;
+        links.pk_stride = pb->pk_stride;
+        if (sharded) {
+            links.rank = pb->comm->rank;
+            for (int r = 0; r < pb->comm->nranks; ++r)
+                links.peer[r] = pb->comm->peer_channel[r];
+        }
+    }
     CK(trs_launch_server(pb->P, channel_of(pb), sharded ? pb->comm->nranks : 1, pb->pk_stride, pb->d_state,
                          pb->d_packet, pb->d_req, tr ? pb->d_partrace : nullptr, tr ? pb->d_ssrtrace : nullptr,
                          tr ? pb->d_condtrace : nullptr, pb->d_ndone, pb->d_flags, pb->d_hstate, pb->watchdog_ns,
-                         pb->handshake_ns, pb->srv_stream));
+                         pb->handshake_ns, links, pb->srv_stream));
     ++pb->launches;
     pb->server_pending = false;
     return GSLNLS_SUCCESS;

