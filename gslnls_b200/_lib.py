@@ -21,8 +21,13 @@ class Result(C.Structure):
         ("info", C.c_int), ("status", C.c_char_p), ("algorithm", C.c_char_p), ("neval", C.c_int64 * 4),
         ("npass", C.c_int64), ("ntrace", C.c_int), ("partrace", c_double_p), ("ssrtrace", c_double_p),
         ("condtrace", c_double_p), ("resid", c_double_p), ("grad", c_double_p), ("n_local", C.c_int64),
-        ("jtj", c_double_p), ("grad_vec", c_double_p),
+        ("jtj", c_double_p), ("grad_vec", c_double_p), ("x_final", c_double_p),
     ]
+
+
+class IrlsInfo(C.Structure):
+    """struct gslnls_irls_info"""
+    _fields_ = [("sigma", C.c_double), ("delta", C.c_double), ("niter", C.c_int), ("status", C.c_int)]
 
 
 class MstartResult(C.Structure):
@@ -81,6 +86,10 @@ SIGNATURES = {
     "gslnls_problem_channel_stats": (C.c_int, [C.c_void_p, C.c_int, c_double_p, c_double_p, C.POINTER(C.c_int64)]),
     "gslnls_problem_fit_batch": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int_p, c_double_p, c_double_p,
                                            c_double_p, c_double_p, c_int_p, c_int_p]),
+    "gslnls_problem_fit_irls": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, C.c_int, c_double_p, C.c_int,
+                                          C.c_double, C.POINTER(Result), C.POINTER(IrlsInfo)]),
+    "gslnls_problem_get_weights": (C.c_int, [C.c_void_p, c_double_p]),
+    "gslnls_problem_median_abs_resid": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
     "gslnls_problem_multistart": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_int_p, c_double_p, c_int_p, c_double_p,
                                             C.POINTER(MstartResult)]),
     "gslnls_mstart_result_free": (None, [C.POINTER(MstartResult)]),

@@ -34,6 +34,7 @@ struct Variant {
     std::string log;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t pass = nullptr, materialise = nullptr;
+    cudaKernel_t irls_hist = nullptr, irls_above = nullptr, irls_weights = nullptr, irls_scale = nullptr;
     cudaKernel_t persistent = nullptr; // nls_pass_persistent (TMA-ring variants only): one launch per fit
     bool loaded = false;
     size_t pass_smem = 0; // dynamic shared memory of one nls_pass CTA (tiled variant)

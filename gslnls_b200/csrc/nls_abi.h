@@ -74,3 +74,31 @@ struct NlsMaterialiseParams {
     double *grad;         // n*p column-major or nullptr
     double h_df;
 };
+
+// IRLS support kernels (robust losses, src/nls_irls.c): unweighted residuals r_i = fn(theta)_i - y_i are
+// recomputed from the resident columns in every pass -- nothing of size n besides the weights column is written
+struct NlsIrlsParams {
+    const double *vars[NLS_MAX_VARS];
+    const double *y;
+    long long n;
+    const double *theta;          // p doubles (device)
+    // radix select of the k-th smallest |r| (bit pattern of a non-negative double is monotone)
+    unsigned long long prefix;    // bits above `shift + 8` already fixed
+    int shift;                    // current digit: bits [shift, shift + 8)
+    int pad_;
+    unsigned long long *hist;     // [256] counts of the current digit among the keys matching the prefix
+    unsigned long long pivot;     // count / min pass: key of the order statistic found
+    unsigned long long *cnt_min;  // [2]: #{key <= pivot}, min{key > pivot}
+    // weights pass
+    double sigma;                 // scale: 1.4826 median |r|
+    int loss;                     // 1 huber 2 barron 3 bisquare 4 welsh 5 optimal 6 hampel 7 ggw 8 lqq
+    int pad2_;
+    double cc[3];                 // tuning constants of the loss (R/nls_rho.R)
+    double *wout;                 // n: max(psi(r/sigma) / (r/sigma), eps), before normalisation
+    double *psi, *psip;           // n each or nullptr
+    double *partial;              // [gridDim.x] per-CTA sums of wout (summed in CTA order on the host)
+    // scale pass: wout[i] *= scale * (userw ? userw[i] : 1)
+    double scale;
+    const double *userw;
+    double h_df;
+};

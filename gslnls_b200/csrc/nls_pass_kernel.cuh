@@ -1290,3 +1290,226 @@ extern "C" __global__ void __launch_bounds__(256) nls_materialise(const NlsMater
         }
     }
 }
+
+// ------------------------------------------------------------------------------------ IRLS (robust losses)
+// The reference's iteratively reweighted least squares, src/nls_irls.c:412-546: after every weighted fit the
+// unweighted residuals give the scale sigma = 1.4826 median |r| and the weights w_i = psi(r_i / sigma) /
+// (r_i / sigma) of the chosen loss.  psi / psi' below restate src/nls_irls.c:10-330 (themselves credited to
+// robustbase's lmrob.c).  The median comes from a radix select over the bit patterns of |r_i|, 8 bits per
+// pass, each pass re-deriving r_i from the resident columns (16 bytes per observation, nothing stored).
+static __device__ __forceinline__ double nls_irls_resid(const NlsThread &T, const NlsIrlsParams &prm, long long i)
+{
+    double xa[NLS_NV];
+#pragma unroll
+    for (int k = 0; k < GSLNLS_NVAR; ++k)
+        xa[k] = prm.vars[k][i];
+    const double f = nls_model_f(T.th, xa);
+    return nls_finite(f) ? f - prm.y[i] : NLS_INF; // src/nls_large.c:464-467
+}
+static __device__ __forceinline__ void nls_irls_theta(const NlsIrlsParams &prm, NlsThread &T)
+{
+#pragma unroll
+    for (int j = 0; j < NLS_P; ++j) {
+        T.th[j] = prm.theta[j];
+        T.vv[j] = 0.0;
+        T.dl[j] = T.idl[j] = 0.0;
+    }
+    T.h_fvv = 0.0;
+}
+
+extern "C" __global__ void __launch_bounds__(256) nls_irls_hist(const NlsIrlsParams prm)
+{
+    __shared__ unsigned int sh[256];
+    nls_exp_init();
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    NlsThread T;
+    nls_irls_theta(prm, T);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(nls_irls_resid(T, prm, i)));
+        if (prm.shift >= 56 || (key >> (prm.shift + 8)) == prm.prefix)
+            atomicAdd(&sh[(unsigned)(key >> prm.shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x])
+        atomicAdd(prm.hist + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+}
+
+// #{|r| <= pivot} and min{|r| > pivot}: the upper middle element of an even-length median
+extern "C" __global__ void __launch_bounds__(256) nls_irls_above(const NlsIrlsParams prm)
+{
+    nls_exp_init();
+    NlsThread T;
+    nls_irls_theta(prm, T);
+    unsigned long long cnt = 0ull, mn = ~0ull;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(nls_irls_resid(T, prm, i)));
+        if (key <= prm.pivot)
+            ++cnt;
+        else if (key < mn)
+            mn = key;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        const unsigned long long m2 = __shfl_down_sync(0xffffffffu, mn, o);
+        mn = m2 < mn ? m2 : mn;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(prm.cnt_min, cnt);
+        atomicMin(prm.cnt_min + 1, mn);
+    }
+}
+
+// ---- psi = rho' and psi' = rho'' of the eight losses (src/nls_irls.c:10-330) ----
+static __device__ double nls_psi(double x, const double *c, int which, double *dpsi)
+{
+    const double ax = fabs(x);
+    switch (which) {
+    default:
+    case 1: { // huber
+        *dpsi = ax >= c[0] ? 0.0 : 1.0;
+        return x <= -c[0] ? -c[0] : (x < c[0] ? x : c[0]);
+    }
+    case 2: { // barron
+        const double alpha = c[0], c2 = c[1] * c[1], x2 = x * x, xc2 = x2 / c2;
+        const double se = 1.4901161193847656e-08;
+        if (fabs(alpha - 2.0) < se) {
+            *dpsi = 1.0 / c2;
+            return x / c2;
+        } else if (fabs(alpha) < se) {
+            *dpsi = -2.0 * (x2 - 2.0 * c2) / ((2.0 * c2 + x2) * (2.0 * c2 + x2));
+            return 2.0 * x / (x2 + 2.0 * c2);
+        } else if (alpha > -1e8) {
+            const double denom = x2 - (alpha - 2.0) * c2;
+            *dpsi = (alpha - 2.0) * ((alpha - 2.0) * c2 - (alpha - 1.0) * x2) *
+                    pow(1.0 - x2 / ((alpha - 2.0) * c2), 0.5 * alpha) / (denom * denom);
+            return x / c2 * pow(xc2 / fabs(alpha - 2.0) + 1.0, 0.5 * alpha - 1.0);
+        }
+        *dpsi = exp(-x2 / (2.0 * c2)) * (c2 - x2) / (c2 * c2);
+        return x / c2 * exp(-0.5 * xc2);
+    }
+    case 3: { // bisquare
+        if (ax > c[0]) {
+            *dpsi = 0.0;
+            return 0.0;
+        }
+        const double a = x / c[0], u = 1.0 - a * a, a2 = a * a;
+        *dpsi = (1.0 - a2) * (1.0 - 5.0 * a2);
+        return x * u * u;
+    }
+    case 4: { // welsh / Gauss weight
+        const double a = x / c[0];
+        if (fabs(a) > 37.7) {
+            *dpsi = 0.0;
+            return 0.0;
+        }
+        const double e = exp(-(a * a) / 2.0);
+        *dpsi = e * (1.0 - a * a);
+        return x * e;
+    }
+    case 5: { // optimal
+        const double R1 = -1.944, R2 = 1.728, R3 = -0.312, R4 = 0.016;
+        const double ac = x / c[0], aa = fabs(ac);
+        if (aa > 3.0) {
+            *dpsi = 0.0;
+            return 0.0;
+        } else if (aa > 2.0) {
+            const double a2 = ac * ac;
+            *dpsi = R1 + a2 * (3.0 * R2 + a2 * (5.0 * R3 + a2 * 7.0 * R4));
+            const double v = c[0] * ((((R4 * a2 + R3) * a2 + R2) * a2 + R1) * ac);
+            return ac > 0.0 ? (v > 0.0 ? v : 0.0) : -fabs(v);
+        }
+        *dpsi = 1.0;
+        return x;
+    }
+    case 6: { // hampel
+        const double a = 1.5 * c[0], b = 3.5 * c[0], r = 8.0 * c[0];
+        const double sx = x < 0.0 ? -1.0 : 1.0;
+        if (ax <= a) {
+            *dpsi = 1.0;
+            return x;
+        } else if (ax <= b) {
+            *dpsi = 0.0;
+            return sx * a;
+        } else if (ax <= r) {
+            *dpsi = a / (b - r);
+            return sx * a * (r - ax) / (r - b);
+        }
+        *dpsi = 0.0;
+        return 0.0;
+    }
+    case 7: { // ggw
+        if (ax < c[2]) {
+            *dpsi = 1.0;
+            return x;
+        }
+        const double ea = -pow(ax - c[2], c[1]) / (2.0 * c[0]);
+        if (ea < -708.4) {
+            *dpsi = 0.0;
+            return 0.0;
+        }
+        *dpsi = exp(ea) * (1.0 - c[1] / (2.0 * c[0]) * ax * pow(ax - c[2], c[1] - 1.0));
+        return x * exp(ea);
+    }
+    case 8: { // lqq
+        if (ax <= c[1]) {
+            *dpsi = 1.0;
+            return x;
+        }
+        const double k01 = c[0] + c[1], sg = x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0);
+        if (ax <= k01) {
+            *dpsi = 1.0 - c[2] / c[0] * (ax - c[1]);
+            return sg * (ax - c[2] * (ax - c[1]) * (ax - c[1]) / c[0] / 2.0);
+        }
+        const double s5 = c[2] - 1.0, s6 = -2.0 * k01 + c[0] * c[2];
+        const double aa = (c[0] * c[2] - 2.0 * k01) / (1.0 - c[2]);
+        *dpsi = ax < k01 + aa ? -(1.0 - c[2]) * ((ax - k01) / aa - 1.0) : 0.0;
+        if (ax < k01 - s6 / s5)
+            return (x > 0.0 ? 1.0 : -1.0) * (-s6 / 2.0 - s5 * s5 / s6 * ((ax - k01) * (ax - k01) / 2.0 + s6 / s5 * (ax - k01)));
+        return 0.0;
+    }
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(256) nls_irls_weights(const NlsIrlsParams prm)
+{
+    __shared__ double sw[8];
+    nls_exp_init();
+    NlsThread T;
+    nls_irls_theta(prm, T);
+    double acc = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride) {
+        const double rs = nls_irls_resid(T, prm, i) / prm.sigma;
+        double dpsi;
+        const double ps = nls_psi(rs, prm.cc, prm.loss, &dpsi);
+        const double q = ps / rs;
+        const double wt = q > 2.2204460492503131e-16 ? q : 2.2204460492503131e-16; // gsl_max(psi / r, eps); 0 / 0 -> eps
+        prm.wout[i] = wt;
+        if (prm.psi)
+            prm.psi[i] = ps;
+        if (prm.psip)
+            prm.psip[i] = dpsi;
+        acc += wt;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0)
+        sw[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w)
+            s += sw[w];
+        prm.partial[blockIdx.x] = s;
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(256) nls_irls_scale(const NlsIrlsParams prm)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride)
+        prm.wout[i] = prm.wout[i] * prm.scale * (prm.userw ? prm.userw[i] : 1.0);
+}

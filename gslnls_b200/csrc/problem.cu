@@ -1220,6 +1220,7 @@ GSLNLS_API int gslnls_problem_fit_end(gslnls_problem *pb, int want_resid_grad, g
         for (int j = i + 1; j < p; ++j)
             out->jtj[i * p + j] = out->jtj[j * p + i];
     out->grad_vec = dup(v + 2 * p, p);
+    out->x_final = dup(v, p);
     out->ssr = S[trs::S_CHISQ1];
     out->ssrtol = S[trs::S_CHISQ0] - S[trs::S_CHISQ1];
     out->chisq_init = S[trs::S_CHISQ_INIT];
@@ -1759,6 +1760,7 @@ GSLNLS_API void gslnls_result_free(gslnls_result *r)
         return;
     std::free(r->par); std::free(r->covar); std::free(r->partrace); std::free(r->ssrtrace);
     std::free(r->condtrace); std::free(r->resid); std::free(r->grad); std::free(r->jtj); std::free(r->grad_vec);
+    std::free(r->x_final);
     std::memset(r, 0, sizeof(*r));
 }
 
@@ -1950,6 +1952,216 @@ GSLNLS_API int gslnls_qrng_points(int dim, int count, double *out)
             g.next(out + (size_t)i * dim);
     }
     return GSLNLS_SUCCESS;
+}
+
+} // extern "C"
+
+// ---- IRLS: robust losses on the large path (src/nls_irls.c:412-546) -------------------------------------
+namespace {
+struct IrlsScratch {
+    unsigned long long *d_hist = nullptr; // [256] + cnt_min [2]
+    double *d_partial = nullptr;
+    double *d_userw = nullptr;
+    double *d_theta = nullptr;
+    ~IrlsScratch()
+    {
+        cudaFree(d_hist); cudaFree(d_partial); cudaFree(d_userw); cudaFree(d_theta);
+    }
+};
+
+void irls_base_params(const gslnls_problem *pb, const double *d_theta, NlsIrlsParams &prm)
+{
+    std::memset(&prm, 0, sizeof(prm));
+    for (int k = 0; k < pb->nvar; ++k)
+        prm.vars[k] = pb->dvars[k];
+    prm.y = pb->dy;
+    prm.n = pb->n;
+    prm.theta = d_theta;
+    prm.h_df = pb->h_df;
+}
+
+// median of |fn(theta) - y| as gsl_median computes it (src/nls_utils.c:162-189): middle element, or the mean
+// of the two middle elements; radix select over the bit patterns, 8 bits per streaming pass
+int irls_median(gslnls_problem *pb, const double *d_theta, IrlsScratch &sc, double *median)
+{
+    const int64_t n = pb->n;
+    if (n == 0) {
+        *median = 0.0;
+        return GSLNLS_SUCCESS;
+    }
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)pb->num_sms * 8);
+    NlsIrlsParams prm;
+    irls_base_params(pb, d_theta, prm);
+    prm.hist = sc.d_hist;
+    prm.cnt_min = sc.d_hist + 256;
+    unsigned long long rank = (unsigned long long)((n - 1) / 2), prefix = 0ull, hist[256];
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        CK(cudaMemsetAsync(sc.d_hist, 0, sizeof(unsigned long long) * 256, pb->stream));
+        prm.prefix = prefix;
+        prm.shift = shift;
+        void *args[] = {&prm};
+        CK(cudaLaunchKernel((const void *)pb->var->irls_hist, dim3(blocks), dim3(256), args, 0, pb->stream));
+        ++pb->launches;
+        CK(cudaMemcpyAsync(hist, sc.d_hist, sizeof(hist), cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        int b = 0;
+        for (; b < 255 && rank >= hist[b]; ++b)
+            rank -= hist[b];
+        prefix = (prefix << 8) | (unsigned long long)b;
+    }
+    double lo;
+    std::memcpy(&lo, &prefix, sizeof(lo));
+    *median = lo;
+    if ((n - 1) / 2 != n / 2) { // even length: the next order statistic as well
+        unsigned long long init[2] = {0ull, ~0ull}, got[2];
+        CK(cudaMemcpyAsync(sc.d_hist + 256, init, sizeof(init), cudaMemcpyHostToDevice, pb->stream));
+        prm.pivot = prefix;
+        void *args[] = {&prm};
+        CK(cudaLaunchKernel((const void *)pb->var->irls_above, dim3(blocks), dim3(256), args, 0, pb->stream));
+        ++pb->launches;
+        CK(cudaMemcpyAsync(got, sc.d_hist + 256, sizeof(got), cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        double hi = lo;
+        if (got[0] <= (unsigned long long)(n / 2)) // fewer than n/2 + 1 elements <= lo: the upper middle is larger
+            std::memcpy(&hi, &got[1], sizeof(hi));
+        *median = (lo + hi) / 2.0;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+int irls_scratch_init(gslnls_problem *pb, IrlsScratch &sc, bool want_userw)
+{
+    CK(cudaMalloc(&sc.d_hist, sizeof(unsigned long long) * 258));
+    CK(cudaMalloc(&sc.d_partial, sizeof(double) * (size_t)pb->num_sms * 8));
+    CK(cudaMalloc(&sc.d_theta, sizeof(double) * pb->p));
+    if (want_userw) {
+        CK(cudaMalloc(&sc.d_userw, sizeof(double) * (size_t)std::max<int64_t>(pb->n, 1)));
+        CK(cudaMemcpyAsync(sc.d_userw, pb->dw, sizeof(double) * (size_t)pb->n, cudaMemcpyDeviceToDevice, pb->stream));
+    }
+    return GSLNLS_SUCCESS;
+}
+} // namespace
+
+extern "C" {
+
+GSLNLS_API int gslnls_problem_median_abs_resid(gslnls_problem *pb, const double *theta, double *median)
+{
+    if (!pb || !theta || !median)
+        return GSLNLS_EINVAL;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    IrlsScratch sc;
+    rc = irls_scratch_init(pb, sc, false);
+    if (rc)
+        return rc;
+    CK(cudaMemcpyAsync(sc.d_theta, theta, sizeof(double) * pb->p, cudaMemcpyHostToDevice, pb->stream));
+    return irls_median(pb, sc.d_theta, sc, median);
+}
+
+GSLNLS_API int gslnls_problem_get_weights(gslnls_problem *pb, double *weights)
+{
+    if (!pb || !weights || !pb->dw)
+        return GSLNLS_EINVAL;
+    CK(cudaSetDevice(pb->device));
+    CK(cudaMemcpyAsync(weights, pb->dw, sizeof(double) * (size_t)pb->n, cudaMemcpyDeviceToHost, pb->stream));
+    CK(cudaStreamSynchronize(pb->stream));
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_problem_fit_irls(gslnls_problem *pb, const double *start, const int *control_int,
+                                       const double *control_dbl, int loss, const double *cc, int irls_maxiter,
+                                       double irls_xtol, gslnls_result *out, gslnls_irls_info *info)
+{
+    if (!pb || !start || !control_int || !control_dbl || !cc || !out || !info || loss < 1 || loss > 8 || irls_maxiter < 1)
+        return GSLNLS_EINVAL;
+    if (!pb->has_w || !pb->dw || pb->bound) {
+        set_error("IRLS needs a problem created with has_weights = 1 and library-owned columns (the weights "
+                  "column is the working vector)");
+        return GSLNLS_EINVAL;
+    }
+    if (pb->comm && pb->comm->nranks > 1) {
+        set_error("IRLS on a sharded problem is not built (the median needs a cross-rank histogram)");
+        return GSLNLS_EINVAL;
+    }
+    std::memset(out, 0, sizeof(*out));
+    info->sigma = 1.0; info->delta = 0.0; info->niter = 0; info->status = GSLNLS_FAILURE;
+    const int p = pb->p;
+    int rc = prepare(pb, 1, 0, false);
+    if (rc)
+        return rc;
+    IrlsScratch sc;
+    rc = irls_scratch_init(pb, sc, true);
+    if (rc)
+        return rc;
+    double *d_work = const_cast<double *>(pb->dw); // library-owned (checked above)
+    std::vector<double> prev(start, start + p), cur(p);
+    const int blocks = (int)std::min<int64_t>(std::max<int64_t>((pb->n + 255) / 256, 1), (int64_t)pb->num_sms * 8);
+    int status = GSLNLS_CONTINUE;
+    for (;;) {
+        info->niter += 1;
+        gslnls_result_free(out);
+        // weighted fit with the current weights; every IRLS iteration restarts from the given start values
+        // (gsl_multifit_nlinear_winit(pars->mpopt, ...), src/nls_irls.c:452-457)
+        status = gslnls_problem_fit(pb, start, control_int, control_dbl, 0, out);
+        if (status >= 1000 || status == GSLNLS_EINVAL)
+            return status;
+        if (status == GSLNLS_EBADFUNC || (status == GSLNLS_ENOPROG && info->niter == 1))
+            return status; // :479-484
+        std::memcpy(cur.data(), out->x_final, sizeof(double) * p);
+        rc = prepare(pb, 1, 0, false); // kernels of the launch-ordered variant (the fit may have switched variant)
+        if (rc)
+            return rc;
+        // sigma = 1.4826 median |unweighted residual| (:494)
+        CK(cudaMemcpyAsync(sc.d_theta, cur.data(), sizeof(double) * p, cudaMemcpyHostToDevice, pb->stream));
+        double med = 0.0;
+        rc = irls_median(pb, sc.d_theta, sc, &med);
+        if (rc)
+            return rc;
+        info->sigma = 1.482602218505602 * med;
+        // w_i = max(psi(r_i / sigma) / (r_i / sigma), eps), normalised to sum n, times the user's weights (:496-515)
+        NlsIrlsParams prm;
+        irls_base_params(pb, sc.d_theta, prm);
+        prm.sigma = info->sigma;
+        prm.loss = loss;
+        prm.cc[0] = cc[0]; prm.cc[1] = cc[1]; prm.cc[2] = cc[2];
+        prm.wout = d_work;
+        prm.partial = sc.d_partial;
+        void *args[] = {&prm};
+        CK(cudaLaunchKernel((const void *)pb->var->irls_weights, dim3(blocks), dim3(256), args, 0, pb->stream));
+        std::vector<double> part(blocks);
+        CK(cudaMemcpyAsync(part.data(), sc.d_partial, sizeof(double) * blocks, cudaMemcpyDeviceToHost, pb->stream));
+        CK(cudaStreamSynchronize(pb->stream));
+        double sum_wts = 0.0;
+        for (double v : part)
+            sum_wts += v; // CTA order: deterministic
+        prm.scale = (double)pb->n / sum_wts;
+        prm.userw = sc.d_userw;
+        CK(cudaLaunchKernel((const void *)pb->var->irls_scale, dim3(blocks), dim3(256), args, 0, pb->stream));
+        pb->launches += 2;
+        // convergence of the parameters (test_delta_irls, :365-384)
+        bool conv = true;
+        info->delta = 0.0;
+        for (int i = 0; i < p; ++i) {
+            const double dxi = std::fabs(prev[i] - cur[i]), rel = dxi / std::fabs(cur[i]);
+            info->delta = std::max(info->delta, dxi);
+            if (!((rel < dxi ? rel : dxi) < irls_xtol))
+                conv = false;
+        }
+        if (conv) {
+            info->status = GSLNLS_SUCCESS;
+            CK(cudaStreamSynchronize(pb->stream));
+            return status;
+        }
+        prev = cur;
+        if (info->niter >= irls_maxiter)
+            break;
+    }
+    info->status = GSLNLS_EMAXITER; // :535-541
+    out->conv = GSLNLS_EMAXITER;
+    out->status = gslnls_strerror(GSLNLS_EMAXITER);
+    CK(cudaStreamSynchronize(pb->stream));
+    return GSLNLS_EMAXITER;
 }
 
 } // extern "C"

@@ -15,6 +15,27 @@ from . import _lib
 from .control import ALGORITHMS, gsl_nls_control, pack_control
 
 JAC_MODES = {True: 0, "symbolic": 0, "forward": 1, "center": 2}
+# robust losses of gsl_nls_loss() (R/nls_rho.R:101-144): codes of src/nls_irls.c:300-326, default tuning constants
+LOSSES = {"huber": 1, "barron": 2, "bisquare": 3, "welsh": 4, "optimal": 5, "hampel": 6, "ggw": 7, "lqq": 8}
+LOSS_CC = {"huber": [1.345], "barron": [1.0, 1.345], "bisquare": [4.685061], "welsh": [2.11], "optimal": [1.060158],
+           "hampel": [0.9016085], "ggw": [1.387, 1.5, 1.063], "lqq": [1.473, 0.982, 1.5]}
+
+
+def gsl_nls_loss(rho="default", cc=None):
+    """tuning constants of a robust loss, as gsl_nls_loss() (R/nls_rho.R:101-144) returns them"""
+    if rho == "default":
+        return {"rho": "default", "cc": []}
+    if rho not in LOSSES:
+        raise ValueError("'arg' should be one of \"default\", %s" % ", ".join('"%s"' % k for k in LOSSES))
+    base = LOSS_CC[rho]
+    if cc is None:
+        cc = list(base)
+    elif len(cc) != len(base):
+        raise ValueError("'cc' must be of length %d for function '%s'" % (len(base), rho))
+    cc = [float(v) for v in cc]
+    if rho == "barron" and cc[0] > 2:
+        cc[0] = 2.0
+    return {"rho": rho, "cc": cc}
 # raw weights in the normal equations: "consistent" scales the rows of f and J by sqrt(w) (default);
 # "gsl" reproduces the reference -- libgsl scales f / fvv, gsl_df_large's J^T J stays unweighted
 WEIGHTS_MODES = {"consistent": 0, "gsl": 1}
@@ -69,6 +90,7 @@ def _result_to_dict(res, p, n_local, maxiter, trace, want_rg):
         "algorithm": res.algorithm.decode(), "ssr": res.ssr, "ssrtol": res.ssrtol, "chisq_init": res.chisq_init,
         "neval": {"f": res.neval[0], "dfu": res.neval[1], "df2": res.neval[2], "fvv": res.neval[3]},
         "npass": res.npass, "n": res.n,
+        "x_final": np.ctypeslib.as_array(res.x_final, shape=(p,)).copy(),
     }
     if trace and res.ntrace:
         nt = res.ntrace
@@ -206,6 +228,34 @@ class Problem:
                                                        conv.ctypes.data_as(_lib.c_int_p),
                                                        nit.ctypes.data_as(_lib.c_int_p)))
         return {"par": par, "ssr": ssr, "logdet": ld, "conv": conv, "niter": nit}
+
+    def fit_irls(self, start, loss="huber", cc=None, algorithm="lm", control=None):
+        """robust fit by iteratively reweighted least squares (src/nls_irls.c:412-546); the problem must have a
+        weights column (has_weights=True; upload ones when the user has none).  Returns (fit, irls info)."""
+        ctrl = gsl_nls_control() if control is None else gsl_nls_control(**dict(control))
+        ci, cd = pack_control(ctrl, algorithm, False)
+        st = np.ascontiguousarray(start, dtype=np.float64)
+        lc = gsl_nls_loss(loss, cc)
+        ccv = np.array(list(lc["cc"]) + [0.0] * (3 - len(lc["cc"])), dtype=np.float64)
+        res, info = _lib.Result(), _lib.IrlsInfo()
+        rc = _lib.lib().gslnls_problem_fit_irls(self.handle, _dptr(st), ci.ctypes.data_as(_lib.c_int_p), _dptr(cd),
+                                                LOSSES[lc["rho"]], _dptr(ccv), int(ctrl["irls_maxiter"]),
+                                                float(ctrl["irls_xtol"]), C.byref(res), C.byref(info))
+        _lib.check(rc)
+        out = _result_to_dict(res, st.size, self.n, int(ci[0]), False, False)
+        _lib.lib().gslnls_result_free(C.byref(res))
+        return out, {"sigma": info.sigma, "delta": info.delta, "niter": info.niter, "status": info.status}
+
+    def weights(self):
+        w = np.empty(self.n)
+        _lib.check(_lib.lib().gslnls_problem_get_weights(self.handle, _dptr(w)))
+        return w
+
+    def median_abs_resid(self, theta):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        m = C.c_double()
+        _lib.check(_lib.lib().gslnls_problem_median_abs_resid(self.handle, _dptr(th), C.byref(m)))
+        return m.value
 
     def multistart(self, start_range, has_range=None, algorithm="lm", control=None):
         """multi-start global search (gsl_multistart_driver, src/nls_mstart.c + src/nls.c:274-399) over batched
@@ -495,7 +545,7 @@ def fit_large_multi(model, cols, y, weights, start, algorithm="lm", control=None
 
 def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=None, fvv=None, trace=False,
                   weights=None, y=None, device=0, comm=None, model=None, devices=None, weights_mode="consistent",
-                  **kwargs):
+                  loss="default", **kwargs):
     """Fit a nonlinear least-squares model with the large-problem trust-region path on a B200.
 
     fn        two-sided formula text "y ~ A * exp(-lam * x) + b" (formula method, R/nls_large.R:135),
@@ -506,6 +556,8 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     jac       True: symbolic Jacobian as deriv() would give; "forward"/"center": finite differences
               with the step rule of src/fdjac.c.  Required, as in the reference (R/nls_large.R:319-321)
     fvv       for "lmaccel": True symbolic, "fd" finite difference (src/fdfvv.c); required (:354-356)
+    loss      "default" (least squares) or a robust loss -- name or gsl_nls_loss(...) -- fitted by IRLS as
+              gsl_nls(loss = ) does (src/nls_irls.c:412-546): huber, barron, bisquare, welsh, optimal, hampel, ggw, lqq
     weights_mode  "consistent" (default): g = J^T W f, J^T W J; "gsl": exactly the reference's numbers for
               non-unit weights (sqrt(w) on f only, unweighted J^T J -- what R/nls_large.R:587-600 + libgsl compute)
     """
@@ -594,16 +646,23 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
         ses.upload(cols, lhs, weights)
         cfit = ses.fit(st, algorithm=algorithm, control=ctrl, trace=bool(trace))
         return GslNls(fn, pnames, cfit, ses, mdl, ctrl, algorithm, weights, lhs, bool(trace))
-    pb = Problem(mdl, lhs.size, weights is not None, device)
+    lossd = gsl_nls_loss(loss) if isinstance(loss, str) else dict(loss)
+    robust = lossd["rho"] != "default"
+    pb = Problem(mdl, lhs.size, weights is not None or robust, device)
     pb.set_weights_mode(weights_mode)
-    pb.upload(cols, lhs, weights)
+    pb.upload(cols, lhs, weights if (weights is not None or not robust) else np.ones(lhs.size))
     if comm is not None:
         pb.set_comm(comm)
     ms = None
     if ranges is not None:
         ms = pb.multistart(ranges, has_range, algorithm=algorithm, control=ctrl)
         st = ms["par"]                                          # src/nls.c:534-541: the fit restarts from mpopt
-    cfit = pb.fit(st, algorithm=algorithm, control=ctrl, trace=bool(trace))
+    irls = None
+    if robust:
+        cfit, irls = pb.fit_irls(st, loss=lossd["rho"], cc=lossd["cc"], algorithm=algorithm, control=ctrl)
+    else:
+        cfit = pb.fit(st, algorithm=algorithm, control=ctrl, trace=bool(trace))
     obj = GslNls(fn, pnames, cfit, pb, mdl, ctrl, algorithm, weights, lhs, bool(trace))
     obj.mstart = ms
+    obj.irls = irls
     return obj

@@ -112,6 +112,8 @@ typedef struct gslnls_result {
     int64_t n_local;
     double *jtj;         /* [p*p] column-major J^T J at par (so R = chol(JTJ)^T replaces the O(n p^2) QR) */
     double *grad_vec;    /* [p] J^T f at par */
+    double *x_final;     /* [p] the solver's last accepted iterate w->x, also when conv reports a failure and `par`
+                            therefore carries the start values (read by the IRLS driver, src/nls_irls.c:454,515) */
 } gslnls_result;
 
 /* ---- model compilation ------------------------------------------------------------------- */
@@ -253,6 +255,28 @@ GSLNLS_API int gslnls_problem_fit_batch(gslnls_problem *pb, const double *starts
                                         double *par_out /* S*p */, double *ssr_out /* S */,
                                         double *logdet_out /* S: log det(J^T J) at start, or NULL */,
                                         int *conv_out /* S */, int *niter_out /* S */);
+
+/* ---- robust losses: iteratively reweighted least squares (gsl_multifit_nlinear_rho_driver,
+ *      src/nls_irls.c:412-546; loss functions and default tuning constants R/nls_rho.R:101-144) -----------
+ * loss  1 huber, 2 barron, 3 bisquare, 4 welsh, 5 optimal, 6 hampel, 7 ggw, 8 lqq; cc[3] tuning constants
+ * The problem must have been created with has_weights = 1 (uploaded weights = the user's, or ones): the
+ * weights column is the IRLS working vector and holds the final robustness weights on return.  Every IRLS
+ * iteration is one weighted fit from `start`, then on the device: unweighted residuals -> sigma = 1.4826
+ * median |r| by radix select -> w_i = max(psi(r_i / sigma) / (r_i / sigma), eps), normalised to sum n, times
+ * the user's weights.  `out` is the last weighted fit. */
+typedef struct gslnls_irls_info {
+    double sigma;   /* irls_sigma */
+    double delta;   /* irls_tol: max |x_k - x_{k-1}| of the last iteration (src/nls.c:589-595) */
+    int niter;      /* irls_niter */
+    int status;     /* irls_conv: 0 converged, 11 irls_maxiter reached, -1 not run */
+} gslnls_irls_info;
+GSLNLS_API int gslnls_problem_fit_irls(gslnls_problem *pb, const double *start, const int *control_int,
+                                       const double *control_dbl, int loss, const double *cc, int irls_maxiter,
+                                       double irls_xtol, gslnls_result *out, gslnls_irls_info *info);
+/* the weights column as it stands on the device (after gslnls_problem_fit_irls: the final IRLS weights) */
+GSLNLS_API int gslnls_problem_get_weights(gslnls_problem *pb, double *weights);
+/* test hook: median of |fn(theta) - y| over the resident rows by the device radix select */
+GSLNLS_API int gslnls_problem_median_abs_resid(gslnls_problem *pb, const double *theta, double *median);
 
 /* ---- multi-start global search: the control logic of gsl_multistart_driver (src/nls_mstart.c:24-349) and its
  *      outer loop (src/nls.c:274-399) over the batched kernels above --------------------------------

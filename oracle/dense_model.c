@@ -330,7 +330,7 @@ void orc_fit_result_free(orc_fit_result *r)
 {
     if (!r)
         return;
-    free(r->par); free(r->covar); free(r->partrace); free(r->ssrtrace); free(r->condtrace); free(r->diag); free(r->jtj);
+    free(r->par); free(r->covar); free(r->partrace); free(r->ssrtrace); free(r->condtrace); free(r->diag); free(r->jtj); free(r->xfinal);
     memset(r, 0, sizeof(*r));
 }
 
@@ -470,6 +470,8 @@ int orc_nls_large(orc_rows_fn rows, void *data, const double *y, const double *w
     out->jtj = (double *)calloc(p ? p * p : 1, sizeof(double));
     memcpy(out->diag, orc_diag(w), p * sizeof(double));
     memcpy(out->jtj, orc_JTJ(w), p * p * sizeof(double));
+    out->xfinal = (double *)calloc(p ? p : 1, sizeof(double));
+    memcpy(out->xfinal, orc_position(w), p * sizeof(double));
     out->niter = (int)orc_niter(w);
     out->conv = status;
     out->info = info;

@@ -151,6 +151,7 @@ typedef struct {
     double *condtrace; /* maxiter+1: cond(J) = 1/rcond as callback_large prints it (:733-738); row 0 unused */
     double *diag;      /* p: the trust-region scaling D at exit (trust_state->diag, read by src/nls_mstart.c:318-320) */
     double *jtj;       /* p*p row-major lower: J^T J at exit (for det_cholesky_jtj, src/nls_mstart.c:93) */
+    double *xfinal;    /* p: w->x at exit, also on failure (read by the IRLS driver, src/nls_irls.c:454,515) */
 } orc_fit_result;
 
 /* C_nls_large_internal restated.  control_int[7], control_dbl[8] exactly as packed by

@@ -40,7 +40,7 @@ class _FitResult(C.Structure):
                 ("neval", C.c_size_t * 4), ("partrace", C.POINTER(C.c_double)),
                 ("ssrtrace", C.POINTER(C.c_double)), ("chisq_init", C.c_double),
                 ("condtrace", C.POINTER(C.c_double)), ("diag", C.POINTER(C.c_double)),
-                ("jtj", C.POINTER(C.c_double))]
+                ("jtj", C.POINTER(C.c_double)), ("xfinal", C.POINTER(C.c_double))]
 
 
 def build(force=False):
@@ -149,6 +149,7 @@ def nls_large(model, y, start, x=None, weights=None, algorithm="lm", have_fvv=No
         "niter": res.niter, "conv": res.conv, "info": res.info, "status": L.orc_strerror(status).decode(),
         "ssr": res.ssr, "ssrtol": res.ssrtol, "chisq_init": res.chisq_init,
         "neval": {"f": res.neval[0], "dfu": res.neval[1], "df2": res.neval[2], "fvv": res.neval[3]},
+        "x_final": np.ctypeslib.as_array(res.xfinal, shape=(p,)).copy(),
         "diag": np.ctypeslib.as_array(res.diag, shape=(p,)).copy(),
         "jtj": np.tril(np.ctypeslib.as_array(res.jtj, shape=(p, p)).copy()),
     }

@@ -77,7 +77,8 @@ def test_single_process_multi_gpu_call(ngpu, alg):
     assert multi.nobs() == n
     assert np.allclose(multi.vcov(), single.vcov(), rtol=1e-8)
     assert np.allclose(multi.residuals(), single.residuals(), rtol=1e-9, atol=1e-12)
-    assert multi.cfit["grad"].shape == (n, 3)
+    assert "grad" not in multi.cfit and multi._resid is not None   # lazy: only residuals() has been asked for
+    assert np.allclose(multi.gradient(), single.gradient(), rtol=1e-9, atol=1e-12)
     assert abs(np.sum(multi.residuals() ** 2) - multi.deviance()) <= 1e-9 * multi.deviance()
     # twice in a row: the device group and the per-device buffers are reused
     again = gsl_nls_large("y ~ A * exp(-lam * x) + b", devices=list(range(ngpu)), **kw)

@@ -661,3 +661,60 @@ def test_multistart_config5_shape_finds_the_global_minimum(G):
     assert fit["ssr"] < 1.02 * np.sum((3 * np.exp(-0.5 * x) + 2 * np.exp(-3 * x) - y) ** 2)
     assert got["searches"] >= 8192
     pb.close()
+
+
+# ---------------------------------------------------------------- IRLS robust losses
+def test_device_median_is_exact(G):
+    """radix select over the bit patterns of |fn(theta) - y|: bitwise the median gsl_median() would return
+    (src/nls_utils.c:162-189), odd and even lengths, ties, an infinite residual"""
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True)
+    theta = [4.0, 1.2, 0.8]
+    for n in (1, 2, 3, 10, 255, 256, 1001, 65536, 300_007):
+        x, y = synth_exp(n, seed=n)
+        if n >= 10:
+            y[: n // 3] = np.round(y[: n // 3], 1)        # ties
+        pb = G.Problem(m, n).upload([x], y)
+        r = np.abs(theta[0] * np.exp(-theta[1] * x) + theta[2] - y)
+        got = pb.median_abs_resid(theta)
+        s = np.sort(r)
+        want = s[(n - 1) // 2] if n % 2 else (s[n // 2 - 1] + s[n // 2]) / 2.0
+        assert got == pytest.approx(want, rel=1e-13), n    # the device exp differs from numpy's by an ulp
+        pb.close()
+
+
+@pytest.mark.parametrize("loss", ["huber", "barron", "bisquare", "welsh", "optimal", "hampel", "ggw", "lqq"])
+def test_irls_matches_oracle(G, readme_examples, loss):
+    from oracle import irls as OI
+    e = readme_examples["example1"]
+    x, y = np.array(e["x"]), np.array(e["y"]).copy()
+    y[[3, 11, 19]] += [6.0, -5.0, 8.0]
+    rows = lambda th: th[0] * np.exp(-th[1] * x) + th[2]  # noqa: E731
+    m = G.Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac=True)
+    for userw in (None, 1.0 + (np.arange(x.size) % 3)):
+        pb = G.Problem(m, x.size, has_weights=True).upload([x], y, np.ones(x.size) if userw is None else userw)
+        fit, info = pb.fit_irls([1.0, 1.0, 0.0], loss=loss)
+        ref, rinfo = OI.irls("exp3", y, [1.0, 1.0, 0.0], loss=loss, x=x, rows=rows, weights=userw)
+        assert info["status"] == rinfo["status"] == 0 and info["niter"] == rinfo["niter"], (loss, info, rinfo)
+        assert info["sigma"] == pytest.approx(rinfo["sigma"], rel=1e-8)
+        assert np.allclose(fit["par"], ref["par"], rtol=1e-7), loss
+        assert np.allclose(pb.weights(), rinfo["weights"], rtol=1e-6, atol=1e-12), loss
+        pb.close()
+
+
+def test_irls_high_level_and_scale(G):
+    """gsl_nls_large(loss=...) on a contaminated large sample: the robust fit recovers the truth that the
+    least-squares fit misses; sigma is the MAD scale of the clean noise"""
+    n = 400_003
+    x, y = synth_exp(n)
+    rng = np.random.Generator(np.random.Philox(key=9))
+    bad = rng.choice(n, n // 10, replace=False)
+    y[bad] += 5.0 + 3.0 * rng.random(bad.size)             # 10 % one-sided outliers
+    start = {"A": 1.0, "lam": 1.0, "b": 0.0}
+    ls = G.gsl_nls_large("y ~ A * exp(-lam * x) + b", data={"x": x, "y": y}, start=start, jac=True)
+    rb = G.gsl_nls_large("y ~ A * exp(-lam * x) + b", data={"x": x, "y": y}, start=start, jac=True, loss="bisquare")
+    truth = np.array([5.0, 1.5, 1.0])
+    err_ls = np.abs(np.array(list(ls.coef().values())) - truth)
+    err_rb = np.abs(np.array(list(rb.coef().values())) - truth)
+    assert rb.irls["status"] == 0 and rb.irls["niter"] >= 2
+    assert err_rb[2] < 0.02 and err_ls[2] > 0.4             # the intercept absorbs the outliers in the LS fit
+    assert rb.irls["sigma"] == pytest.approx(0.25, rel=0.1)
