@@ -695,8 +695,10 @@ def test_irls_matches_oracle(G, readme_examples, loss):
         fit, info = pb.fit_irls([1.0, 1.0, 0.0], loss=loss)
         ref, rinfo = OI.irls("exp3", y, [1.0, 1.0, 0.0], loss=loss, x=x, rows=rows, weights=userw)
         assert info["status"] == rinfo["status"] == 0 and info["niter"] == rinfo["niter"], (loss, info, rinfo)
-        assert info["sigma"] == pytest.approx(rinfo["sigma"], rel=1e-8)
-        assert np.allclose(fit["par"], ref["par"], rtol=1e-7), loss
+        # the outer iteration stops at irls_xtol = eps^(1/4) = 1.2e-4: both sides walk the same iterates (same
+        # count), and each weighted fit agrees to its own 1e-8; the smooth losses carry that through at ~1e-7
+        assert info["sigma"] == pytest.approx(rinfo["sigma"], rel=1e-6)
+        assert np.allclose(fit["par"], ref["par"], rtol=1e-6), loss
         assert np.allclose(pb.weights(), rinfo["weights"], rtol=1e-6, atol=1e-12), loss
         pb.close()
 
@@ -717,4 +719,6 @@ def test_irls_high_level_and_scale(G):
     err_rb = np.abs(np.array(list(rb.coef().values())) - truth)
     assert rb.irls["status"] == 0 and rb.irls["niter"] >= 2
     assert err_rb[2] < 0.02 and err_ls[2] > 0.4             # the intercept absorbs the outliers in the LS fit
-    assert rb.irls["sigma"] == pytest.approx(0.25, rel=0.1)
+    # MAD scale of a sample with 10 % gross outliers: 1.4826 x the (0.5 / 0.9) quantile of |N(0, 0.25^2)|
+    from scipy import stats
+    assert rb.irls["sigma"] == pytest.approx(1.4826 * 0.25 * stats.norm.ppf(0.5 + 0.5 * 0.5 / 0.9), rel=0.02)
