@@ -482,9 +482,9 @@ def run_fit_config(args):
                        world, wl.p * (wl.p + 1) // 2 + wl.p + 2,
                        "deposited by the pass kernel in every GPU's mailbox over NVLink peer memory and summed in "
                        "rank order by the resident trust-region warp (no collective call)"
-                       if (comm is not None and comm.has_peer_memory and wl.p <= 32) else
+                       if (comm is not None and comm.has_peer_memory and wl.p <= 64) else
                        ("NCCL all-gather + rank-order sum" if world > 1 else
-                        ("single GPU, resident trust-region warp" if wl.p <= 32 else
+                        ("single GPU, resident trust-region warp" if wl.p <= 64 else
                          "single GPU, launch-ordered trust-region step")))},
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
     }

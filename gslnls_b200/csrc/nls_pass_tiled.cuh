@@ -41,6 +41,14 @@
 #define NT_TILES (NT_PB * (NT_PB + 1) / 2)
 #define NT_GC NT_PB                      /* column-dot partial sums per lane (one per block)  */
 
+#ifndef NT_STAGE_REGS
+#define NT_STAGE_REGS 0 /* 1: consumers release a tile after half of its DMMAs (second half staged in registers).
+                           Measured at p = 48, n = 1e7: no gain (1354.6 vs 1353.3 us per pass); staging the whole
+                           tile spills at 128 registers per thread and costs 45 % (1968.8 us).  The coupling that is
+                           left -- consumers wait 19 % of their time for tiles, producers 20 % for an empty buffer,
+                           one buffer per producer, 11.5 k cycles to produce a slab against 0.8 k of FP64 issue --
+                           needs more tile buffers than 227 KB of shared memory hold at this tile format. */
+#endif
 #define NT_NPROD NLS_UNROLL
 #define NT_NCONS (NLS_NW / (1 + NT_NPROD))
 #define NT_NP (NT_NCONS * NT_NPROD)      /* producer warps (= tile buffers) per CTA           */
@@ -121,7 +129,8 @@ struct NtRowSinkNoDot {
 template <int MODE>
 static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, const NlsThread &T, const NtShared &S,
                                                   int q, double *tile, double *rv, unsigned long long *full,
-                                                  unsigned long long *empty, double &ss, double &nbad)
+                                                  unsigned long long *empty, double &ss, double &nbad,
+                                                  long long &nt_wait_cycles)
 {
     const int lane = threadIdx.x & 31;
     const long long n = prm.n;
@@ -167,7 +176,12 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
             nw = nls_ld1(prm.w + iin);
 #endif
         }
-        nt_bar_wait(empty, (r & 1u) ^ 1u); // the consumer is done with this tile's previous contents
+        {
+            const long long w0 = prm.trace ? clock64() : 0;
+            nt_bar_wait(empty, (r & 1u) ^ 1u); // the consumer is done with this tile's previous contents
+            if (prm.trace)
+                nt_wait_cycles += clock64() - w0;
+        }
         // sqrt(w) scaling folded into the tile store; invalid (padding) lanes store zeros
 #if NLS_W_GSL
         const double swv = valid ? 1.0 : 0.0; // reference-compatible weights: the rows of J stay unweighted
@@ -237,7 +251,8 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
 template <int MODE>
 static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int c, double *tiles,
                                                   unsigned long long *full, unsigned long long *empty,
-                                                  double (&C)[NT_TILES][2], double (&gacc)[NT_GC])
+                                                  double (&C)[NT_TILES][2], double (&gacc)[NT_GC],
+                                                  long long &nt_wait_cycles)
 {
     const int lane = threadIdx.x & 31;
     const long long nslab = (prm.n + 31) >> 5;
@@ -256,10 +271,51 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
             any = true;
             const double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
             const double *rv = tile + NT_COLS * NT_LDT;
-            nt_bar_wait(full + q, r & 1u);
+            {
+                const long long w0 = prm.trace ? clock64() : 0;
+                nt_bar_wait(full + q, r & 1u);
+                if (prm.trace)
+                    nt_wait_cycles += clock64() - w0;
+            }
             // k-step ks covers observations 4 ks .. 4 ks + 3; this lane's fragment element of block b is
             // J[observation 4 ks + fc][column 8 b + fr].  The same registers feed the column dot with r
             // (J^T r, or J^T fvv / J^T (J d)): a partial sum per lane, folded over fc once per launch.
+#if NT_STAGE_REGS
+            // The tile is handed back to its producer after HALF of the slab's DMMAs, not after all of them:
+            // the second half of the tile (k-steps 4..7) moves into registers first.  (Staging the whole tile
+            // up front needs 56 more registers than the 128 a 512-thread CTA leaves per thread: it spills and
+            // the consumer becomes the bottleneck, 1.97 ms per pass against 1.35 ms -- measured.)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                double fragh[4][NT_PB], rkh[4];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const int ks = half * 4 + k4;
+#pragma unroll
+                    for (int b = 0; b < NT_PB; ++b)
+                        fragh[k4][b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+                    rkh[k4] = rv[ks * 4 + fc];
+                }
+                if (half == 1)
+                    nt_bar_arrive(empty + q); // every load of this tile has been issued before (release)
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+#if !defined(NT_DEBUG_SKIP_B)
+                    if (MODE == NLS_MODE_FJ) {
+                        int t = 0;
+#pragma unroll
+                        for (int bi = 0; bi < NT_PB; ++bi)
+#pragma unroll
+                            for (int bj = 0; bj <= bi; ++bj, ++t)
+                                nt_dmma(C[t][0], C[t][1], fragh[k4][bi], fragh[k4][bj]);
+                    }
+#endif
+#pragma unroll
+                    for (int b = 0; b < NT_PB; ++b)
+                        gacc[b] = fma(fragh[k4][b], rkh[k4], gacc[b]);
+                }
+            }
+#else
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
                 double frag[NT_PB];
@@ -283,6 +339,7 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
                 for (int b = 0; b < NT_PB; ++b)
                     gacc[b] = fma(frag[b], rk, gacc[b]);
             }
+#endif
         }
         if (!any)
             break;
@@ -347,21 +404,28 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     double ss = 0.0, nbad = 0.0;
 
     const bool consumer = warp < NT_NCONS;
+    long long nt_wait_cycles = 0; // developer hook: cycles this warp spent waiting for the other role
+    const long long nt_t0 = prm.trace ? clock64() : 0;
     if (consumer) {
         if (mode == NLS_MODE_FJ)
-            nt_consume<NLS_MODE_FJ>(prm, warp, tiles, full, empty, C, gacc);
+            nt_consume<NLS_MODE_FJ>(prm, warp, tiles, full, empty, C, gacc, nt_wait_cycles);
         else
-            nt_consume<NLS_MODE_FVV>(prm, warp, tiles, full, empty, C, gacc); // FVV and JVP: column dots only
+            nt_consume<NLS_MODE_FVV>(prm, warp, tiles, full, empty, C, gacc, nt_wait_cycles); // FVV and JVP: column dots only
     } else {
         const int q = warp - NT_NCONS;
         double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
         double *rv = tile + NT_COLS * NT_LDT;
         if (mode == NLS_MODE_FJ)
-            nt_produce<NLS_MODE_FJ>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+            nt_produce<NLS_MODE_FJ>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
         else if (mode == NLS_MODE_FVV)
-            nt_produce<NLS_MODE_FVV>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+            nt_produce<NLS_MODE_FVV>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
         else
-            nt_produce<NLS_MODE_JVP>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad);
+            nt_produce<NLS_MODE_JVP>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
+    }
+    if (prm.trace && lane == 0 && warp < 16 && blockIdx.y == 0) {
+        // [cta][0..15]: wait cycles of warp w; [cta][16 + w]: cycles warp w spent in its streaming loop
+        prm.trace[(size_t)blockIdx.x * 32 + warp] = (unsigned long long)nt_wait_cycles;
+        prm.trace[(size_t)blockIdx.x * 32 + 16 + warp] = (unsigned long long)(clock64() - nt_t0);
     }
 
     // ---- CTA reduction: warps add their sums into the shared packet in warp order ----

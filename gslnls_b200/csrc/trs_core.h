@@ -291,6 +291,11 @@ struct Solver {
                 out[i] = -out[i];
             return;
         }
+        solve_neg_private(b, out);
+    }
+    // the private substitution: no lane talks to another, so lanes may run it on different right-hand sides
+    TRS_HD void solve_neg_private(const double *b, double *out) const
+    {
         for (int i = 0; i < p; ++i)
             out[i] = b[i];
         for (int i = 0; i < p; ++i) {
@@ -1062,14 +1067,16 @@ struct Solver {
                 C[e] = NAN;
             return;
         }
-        for (int k = 0; k < p; ++k) {
+        // one column of the inverse per lane, private substitution on the shared factor (the shared solve
+        // would spend 2p serial broadcast steps per column; element for element the same arithmetic)
+        for (int k = ln; k < p; k += nl) {
             for (int i = 0; i < p; ++i)
                 w1[i] = (i == k) ? 1.0 : 0.0;
-            solve_neg(w1, w3);
-            if (ln == 0)
-                for (int i = 0; i < p; ++i)
-                    C[i * p + k] = -w3[i];
+            solve_neg_private(w1, w3);
+            for (int i = 0; i < p; ++i)
+                C[i * p + k] = -w3[i];
         }
+        L.sync();
     }
 
     // ---------------------------------------------------------------- the state machine

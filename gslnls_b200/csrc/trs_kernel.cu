@@ -297,7 +297,7 @@ __global__ void trs_channel_begin(char *channel)
 // start of a fit in resident-server mode, one launch: state and request records from start values passed BY
 // VALUE (no host-to-device copy in front of the fit) plus the channel bookkeeping of trs_channel_begin
 struct TrsStart {
-    double v[32];
+    double v[64];
 };
 __global__ void trs_fit_begin(double *state, double *req, const TrsStart st, int p, int *ndone, char *channel)
 {
@@ -317,10 +317,10 @@ __global__ void trs_fit_begin(double *state, double *req, const TrsStart st, int
 cudaError_t trs_launch_fit_begin(double *state, double *req, const double *start_host, int p, int *ndone,
                                  char *channel, cudaStream_t stream)
 {
-    if (p > 32)
+    if (p > 64)
         return cudaErrorInvalidValue;
     TrsStart st;
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < 64; ++i)
         st.v[i] = i < p ? start_host[i] : 0.0;
     trs_fit_begin<<<1, 32, 0, stream>>>(state, req, st, p, ndone, channel);
     return cudaGetLastError();
@@ -369,7 +369,7 @@ cudaError_t launch_sum_rank_packets(const double *gathered, double *packet, int 
 }
 
 int trs_max_p() { return 100; }
-int trs_server_max_p() { return 32; }
+int trs_server_max_p() { return 64; }
 
 cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream)
 {
@@ -397,6 +397,14 @@ cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, i
         TRS_SERVER_LAUNCH(8, false);
     else if (P.p <= 32)
         TRS_SERVER_LAUNCH(32, false);
+    else if (P.p <= 64) {
+        // 2 p^2 doubles of shared memory: 64 KB at p = 64, above the 48 KB default limit
+        cudaError_t e = cudaFuncSetAttribute(trs_server<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(double) * 2 * 64 * 64));
+        if (e != cudaSuccess)
+            return e;
+        TRS_SERVER_LAUNCH(64, false);
+    }
 #undef TRS_SERVER_LAUNCH
     else
         return cudaErrorInvalidValue;

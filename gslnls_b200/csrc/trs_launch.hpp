@@ -25,7 +25,7 @@ cudaError_t trs_launch_set_request(double *req, int mode, const double *theta, c
 // resident-server mode (one fit, one candidate): channel bookkeeping + the server kernel itself
 int trs_server_max_p();
 cudaError_t trs_launch_channel_begin(char *channel, cudaStream_t stream);
-// reset + channel_begin in one launch, start values by value (p <= 32)
+// reset + channel_begin in one launch, start values by value (p <= 64)
 cudaError_t trs_launch_fit_begin(double *state, double *req, const double *start_host, int p, int *ndone,
                                  char *channel, cudaStream_t stream);
 cudaError_t trs_launch_server(const trs::Params &P, char *channel, int nranks, int pk_count, double *state,
