@@ -607,6 +607,19 @@ GSLNLS_API int gslnls_problem_create(const gslnls_model *m, int64_t n_local, int
     pb->wgsl = default_weights_mode();
     if (const char *c = std::getenv("GSLNLS_L2_KEEP_MB"))
         pb->keep_mb = std::atof(c);
+    if (const char *c = std::getenv("GSLNLS_L2_PERSIST_MB")) { // developer aid: L2 set-aside for persisting (evict_last) lines
+        const size_t want = (size_t)(std::atof(c) * 1048576.0);
+        const size_t cap = (size_t)prop.persistingL2CacheMaxSize;
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(want, cap));
+        if (e != cudaSuccess)
+            cudaGetLastError();
+        static bool told = false;
+        if (!told) {
+            std::fprintf(stderr, "gslnls: persisting L2 set-aside %.0f MB requested, device maximum %.0f MB (%s)\n",
+                         want / 1048576.0, cap / 1048576.0, cudaGetErrorString(e));
+            told = true;
+        }
+    }
     if (const char *c = std::getenv("GSLNLS_HANDSHAKE_MS"))
         pb->handshake_ns = (unsigned long long)std::max(1, std::atoi(c)) * 1000000ull;
     CK(cudaStreamCreateWithFlags(&pb->srv_stream, cudaStreamNonBlocking));
