@@ -66,10 +66,13 @@
 enum { NLS_MODE_IDLE = 0, NLS_MODE_FJ = 1, NLS_MODE_FVV = 2, NLS_MODE_JVP = 3 };
 
 // ------------------------------------------------------------------------------------ loads
-// Every streaming load carries an L2 eviction policy.  A pass reads each byte once, but the NEXT pass reads
-// the same bytes again, and 126 MB of L2 sit in front of HBM: rows below prm.keep_rows are loaded evict_last
-// (they stay resident from pass to pass and are served at L2 rate), the rest evict_first (they cycle through
-// what is left and never push the kept lines, or the trust-region server's state, out).
+// L2 eviction policies.  A pass reads each byte once, but the NEXT pass reads the same bytes again and 126 MB of
+// L2 sit in front of HBM, so round 2 tried to keep the head of a shard resident: rows below prm.keep_rows
+// loaded evict_last, the rest evict_first, on both load paths, with and without a persisting set-aside
+// (cudaLimitPersistingL2CacheSize, 79 MB max on B200).  Measured on 100 / 200 / 400 MB shards: no effect
+// (profiles/r02_summary.md), so keep_rows defaults to 0 and only the bulk-copy producer still selects a policy
+// (one scalar select per tile; evict_first keeps the trust-region server's lines in L2).  The per-thread LDG
+// loads carry no L2 hint: a per-lane policy operand makes ptxas wrap every load in a warp-collective loop.
 struct NlsPolicy {
     unsigned long long keep, stream;
     long long keep_rows;
@@ -82,18 +85,17 @@ static __device__ __forceinline__ NlsPolicy nls_policy(long long keep_rows)
     P.keep_rows = keep_rows;
     return P;
 }
-static __device__ __forceinline__ double2 nls_ld2(const double *p, unsigned long long pol)
+static __device__ __forceinline__ double2 nls_ld2(const double *p)
 {
     double2 r;
 #if NLS_STREAM
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
 #else
-    (void)pol;
     asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
 #endif
     return r;
 }
-#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o), ((o) < PL.keep_rows) ? PL.keep : PL.stream)
+#define NLS_LD2(ptr, o) nls_ld2((ptr) + (o))
 static __device__ __forceinline__ double nls_ld1(const double *p)
 {
     double r;
@@ -287,8 +289,6 @@ static __device__ __forceinline__ void nls_stream(const NlsPassParams &prm, cons
     const long long n = prm.n;
     const long long stride = (long long)gridDim.x * NLS_BLOCK;
     long long i = (long long)blockIdx.x * NLS_BLOCK + threadIdx.x;
-    const NlsPolicy PL = nls_policy(prm.keep_rows);
-    (void)PL;
 #if NLS_VEC == 2
     const long long nv = n >> 1;
     i += lo >> 1;

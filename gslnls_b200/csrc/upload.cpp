@@ -68,9 +68,16 @@ int upload_threads_default(int sharing)
 {
     if (const char *c = std::getenv("GSLNLS_UPLOAD_THREADS"))
         return std::max(1, std::atoi(c));
-    // `sharing` uploads run side by side (one per GPU of a multi-GPU call) and share the host cores
+    // `sharing` uploads run side by side (one per GPU of a multi-GPU call) and share the host cores; so do the
+    // sibling ranks of a one-process-per-GPU job (torchrun / mpirun export their count)
     const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    return std::max(1, std::min(8, hw / std::max(1, sharing)));
+    int siblings = 1;
+    for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+        if (const char *c = std::getenv(name)) {
+            siblings = std::max(1, std::atoi(c));
+            break;
+        }
+    return std::max(1, std::min(8, hw / std::max(1, sharing * siblings)));
 }
 
 // copy `ncol` host columns of `bytes` bytes each to their device buffers; returns a GSLNLS code.
