@@ -610,7 +610,8 @@ def gsl_nls_large(fn, data=None, start=None, algorithm="lm", control=None, jac=N
     if not cols and not var_names:
         if lhs.size == 0:
             raise ValueError("no parameters to fit and/or no data variables present")  # :214-216
-    if lhs.size < len(pnames):
+    if comm is None and lhs.size < len(pnames):
+        # a rank of a sharded fit may hold fewer rows than parameters: the library checks the global count
         raise ValueError("negative residual degrees of freedom, cannot fit a model with less observations "
                          "than parameters")  # :286-288
     if weights is not None:
