@@ -500,6 +500,7 @@ void cache_drop(const gslnls_model *m)
 // else is caught by the start-of-fit handshake (trs_server), after which the process stops using the server.
 namespace {
 std::atomic<bool> g_server_unsafe{false};
+std::atomic<int> g_handshake_failures{0}; // consecutive start-of-fit handshakes that timed out
 bool env_set(const char *name)
 {
     const char *c = std::getenv(name);
@@ -1103,7 +1104,18 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
             CK(cudaStreamSynchronize(pb->stream));
             CK(cudaStreamSynchronize(pb->srv_stream));
             pb->server_on = false;
-            g_server_unsafe.store(true);
+            // one timeout can be a hiccup (the host thread descheduled between the two launches); two in a row
+            // mean kernels are being serialised: stop trying in this process
+            const bool give_up = g_handshake_failures.fetch_add(1) + 1 >= 2;
+            if (give_up)
+                g_server_unsafe.store(true);
+            const bool saved_allow = pb->allow_server;
+            pb->allow_server = false; // this fit restarts launch-ordered either way
+            struct Restore {
+                gslnls_problem *pb;
+                bool v;
+                ~Restore() { pb->allow_server = v; }
+            } restore{pb, saved_allow};
             if (pb->comm && pb->comm->nranks > 1) {
                 set_error("the resident trust-region server cannot run next to the pass kernel on this rank "
                           "(kernels are serialised); rerun every rank with GSLNLS_SERVER=0");
@@ -1129,6 +1141,8 @@ GSLNLS_API int gslnls_problem_fit_run(gslnls_problem *pb, int max_passes, int *d
                 return rc;
             fin = pb->h_flags[0] != 0;
         }
+        if (pb->h_flags[0] == 1)
+            g_handshake_failures.store(0);
         if (pb->h_flags[0] == 2) {
             if (pb->comm && pb->comm->nranks > 1)
                 set_error("trust-region server watchdog: a rank never delivered its packet");
