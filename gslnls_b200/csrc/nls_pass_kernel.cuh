@@ -1007,6 +1007,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(c
     __shared__ double sred[NLS_NCW][NLS_PK];
     __shared__ unsigned long long s_seq, s_consumed;
     __shared__ int s_mode, s_last;
+    __shared__ double s_req[2 * NLS_P]; // theta, v of the current request (fetched once per CTA)
     __shared__ volatile int s_stop;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long ntile = prm.n / NLS_TILE;
@@ -1112,8 +1113,14 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(c
                     }
                 }
             }
-            if (mode < 0)
+            if (mode < 0) {
+                // the request record travels with the sequence number: fetch it here, once per CTA, instead of one
+                // L2 round trip per thread after the barrier
                 mode = (int)__ldcg(prm.req);
+#pragma unroll
+                for (int j = 0; j < 2 * NLS_P; ++j)
+                    s_req[j] = __ldcg(prm.req + 1 + j);
+            }
             s_mode = mode;
             s_seq = k;
             if (blockIdx.x == 0 && mode != NLS_MODE_IDLE)
@@ -1125,7 +1132,17 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, 1) nls_pass_persistent(c
             break;
         nls_trace(prm, 1);
         NlsThread T;
-        nls_load_request(prm, prm.req, T);
+#pragma unroll
+        for (int j = 0; j < NLS_P; ++j) { // as nls_load_request, from the CTA's copy
+            T.th[j] = s_req[j];
+            T.vv[j] = s_req[NLS_P + j];
+            double d = prm.h_df * fabs(T.th[j]);
+            if (d == 0.0)
+                d = prm.h_df;
+            T.dl[j] = d;
+            T.idl[j] = 1.0 / d;
+        }
+        T.h_fvv = prm.h_fvv;
         double acc[NLS_PK];
 #pragma unroll
         for (int e = 0; e < NLS_PK; ++e)

@@ -253,7 +253,10 @@ __global__ void __launch_bounds__(32) trs_server(const trs::Params P, char *chan
         }
         __syncwarp();
         S.advance(state, packet, req, partrace, ssrtrace, condtrace);
-        __threadfence();
+        // the request record (and the trace rows) are written by lane 0 alone: its release store orders them; a
+        // finished fit also stored the state record from every lane, which the fence below the loop covers
+        if (S.phase == trs::PH_DONE)
+            __threadfence();
         __syncwarp();
         if (lane == 0) {
             st_release_gpu(req_seq, k + 1ull);
