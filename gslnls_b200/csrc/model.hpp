@@ -62,6 +62,7 @@ namespace gslnls {
 // persistent: the fit will run the one-launch-per-fit kernel, which exists for the TMA-ring variant only
 KernelTune default_tune(int p, double shard_bytes = 0.0, bool persistent = false);
 size_t tiled_smem_bytes(int p, int block, int nprod, int nconst); // dynamic shared memory of the tiled pass kernel
+int tiled_num_buffers(int p, int block, int nprod, int nconst);   // tile buffers of its CTA-wide ring (NT_NBUF)
 size_t tma_smem_bytes(int narr, int block, int unroll, int stages); // dynamic shared memory of the TMA-staged pass kernel
 std::string nvrtc_arch_for_device(int device); // "sm_100a" on B200; used as --gpu-architecture
 void cache_drop(const gslnls_model *m); // problem.cu: release one-shot problems cached for m (nullptr: all)

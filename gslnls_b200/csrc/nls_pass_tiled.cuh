@@ -53,6 +53,15 @@
 #define NT_NCONS (NLS_NW / (1 + NT_NPROD))
 #define NT_NP (NT_NCONS * NT_NPROD)      /* producer warps (= tile buffers) per CTA           */
 #define NT_TILE_DOUBLES (NT_COLS * NT_LDT + 32)
+// Tile buffers form a CTA-wide ring that is decoupled from the producers: CTA-local slab number L (round r,
+// producer q: L = r NT_NP + q) lives in buffer L mod NT_NBUF.  With one buffer per producer (NT_NBUF == NT_NP, the
+// round-1 layout) a producer cannot start its next slab before its previous one has been consumed, and both
+// roles measured ~20 % of their time waiting for each other; with NT_NBUF = NT_NP + 3 (what 227 KB of shared
+// memory hold at p = 48) a producer only waits if the consumers are more than a full round behind.  The order
+// in which a consumer contracts slabs -- hence every sum -- is unchanged.  The host passes NT_NBUF (model.cpp).
+#ifndef NT_NBUF
+#define NT_NBUF NT_NP
+#endif
 
 #if NT_TILES > 28
 #error "nls_pass_tiled: p > 56 needs the tile set split across warps (not built yet)"
@@ -128,8 +137,8 @@ struct NtRowSinkNoDot {
 // ---------------------------------------------------------------- producer: phase A
 template <int MODE>
 static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, const NlsThread &T, const NtShared &S,
-                                                  int q, double *tile, double *rv, unsigned long long *full,
-                                                  unsigned long long *empty, double &ss, double &nbad,
+                                                  int q, double *tiles, unsigned long long *full_base,
+                                                  unsigned long long *empty_base, double &ss, double &nbad,
                                                   long long &nt_wait_cycles)
 {
     const int lane = threadIdx.x & 31;
@@ -153,6 +162,11 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
     }
     int nbad_i = 0;
     for (unsigned r = 0; slab < nslab; slab += wstride, ++r) {
+        // ring position of this slab: buffer, and how many times that buffer has been used before
+        const unsigned L = r * NT_NP + (unsigned)q, buf = L % NT_NBUF, use = L / NT_NBUF;
+        double *tile = tiles + (size_t)buf * NT_TILE_DOUBLES;
+        double *rv = tile + NT_COLS * NT_LDT;
+        unsigned long long *full = full_base + buf, *empty = empty_base + buf;
         const long long i = (slab << 5) + lane;
         const bool valid = i < n;
         double xa[NLS_NV];
@@ -178,7 +192,7 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
         }
         {
             const long long w0 = prm.trace ? clock64() : 0;
-            nt_bar_wait(empty, (r & 1u) ^ 1u); // the consumer is done with this tile's previous contents
+            nt_bar_wait(empty, (use & 1u) ^ 1u); // the consumer is done with this buffer's previous contents
             if (prm.trace)
                 nt_wait_cycles += clock64() - w0;
         }
@@ -269,11 +283,12 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
             if (slab >= nslab)
                 continue;
             any = true;
-            const double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
+            const unsigned L = r * NT_NP + (unsigned)q, buf = L % NT_NBUF, use = L / NT_NBUF;
+            const double *tile = tiles + (size_t)buf * NT_TILE_DOUBLES;
             const double *rv = tile + NT_COLS * NT_LDT;
             {
                 const long long w0 = prm.trace ? clock64() : 0;
-                nt_bar_wait(full + q, r & 1u);
+                nt_bar_wait(full + buf, use & 1u);
                 if (prm.trace)
                     nt_wait_cycles += clock64() - w0;
             }
@@ -297,7 +312,7 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
                     rkh[k4] = rv[ks * 4 + fc];
                 }
                 if (half == 1)
-                    nt_bar_arrive(empty + q); // every load of this tile has been issued before (release)
+                    nt_bar_arrive(empty + buf); // every load of this tile has been issued before (release)
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
 #if !defined(NT_DEBUG_SKIP_B)
@@ -324,7 +339,7 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
                     frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
                 const double rk = rv[ks * 4 + fc];
                 if (ks == 7)
-                    nt_bar_arrive(empty + q); // every load of this tile has been issued before (release)
+                    nt_bar_arrive(empty + buf); // every load of this tile has been issued before (release)
 #if !defined(NT_DEBUG_SKIP_B)
                 if (MODE == NLS_MODE_FJ) {
                     int t = 0;
@@ -365,10 +380,10 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
     // shared memory: NT_NP tiles [NT_COLS][NT_LDT] + rv[32]; the CTA packet [NLS_PK]; theta, v and the
     // model's launch invariants; the full / empty barriers of every tile
     double *tiles = nt_smem;
-    double *pk = nt_smem + (size_t)NT_NP * NT_TILE_DOUBLES;
+    double *pk = nt_smem + (size_t)NT_NBUF * NT_TILE_DOUBLES;
     double *s_th = pk + NLS_PK, *s_vv = s_th + NLS_P, *s_cfj = s_vv + NLS_P, *s_cfvv = s_cfj + NT_NC_FJ;
-    unsigned long long *full = (unsigned long long *)(s_cfvv + NT_NC_FVV), *empty = full + NT_NP;
-    for (int e = threadIdx.x; e < NT_NP * NT_TILE_DOUBLES; e += NLS_BLOCK)
+    unsigned long long *full = (unsigned long long *)(s_cfvv + NT_NC_FVV), *empty = full + NT_NBUF;
+    for (int e = threadIdx.x; e < NT_NBUF * NT_TILE_DOUBLES; e += NLS_BLOCK)
         tiles[e] = 0.0; // padding columns stay zero for the whole launch
     for (int e = threadIdx.x; e < NLS_PK; e += NLS_BLOCK)
         pk[e] = 0.0;
@@ -376,7 +391,7 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
         s_th[j] = __ldcg(req + 1 + j);
         s_vv[j] = __ldcg(req + 1 + NLS_P + j);
     }
-    if (threadIdx.x < NT_NP) {
+    if (threadIdx.x < NT_NBUF) {
         nt_bar_init(full + threadIdx.x, 32);
         nt_bar_init(empty + threadIdx.x, 32);
     }
@@ -413,14 +428,12 @@ extern "C" __global__ void __launch_bounds__(NLS_BLOCK, NLS_MINB) nls_pass(const
             nt_consume<NLS_MODE_FVV>(prm, warp, tiles, full, empty, C, gacc, nt_wait_cycles); // FVV and JVP: column dots only
     } else {
         const int q = warp - NT_NCONS;
-        double *tile = tiles + (size_t)q * NT_TILE_DOUBLES;
-        double *rv = tile + NT_COLS * NT_LDT;
         if (mode == NLS_MODE_FJ)
-            nt_produce<NLS_MODE_FJ>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
+            nt_produce<NLS_MODE_FJ>(prm, T, S, q, tiles, full, empty, ss, nbad, nt_wait_cycles);
         else if (mode == NLS_MODE_FVV)
-            nt_produce<NLS_MODE_FVV>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
+            nt_produce<NLS_MODE_FVV>(prm, T, S, q, tiles, full, empty, ss, nbad, nt_wait_cycles);
         else
-            nt_produce<NLS_MODE_JVP>(prm, T, S, q, tile, rv, full + q, empty + q, ss, nbad, nt_wait_cycles);
+            nt_produce<NLS_MODE_JVP>(prm, T, S, q, tiles, full, empty, ss, nbad, nt_wait_cycles);
     }
     if (prm.trace && lane == 0 && warp < 16 && blockIdx.y == 0) {
         // [cta][0..15]: wait cycles of warp w; [cta][16 + w]: cycles warp w spent in its streaming loop
