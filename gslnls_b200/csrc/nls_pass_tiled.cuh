@@ -35,9 +35,14 @@
 
 #define NT_PB ((NLS_P + 7) / 8)          /* 8-wide parameter blocks                         */
 #define NT_COLS (NT_PB * 8)              /* J columns incl. zero padding                    */
-#define NT_LDT 36                        /* tile row pitch in doubles: == 4 (mod 8), so both the
-                                            column stores (32 consecutive doubles) and the 4x8
-                                            fragment loads hit 16 distinct 8-byte banks per half-warp */
+#define NT_LDT 32                        /* tile column pitch in doubles: the 32 observations of a slab, no padding.
+                                            Element (column j, observation i) sits at NT_AT(j, i): the observation
+                                            index is XOR-swizzled with the column's low two bits, so both the column
+                                            stores (a permutation of 32 consecutive doubles) and the 4x8 fragment
+                                            loads (columns fr, observations 4 ks + fc) hit 16 distinct 8-byte banks
+                                            per half-warp.  (A padded pitch of 36 does the same with 12 % more
+                                            shared memory -- one tile buffer per CTA at p = 48.) */
+#define NT_AT(j, i) ((j) * NT_LDT + ((i) ^ (((j) & 3) << 2)))
 #define NT_TILES (NT_PB * (NT_PB + 1) / 2)
 #define NT_GC NT_PB                      /* column-dot partial sums per lane (one per block)  */
 
@@ -53,15 +58,34 @@
 #define NT_NCONS (NLS_NW / (1 + NT_NPROD))
 #define NT_NP (NT_NCONS * NT_NPROD)      /* producer warps (= tile buffers) per CTA           */
 #define NT_TILE_DOUBLES (NT_COLS * NT_LDT + 32)
-// Tile buffers form a CTA-wide ring that is decoupled from the producers: CTA-local slab number L (round r,
-// producer q: L = r NT_NP + q) lives in buffer L mod NT_NBUF.  With one buffer per producer (NT_NBUF == NT_NP, the
-// round-1 layout) a producer cannot start its next slab before its previous one has been consumed, and both
-// roles measured ~20 % of their time waiting for each other; with NT_NBUF = NT_NP + 3 (what 227 KB of shared
-// memory hold at p = 48) a producer only waits if the consumers are more than a full round behind.  The order
-// in which a consumer contracts slabs -- hence every sum -- is unchanged.  The host passes NT_NBUF (model.cpp).
+// Tile buffers are decoupled from the producers: every consumer owns a ring of R_c buffers that its NT_NPROD
+// producers fill in the consumer's own consumption order (slab number Lc = r NT_NPROD + j of round r, producer
+// j lives in buffer base_c + Lc mod R_c).  With one buffer per producer (R_c = NT_NPROD, the round-1 layout) a
+// producer cannot start its next slab before its previous one has been consumed, and both roles measured ~20 %
+// of their time waiting for each other; the NT_NBUF buffers that 227 KB of shared memory hold (NT_NP + 3 at
+// p = 48) are dealt out 4,4,4,3.  The rings are per consumer because mbarrier waits only see the phase PARITY:
+// a waiter must never be two phases away from its barrier.  Inside one consumer's ring that holds by
+// construction -- the consumer takes its slabs in order, so a producer that has filled its previous slab
+// Lc - NT_NPROD knows every slab up to Lc - NT_NPROD - R_c has been consumed, and Lc - 2 R_c is among them when
+// R_c >= NT_NPROD -- whereas a ring shared by independent consumers can alias (a fast consumer's producer would
+// read "free" off a buffer a slow consumer is two uses behind on).  The order in which a consumer contracts
+// slabs -- hence every sum -- does not depend on the ring sizes.  The host passes NT_NBUF (model.cpp).
 #ifndef NT_NBUF
 #define NT_NBUF NT_NP
 #endif
+#if NT_NBUF / NT_NCONS < NT_NPROD
+#error "nls_pass_tiled: every consumer needs at least one tile buffer per producer"
+#endif
+// ring position of round r of producer q: buffer and how many times that buffer has been used before
+static __device__ __forceinline__ void nt_ring_pos(int q, unsigned r, unsigned &buf, unsigned &use)
+{
+    const int c = q / NT_NPROD, j = q - c * NT_NPROD;
+    const int RB = NT_NBUF / NT_NCONS, RX = NT_NBUF % NT_NCONS;
+    const unsigned R = (unsigned)(RB + (c < RX ? 1 : 0)), base = (unsigned)(c * RB + (c < RX ? c : RX));
+    const unsigned Lc = r * NT_NPROD + (unsigned)j;
+    buf = base + Lc % R;
+    use = Lc / R;
+}
 
 #if NT_TILES > 28
 #error "nls_pass_tiled: p > 56 needs the tile set split across warps (not built yet)"
@@ -118,20 +142,22 @@ struct NtShared {
 // sqrt(w) (0 for the padding lanes of the last slab) straight into this lane's tile column; the
 // JVP mode also needs u = row . d, accumulated on the way
 struct NtRowSink {
-    double *col; // &tile[lane]
+    double *tile;
+    int lane;
     const double *vv;
     double sw, u;
     __device__ __forceinline__ void operator()(int j, double v)
     {
         const double s = v * sw;
-        col[j * NT_LDT] = s;
+        tile[NT_AT(j, lane)] = s;
         u = fma(s, vv[j], u);
     }
 };
 struct NtRowSinkNoDot {
-    double *col;
+    double *tile;
+    int lane;
     double sw;
-    __device__ __forceinline__ void operator()(int j, double v) { col[j * NT_LDT] = v * sw; }
+    __device__ __forceinline__ void operator()(int j, double v) { tile[NT_AT(j, lane)] = v * sw; }
 };
 
 // ---------------------------------------------------------------- producer: phase A
@@ -162,8 +188,8 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
     }
     int nbad_i = 0;
     for (unsigned r = 0; slab < nslab; slab += wstride, ++r) {
-        // ring position of this slab: buffer, and how many times that buffer has been used before
-        const unsigned L = r * NT_NP + (unsigned)q, buf = L % NT_NBUF, use = L / NT_NBUF;
+        unsigned buf, use;
+        nt_ring_pos(q, r, buf, use);
         double *tile = tiles + (size_t)buf * NT_TILE_DOUBLES;
         double *rv = tile + NT_COLS * NT_LDT;
         unsigned long long *full = full_base + buf, *empty = empty_base + buf;
@@ -207,11 +233,11 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
         f = xa[0]; // timing experiment: no model evaluation, tile keeps its initial contents
 #elif GSLNLS_JAC_MODE == 0
         if (MODE == NLS_MODE_JVP || (MODE == NLS_MODE_FVV && GSLNLS_FVV_MODE == 2)) {
-            NtRowSink sink{tile + lane, S.vv, swv, 0.0};
+            NtRowSink sink{tile, lane, S.vv, swv, 0.0};
             nls_model_fj_c(S.th, S.c_fj, xa, f, sink);
             u = sink.u;
         } else {
-            NtRowSinkNoDot sink{tile + lane, swv};
+            NtRowSinkNoDot sink{tile, lane, swv};
             nls_model_fj_c(S.th, S.c_fj, xa, f, sink);
         }
 #else
@@ -219,7 +245,7 @@ static __device__ __forceinline__ void nt_produce(const NlsPassParams &prm, cons
         nls_fj(T, xa, f, J);
 #pragma unroll
         for (int j = 0; j < NLS_P; ++j) {
-            tile[j * NT_LDT + lane] = J[j] * swv;
+            tile[NT_AT(j, lane)] = J[j] * swv;
             u = fma(J[j] * swv, S.vv[j], u);
         }
 #endif
@@ -272,6 +298,8 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
     const long long nslab = (prm.n + 31) >> 5;
     const long long wstride = (long long)gridDim.x * NT_NP;
     const int fr = lane >> 2, fc = lane & 3; // fragment coordinates of this lane
+    // NT_AT(8 b + fr, 4 ks + fc) = 8 b NT_LDT + frow + ((4 ks) ^ fx): fc sits below the swizzled bits
+    const int frow = fr * NT_LDT + fc, fx = (fr & 3) << 2;
     // producers q = c NT_NPROD + j, j = 0..NT_NPROD-1, each in its own slab sequence; the consumer
     // takes their tiles in the fixed order (round 0: j = 0, 1, ..; round 1: ..) -- deterministic sums
     for (unsigned r = 0;; ++r) {
@@ -283,7 +311,8 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
             if (slab >= nslab)
                 continue;
             any = true;
-            const unsigned L = r * NT_NP + (unsigned)q, buf = L % NT_NBUF, use = L / NT_NBUF;
+            unsigned buf, use;
+            nt_ring_pos(q, r, buf, use);
             const double *tile = tiles + (size_t)buf * NT_TILE_DOUBLES;
             const double *rv = tile + NT_COLS * NT_LDT;
             {
@@ -308,7 +337,7 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
                     const int ks = half * 4 + k4;
 #pragma unroll
                     for (int b = 0; b < NT_PB; ++b)
-                        fragh[k4][b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+                        fragh[k4][b] = tile[b * 8 * NT_LDT + frow + ((ks * 4) ^ fx)];
                     rkh[k4] = rv[ks * 4 + fc];
                 }
                 if (half == 1)
@@ -336,7 +365,7 @@ static __device__ __forceinline__ void nt_consume(const NlsPassParams &prm, int 
                 double frag[NT_PB];
 #pragma unroll
                 for (int b = 0; b < NT_PB; ++b)
-                    frag[b] = tile[(b * 8 + fr) * NT_LDT + ks * 4 + fc];
+                    frag[b] = tile[b * 8 * NT_LDT + frow + ((ks * 4) ^ fx)];
                 const double rk = rv[ks * 4 + fc];
                 if (ks == 7)
                     nt_bar_arrive(empty + buf); // every load of this tile has been issued before (release)
