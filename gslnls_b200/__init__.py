@@ -7,6 +7,7 @@ include/gslnls_b200.h); importing this package without that library raises.
 from .control import gsl_nls_control, pack_control  # noqa: F401
 from .nls_large import (GslNls, Model, Problem, Session, fit_large_multi, gsl_nls_large,  # noqa: F401
                         gsl_nls_loss)
+from .sparse import SparseProblem  # noqa: F401
 
 __all__ = ["gsl_nls_large", "gsl_nls_control", "GslNls", "Model", "Problem", "pack_control", "fit_large_multi",
-           "Session", "gsl_nls_loss"]
+           "Session", "gsl_nls_loss", "SparseProblem"]

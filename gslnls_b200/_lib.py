@@ -37,6 +37,15 @@ class MstartResult(C.Structure):
                 ("status", C.c_int), ("searches", C.c_int64)]
 
 
+class SparseResult(C.Structure):
+    """struct gslnls_sparse_result"""
+    _fields_ = [("p", C.c_int), ("nrows", C.c_int64), ("nterms", C.c_int64), ("nnz", C.c_int64), ("par", c_double_p),
+                ("ssr", C.c_double), ("ssrtol", C.c_double), ("chisq_init", C.c_double), ("niter", C.c_int),
+                ("conv", C.c_int), ("info", C.c_int), ("status", C.c_char_p), ("neval", C.c_int64 * 4),
+                ("cg_iters", C.c_int64), ("launches", C.c_int64), ("ntrace", C.c_int), ("ssrtrace", c_double_p),
+                ("grad_vec", c_double_p), ("jtj", c_double_p), ("resid", c_double_p)]
+
+
 # every symbol include/gslnls_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gslnls_model_compile": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.c_int,
@@ -94,6 +103,17 @@ SIGNATURES = {
                                             C.POINTER(MstartResult)]),
     "gslnls_mstart_result_free": (None, [C.POINTER(MstartResult)]),
     "gslnls_qrng_points": (C.c_int, [C.c_int, C.c_int, c_double_p]),
+    "gslnls_sparse_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "gslnls_sparse_free": (None, [C.c_void_p]),
+    "gslnls_sparse_add_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(c_double_p), c_int_p,
+                                          C.POINTER(c_int_p), c_int_p, C.c_int64]),
+    "gslnls_sparse_set_response": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "gslnls_sparse_finalize": (C.c_int, [C.c_void_p]),
+    "gslnls_sparse_nnz": (C.c_int64, [C.c_void_p]),
+    "gslnls_sparse_fit": (C.c_int, [C.c_void_p, c_double_p, c_int_p, c_double_p, C.c_int, C.c_int,
+                                    C.POINTER(SparseResult)]),
+    "gslnls_sparse_eval": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gslnls_sparse_result_free": (None, [C.POINTER(SparseResult)]),
     "gslnls_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "gslnls_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "gslnls_comm_create_local": (C.c_int, [C.c_int, c_int_p, C.POINTER(C.c_void_p)]),

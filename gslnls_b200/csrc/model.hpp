@@ -36,6 +36,7 @@ struct Variant {
     cudaKernel_t pass = nullptr, materialise = nullptr;
     cudaKernel_t irls_hist = nullptr, irls_above = nullptr, irls_weights = nullptr, irls_scale = nullptr;
     cudaKernel_t persistent = nullptr; // nls_pass_persistent (TMA-ring variants only): one launch per fit
+    cudaKernel_t sparse_eval = nullptr; // nls_sparse_eval (symbolic Jacobian, p <= 16): term values + nonzeros of J
     bool loaded = false;
     size_t pass_smem = 0; // dynamic shared memory of one nls_pass CTA (tiled variant)
     std::vector<int> smem_devices; // devices on which the dynamic shared-memory limit has been raised

@@ -102,3 +102,20 @@ struct NlsIrlsParams {
     const double *userw;
     double h_df;
 };
+
+// Sparse-row problems (src/nls_large.c:528-648: the model returns J as a dgT/dgC/dgRMatrix).  A row of such a
+// model touches a handful of the P parameters; the compiled row function sees them as its local parameters
+// th[0..k), gathered per TERM from the global vector: th[s] = theta[slot_base[s] + (slot_index[s] ?
+// slot_index[s][t] : 0)].  One launch evaluates every term of a block and stores its value and its k partial
+// derivatives -- the nonzeros of J, slot-major so that every store is coalesced.
+#define NLS_SP_MAXSLOT 16
+struct NlsSparseEvalParams {
+    const double *vars[NLS_MAX_VARS];        // data columns of the block, nterms doubles each
+    const int *slot_index[NLS_SP_MAXSLOT];   // index column of local parameter s, or nullptr (scalar parameter)
+    int slot_base[NLS_SP_MAXSLOT];           // first global index of the parameter (vector) slot s refers to
+    long long nterms;
+    const double *theta;                     // [P] global parameters (device)
+    double *tv;                              // [nterms] term values
+    double *jv;                              // [k][nterms] partial derivatives
+    unsigned long long *nbad;                // [2] += terms whose value / whose derivatives are not finite
+};

@@ -1530,3 +1530,40 @@ extern "C" __global__ void __launch_bounds__(256) nls_irls_scale(const NlsIrlsPa
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < prm.n; i += stride)
         prm.wout[i] = prm.wout[i] * prm.scale * (prm.userw ? prm.userw[i] : 1.0);
 }
+
+// ---------------------------------------------------------------- sparse-row problems: term evaluation
+// (csrc/sparse.cu holds the model-independent part: row sums, J d, J^T u, the matrix-free cgst solver)
+#if GSLNLS_JAC_MODE == 0 && GSLNLS_P <= NLS_SP_MAXSLOT
+extern "C" __global__ void __launch_bounds__(256) nls_sparse_eval(const NlsSparseEvalParams prm)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned int badf = 0, badj = 0;
+    nls_exp_init();
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < prm.nterms; t += stride) {
+        double th[NLS_P], xa[NLS_NV], f, J[NLS_P];
+#pragma unroll
+        for (int s = 0; s < NLS_P; ++s) {
+            const int *ix = prm.slot_index[s];
+            th[s] = prm.theta[prm.slot_base[s] + (ix ? ix[t] : 0)];
+        }
+#pragma unroll
+        for (int k = 0; k < GSLNLS_NVAR; ++k)
+            xa[k] = prm.vars[k][t];
+        nls_model_fj(th, xa, f, J);
+        const bool okf = nls_finite(f);
+        prm.tv[t] = okf ? f : NLS_INF; // a non-finite value makes the residual +Inf, src/nls_large.c:464-465
+        bool okj = true;
+#pragma unroll
+        for (int s = 0; s < NLS_P; ++s) {
+            okj = okj && nls_finite(J[s]);
+            prm.jv[(long long)s * prm.nterms + t] = J[s];
+        }
+        badf += okf ? 0u : 1u;
+        badj += okj ? 0u : 1u; // -> GSL_EBADFUNC when this Jacobian is adopted, src/nls_large.c:560-566
+    }
+    if (badf)
+        atomicAdd(prm.nbad, (unsigned long long)badf);
+    if (badj)
+        atomicAdd(prm.nbad + 1, (unsigned long long)badj);
+}
+#endif

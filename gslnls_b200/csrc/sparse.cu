@@ -1,0 +1,1143 @@
+// sparse.cu -- sparse-row problems: gsl_nls_large() with a sparse Jacobian (src/nls_large.c:528-648) on the GPU.
+//
+// The reference lets the model return J as a dgT/dgC/dgRMatrix (R/nls_large.R:397-404), rebuilds a triplet
+// gsl_spmatrix from it on every callback (src/nls_large.c:575-622), applies it with gsl_spblas_dgemv (:638) and
+// densifies it for dsyrk whenever the solver wants J^T J (:641-648).  README Example 4 (Penalty function I,
+// p = 500) and inst/unit_tests/unit_tests_gslnls.R:302-346 are its use cases: many parameters, each row touching
+// a few of them.  R closures cannot run here, so the structure comes in as data:
+//
+//   * a problem is a list of BLOCKS; a block is a compiled row formula in k <= 16 local parameters plus, per local
+//     parameter, where it lives in the global vector: a fixed index, or base + an int32 index column (one entry
+//     per term).  "A[g] * exp(-lam * x)" with a group column g is one block; Penalty I is two;
+//   * every term belongs to a row (identity by default); a row is the SUM of its terms minus y_row -- that is how
+//     a dense row such as sum(theta^2) - 0.25 is expressed: p one-parameter terms that share a row.
+//
+// K-sp1  nls_sparse_eval (NVRTC, nls_pass_kernel.cuh): term values and the nonzeros of J, coalesced, per block.
+// K-sp2  sp_step (this file, one cooperative launch per trial point): everything else of
+//        gsl_multilarge_nlinear_iterate / _test / driver2 for trs = cgst -- residual rows, J^T f, diag(J^T J),
+//        More' scaling, the Steihaug-Toint iteration with J d and J^T (J d) applied from the stored nonzeros
+//        (matrix-free, like GSL's cgst.c which calls the df callback twice per CG iteration), rho, accept / reject,
+//        convergence tests.  Vectors of length P and R live in global memory; scalars are recomputed by every
+//        thread from the same deterministic partial sums, so the whole grid takes the same branches and the only
+//        synchronisation is grid.sync() between phases.  No atomics on data: row sums and column sums are
+//        segmented gathers over index lists built once on the host (entries sorted by row / by column, cut into
+//        items of <= 2048 entries, one warp per item, items of a segment added in order) -- run-to-run bitwise
+//        reproducible like the dense path.
+//
+// Algorithms other than cgst need a dense P x P factorisation and stay on the dense path (P <= 64).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gslnls_b200.h"
+#include "model.hpp"
+#include "nls_abi.h"
+
+namespace cg = cooperative_groups;
+
+namespace gslnls {
+extern thread_local std::string g_last_error;
+void set_error(const std::string &s);
+} // namespace gslnls
+using namespace gslnls;
+
+namespace {
+
+constexpr int SP_BLOCK = 256;
+constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
+constexpr int SP_NRED = 6;    // scalar reduction slots
+
+enum { SP_PH_INIT = 0, SP_PH_TRIAL = 1, SP_PH_DONE = 2 };
+
+struct SpBlockDev {
+    long long term0, nterms, ent0;
+    int k, pad;
+};
+
+// a family of segmented sums: entries grouped by segment (row or column), cut into items
+struct SpSeg {
+    const int *ent_a;            // per entry: gather index (row sums: term id; column sums: position in jv)
+    const int *ent_b;            // per entry: row id (column sums) or nullptr
+    const long long *item_begin; // [nitems + 1] entry ranges
+    const int *seg_itemptr;      // [nseg + 1] item ranges of each segment
+    int nitems, nseg;
+    double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
+};
+
+struct SpState {
+    int phase, cur;      // what the next launch finds; index of the buffers (tv, jv, f) that hold the accepted point
+    int iter, niter;     // driver2's counter, gsl_multilarge_nlinear_niter
+    int bad_steps;
+    int conv, info;      // final status / convergence reason
+    int pad_;
+    double delta, normf; // trust radius, ||f(x)||
+    double chisq0, chisq1, chisq_init;
+    long long nevalf, nevaldfu, nevaldf2, cg_iters;
+};
+
+struct SpDev {
+    int P, R, nblocks, maxiter, scale, want_trace;
+    long long T, E;
+    long long cg_maxit;
+    double factor_up, factor_down, xtol, gtol, cg_tol;
+    const SpBlockDev *blocks;
+    const int *ecol;   // [E] column (global parameter) of every stored nonzero
+    const double *y;   // [R] or nullptr (zeros)
+    const double *sw;  // [R] sqrt(weights) or nullptr
+    double *tv[2], *jv[2];
+    unsigned long long *nbad[2]; // per buffer: {non-finite values, non-finite derivatives}
+    SpSeg rows, cols;            // rows.ent_a == nullptr: one term per row, term t is row t
+    double *tmpT, *f[2], *workn;
+    double *x, *x_trial, *dx, *g, *diag, *z, *r, *d, *jjj, *wp;
+    double *red;       // [SP_NRED][gridDim.x]
+    SpState *st;       // device
+    SpState *host_st;  // mapped host copy written at the end of every launch
+    double *ssrtrace;  // [maxiter + 1]
+    double *jtj;       // [P * P] column-major, filled by sp_jtj on request
+};
+
+// ------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ double sp_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the CTA, every thread gets it; fixed association (lanes by xor tree, warps in order)
+__device__ double sp_block_sum(double v, double *sm)
+{
+    v = sp_warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+        sm[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < SP_BLOCK / 32; ++i)
+        s += sm[i];
+    __syncthreads();
+    return s;
+}
+__device__ void sp_put(const SpDev &S, int slot, double v, double *sm)
+{
+    const double s = sp_block_sum(v, sm);
+    if (threadIdx.x == 0)
+        S.red[(size_t)slot * gridDim.x + blockIdx.x] = s;
+}
+// after a grid.sync(): the grid-wide sum, identical in every thread of every CTA
+__device__ double sp_total(const SpDev &S, int slot, double *sm)
+{
+    double v = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += SP_BLOCK)
+        v += S.red[(size_t)slot * gridDim.x + i];
+    return sp_block_sum(v, sm);
+}
+__device__ double sp_block_max(double v, double *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+        sm[w] = v;
+    __syncthreads();
+    double s = sm[0];
+    for (int i = 1; i < SP_BLOCK / 32; ++i)
+        s = fmax(s, sm[i]);
+    __syncthreads();
+    return s;
+}
+
+#define SP_GTID ((long long)blockIdx.x * SP_BLOCK + threadIdx.x)
+#define SP_GSTRIDE ((long long)gridDim.x * SP_BLOCK)
+
+// u_t = sum_s J[t, s] * vec[col(t, s)] / (dscale ? dscale[col] : 1) for every term -> S.tmpT   (first half of J v)
+__device__ void sp_term_dot(const SpDev &S, const double *jv, const double *vec, const double *dscale)
+{
+    for (int b = 0; b < S.nblocks; ++b) {
+        const SpBlockDev B = S.blocks[b];
+        for (long long t = SP_GTID; t < B.nterms; t += SP_GSTRIDE) {
+            double u = 0.0;
+            for (int s = 0; s < B.k; ++s) {
+                const long long e = B.ent0 + (long long)s * B.nterms + t;
+                const int c = S.ecol[e];
+                const double v = dscale ? vec[c] / dscale[c] : vec[c];
+                u = fma(jv[e], v, u);
+            }
+            S.tmpT[B.term0 + t] = u;
+        }
+    }
+}
+
+// items of a segmented sum: one warp per item, lanes stride the item's entries, xor tree at the end
+template <int KIND> // 0: rows (value = src[ent_a]); 1: columns (value = jv[ent_a] * wv[ent_b], and squares)
+__device__ void sp_items(const SpSeg &G, const double *src, const double *wv, const double *sw, bool squares)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = SP_GTID >> 5, nwarp = SP_GSTRIDE >> 5;
+    for (long long it = warp; it < G.nitems; it += nwarp) {
+        const long long a = G.item_begin[it], b = G.item_begin[it + 1];
+        double s = 0.0, s2 = 0.0;
+        for (long long e = a + lane; e < b; e += 32) {
+            if (KIND == 0) {
+                s += src[G.ent_a[e]];
+            } else {
+                const int row = G.ent_b[e];
+                const double j = sw ? src[G.ent_a[e]] * sw[row] : src[G.ent_a[e]];
+                if (wv)
+                    s = fma(j, wv[row], s);
+                if (squares)
+                    s2 = fma(j, j, s2);
+            }
+        }
+        s = sp_warp_sum(s);
+        if (squares)
+            s2 = sp_warp_sum(s2);
+        if (lane == 0) {
+            G.ipart[it] = s;
+            if (squares)
+                G.ipart2[it] = s2;
+        }
+    }
+}
+__device__ __forceinline__ double sp_seg_total(const SpSeg &G, const double *ipart, int seg)
+{
+    double s = 0.0;
+    for (int i = G.seg_itemptr[seg]; i < G.seg_itemptr[seg + 1]; ++i)
+        s += ipart[i];
+    return s;
+}
+
+// out_r = sw_r * (sum of the row's terms - y_r); sum of squares -> reduction slot.  Contains one grid.sync()
+// when rows aggregate terms.
+__device__ void sp_rowsum(cg::grid_group &grid, const SpDev &S, const double *tsrc, double *out, bool sub_y, int slot,
+                          double *sm)
+{
+    const bool ident = S.rows.ent_a == nullptr;
+    if (!ident) {
+        sp_items<0>(S.rows, tsrc, nullptr, nullptr, false);
+        grid.sync();
+    }
+    double acc = 0.0;
+    for (long long r = SP_GTID; r < S.R; r += SP_GSTRIDE) {
+        double v = ident ? tsrc[r] : sp_seg_total(S.rows, S.rows.ipart, (int)r);
+        if (sub_y && S.y)
+            v -= S.y[r];
+        if (S.sw)
+            v *= S.sw[r];
+        out[r] = v;
+        acc = fma(v, v, acc);
+    }
+    sp_put(S, slot, acc, sm);
+}
+
+// g = J^T u (and jjj = diag(J^T J) when squares) from the nonzeros jv; u is a weighted row vector.  grid.sync()
+// inside; the caller syncs before using g.
+__device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv, const double *u, double *gout,
+                          bool squares)
+{
+    sp_items<1>(S.cols, jv, u, S.sw, squares);
+    grid.sync();
+    for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        if (gout)
+            gout[k] = sp_seg_total(S.cols, S.cols.ipart, (int)k);
+        if (squares)
+            S.jjj[k] = sp_seg_total(S.cols, S.cols.ipart2, (int)k);
+    }
+}
+
+// Steihaug-Toint step: GSL multilarge_nlinear/cgst.c, statement order of the restatement in
+// oracle/multilarge.c:994-1060.  Returns 0 with dx and x_trial written, or GSLNLS_EMAXITER.
+__device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, double delta, long long &cg_iters,
+                       long long &ndfu, double *sm)
+{
+    // z = 0, r = d = -D^-1 g
+    double acc = 0.0;
+    for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        const double v = S.g[k] / S.diag[k];
+        S.z[k] = 0.0;
+        S.r[k] = -v;
+        S.d[k] = -v;
+        acc = fma(v, v, acc);
+    }
+    sp_put(S, 0, acc, sm);
+    grid.sync();
+    double norm_r2 = sp_total(S, 0, sm);
+    const double cg_norm_g = sqrt(norm_r2);
+    int exit_kind = -1; // 0: z / D, 1: (z + tau d) / D
+    double tau = 0.0;
+    int status = 0;
+    for (long long it = 0;; ++it) {
+        if (it >= S.cg_maxit) {
+            exit_kind = 0;
+            status = GSLNLS_EMAXITER;
+            break;
+        }
+        ++cg_iters;
+        // workn = J D^-1 d
+        sp_term_dot(S, jv, S.d, S.diag);
+        grid.sync();
+        sp_rowsum(grid, S, S.tmpT, S.workn, false, 0, sm);
+        ++ndfu;
+        double zz = 0.0, dd = 0.0, zd = 0.0;
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+            const double zk = S.z[k], dk = S.d[k];
+            zz = fma(zk, zk, zz);
+            dd = fma(dk, dk, dd);
+            zd = fma(zk, dk, zd);
+        }
+        sp_put(S, 1, zz, sm);
+        sp_put(S, 2, dd, sm);
+        sp_put(S, 3, zd, sm);
+        grid.sync();
+        const double normJd2 = sp_total(S, 0, sm);
+        zz = sp_total(S, 1, sm);
+        dd = sp_total(S, 2, sm);
+        zd = sp_total(S, 3, sm);
+        // tau of cgst_calc_tau: the positive root of ||z + tau d|| = delta
+        const double norm_p = sqrt(zz), norm_q = sqrt(dd);
+        const double t1 = zd / (norm_q * norm_q);
+        const double t2 = t1 * zd + (delta + norm_p) * (delta - norm_p);
+        const double tau_b = -t1 + sqrt(t2) / norm_q;
+        if (normJd2 == 0.0) {
+            exit_kind = 1;
+            tau = tau_b;
+            break;
+        }
+        const double alpha = norm_r2 / normJd2; // (||r|| / ||J D^-1 d||)^2
+        const double znew2 = zz + alpha * (2.0 * zd + alpha * dd);
+        if (sqrt(fmax(znew2, 0.0)) >= delta) {
+            exit_kind = 1;
+            tau = tau_b;
+            break;
+        }
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+            S.z[k] = fma(alpha, S.d[k], S.z[k]);
+        // r -= alpha D^-1 J^T workn
+        sp_colsum(grid, S, jv, S.workn, S.wp, false);
+        ++ndfu;
+        // (same threads wrote wp[k] and read it: the k loops of colsum and this one use the same mapping)
+        acc = 0.0;
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+            const double rk = S.r[k] - (S.wp[k] / S.diag[k]) * alpha;
+            S.r[k] = rk;
+            acc = fma(rk, rk, acc);
+        }
+        sp_put(S, 0, acc, sm);
+        grid.sync();
+        const double norm_rp1_2 = sp_total(S, 0, sm);
+        if (sqrt(norm_rp1_2) / cg_norm_g < S.cg_tol) {
+            exit_kind = 0;
+            break;
+        }
+        const double beta = norm_rp1_2 / norm_r2;
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+            S.d[k] = fma(beta, S.d[k], S.r[k]);
+        norm_r2 = norm_rp1_2;
+        grid.sync();
+    }
+    for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        const double v = (exit_kind == 1 ? fma(tau, S.d[k], S.z[k]) : S.z[k]) / S.diag[k];
+        S.dx[k] = v;
+        S.x_trial[k] = S.x[k] + v;
+    }
+    grid.sync();
+    return status;
+}
+
+// gsl_multilarge_nlinear_test (convergence.c) on x, dx, g, ||f||: 0 continue, 1 step, 2 gradient
+__device__ int sp_test(cg::grid_group &grid, const SpDev &S, double normf, double *sm)
+{
+    double viol = 0.0, gmax = 0.0;
+    for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        const double xk = S.x[k];
+        const double tol = S.xtol * S.xtol + S.xtol * fabs(xk);
+        if (!(fabs(S.dx[k]) < tol))
+            viol = 1.0;
+        gmax = fmax(gmax, fabs(fmax(xk, 1.0) * S.g[k]));
+    }
+    viol = sp_block_max(viol, sm);
+    gmax = sp_block_max(gmax, sm);
+    if (threadIdx.x == 0) {
+        S.red[(size_t)4 * gridDim.x + blockIdx.x] = viol;
+        S.red[(size_t)5 * gridDim.x + blockIdx.x] = gmax;
+    }
+    grid.sync();
+    viol = 0.0;
+    gmax = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += SP_BLOCK) {
+        viol = fmax(viol, S.red[(size_t)4 * gridDim.x + i]);
+        gmax = fmax(gmax, S.red[(size_t)5 * gridDim.x + i]);
+    }
+    viol = sp_block_max(viol, sm);
+    gmax = sp_block_max(gmax, sm);
+    if (viol == 0.0)
+        return 1;
+    const double phi = 0.5 * normf * normf;
+    if (gmax <= S.gtol * fmax(phi, 1.0))
+        return 2;
+    return 0;
+}
+
+// J^T f and diag(J^T J) at the accepted point, scaling update (GSL scaling.c)
+__device__ void sp_gradient_and_scale(cg::grid_group &grid, const SpDev &S, const double *jv, const double *f, bool init)
+{
+    sp_colsum(grid, S, jv, f, S.g, true);
+    for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        const double Jjj = S.jjj[k];
+        const double norm = (Jjj <= 0.0) ? 1.0 : sqrt(Jjj);
+        double dk;
+        if (S.scale == 1) // levenberg
+            dk = 1.0;
+        else if (S.scale == 2) // marquardt
+            dk = norm;
+        else // more
+            dk = init ? fmax(0.0, norm) : fmax(S.diag[k], norm);
+        S.diag[k] = dk;
+    }
+    grid.sync();
+}
+
+__global__ void __launch_bounds__(SP_BLOCK) sp_step(const SpDev S)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[SP_BLOCK / 32];
+    SpState st = *S.st;
+    grid.sync(); // every thread holds its copy before thread 0 rewrites the state at the end
+    int cur = st.cur;
+    bool done = false, need_step = false;
+    int iterate_status = 0;
+    bool end_iter = false;
+
+    if (st.phase == SP_PH_INIT) {
+        // trust_init (oracle/multilarge.c:1104-1140): f, g = J^T f, J^T J (its diagonal), D, delta
+        sp_rowsum(grid, S, S.tv[cur], S.f[cur], true, 0, sm);
+        ++st.nevalf;
+        grid.sync();
+        const double ff = sp_total(S, 0, sm);
+        st.normf = sqrt(ff);
+        st.chisq_init = st.chisq1 = ff;
+        if (S.want_trace && SP_GTID == 0)
+            S.ssrtrace[0] = ff;
+        if (S.nbad[cur][1] != 0) { // Missing/infinite values not allowed when evaluating jac (src/nls_large.c:560)
+            st.conv = st.info = GSLNLS_EBADFUNC;
+            done = true;
+        } else {
+            sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], true);
+            ++st.nevaldfu;
+            ++st.nevaldf2;
+            double acc = 0.0;
+            for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+                const double v = S.diag[k] * S.x[k];
+                acc = fma(v, v, acc);
+                S.dx[k] = 0.0;
+            }
+            sp_put(S, 0, acc, sm);
+            grid.sync();
+            st.delta = 0.3 * fmax(1.0, sqrt(sp_total(S, 0, sm)));
+            st.chisq0 = st.chisq1; // driver2: first iterate call
+            st.bad_steps = 0;
+            if (S.maxiter == 0) { // evaluation only (gslnls_sparse_eval)
+                st.conv = st.info = 0;
+                done = true;
+            } else {
+                need_step = true;
+            }
+        }
+    } else {
+        // the trial point has been evaluated into buffer 1 - cur: trust_eval_step / accept / reject
+        const int tr = 1 - cur;
+        sp_rowsum(grid, S, S.tv[tr], S.f[tr], true, 0, sm);
+        ++st.nevalf;
+        // predicted reduction of the quadratic model: needs g . dx and ||J dx||^2 (J of the accepted point)
+        sp_term_dot(S, S.jv[cur], S.dx, nullptr);
+        double gdx = 0.0;
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+            gdx = fma(S.g[k], S.dx[k], gdx);
+        sp_put(S, 2, gdx, sm);
+        grid.sync();
+        const double ff_trial = sp_total(S, 0, sm);
+        gdx = sp_total(S, 2, sm);
+        sp_rowsum(grid, S, S.tmpT, S.workn, false, 1, sm);
+        grid.sync();
+        const double jdx2 = sp_total(S, 1, sm);
+        const double normf_trial = sqrt(ff_trial);
+        double rho;
+        if (!(normf_trial < st.normf)) {
+            rho = -1.0;
+        } else {
+            const double u = normf_trial / st.normf;
+            const double actual = 1.0 - u * u;
+            const double nf2 = st.normf * st.normf;
+            const double pred = -2.0 * gdx / nf2 - jdx2 / nf2;
+            rho = pred > 0.0 ? actual / pred : -1.0;
+        }
+        const bool found = rho > 0.0;
+        if (rho > 0.75)
+            st.delta *= S.factor_up;
+        else if (rho < 0.25)
+            st.delta /= S.factor_down;
+        if (found) {
+            cur = tr;
+            st.cur = cur;
+            for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+                S.x[k] = S.x_trial[k];
+            st.normf = normf_trial;
+            if (S.nbad[cur][1] != 0) {
+                iterate_status = GSLNLS_EBADFUNC;
+            } else {
+                sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], false);
+                ++st.nevaldfu;
+                ++st.nevaldf2;
+            }
+            end_iter = true;
+        } else if (++st.bad_steps > 15) {
+            iterate_status = GSLNLS_ENOPROG;
+            end_iter = true;
+        } else {
+            need_step = true;
+        }
+    }
+
+    while (!done) {
+        if (end_iter) {
+            // tail of gsl_multilarge_nlinear_iterate + the body of driver2 (src/nls_fit.c:153-224)
+            end_iter = false;
+            ++st.niter;
+            st.chisq1 = st.normf * st.normf;
+            if (iterate_status == GSLNLS_EBADFUNC || (iterate_status == GSLNLS_ENOPROG && st.iter == 0)) {
+                st.conv = st.info = iterate_status;
+                done = true;
+                break;
+            }
+            ++st.iter;
+            if (S.want_trace && SP_GTID == 0)
+                S.ssrtrace[st.iter] = st.chisq1;
+            grid.sync(); // x, g complete
+            const int info = sp_test(grid, S, st.normf, sm);
+            if (info) {
+                st.conv = 0;
+                st.info = info;
+                done = true;
+                break;
+            }
+            if (st.iter >= S.maxiter) {
+                st.conv = GSLNLS_EMAXITER;
+                st.info = 0;
+                done = true;
+                break;
+            }
+            st.chisq0 = st.chisq1;
+            st.bad_steps = 0;
+            iterate_status = 0;
+            need_step = true;
+        }
+        if (need_step) {
+            need_step = false;
+            grid.sync();
+            const int s = sp_cgst(grid, S, S.jv[cur], st.delta, st.cg_iters, st.nevaldfu, sm);
+            if (s == 0)
+                break; // x_trial is ready: the host evaluates it
+            // the step failed: rho = -1, shrink and retry (oracle/multilarge.c:1199-1225)
+            st.delta /= S.factor_down;
+            if (++st.bad_steps > 15) {
+                iterate_status = GSLNLS_ENOPROG;
+                end_iter = true;
+            } else {
+                need_step = true;
+            }
+        }
+    }
+    st.phase = done ? SP_PH_DONE : SP_PH_TRIAL;
+    if (SP_GTID == 0) {
+        *S.st = st;
+        *S.host_st = st;
+        __threadfence_system();
+    }
+}
+
+// J^T J column by column: column c is J^T (J e_c) -- P applications of the stored operator, each deterministic
+__global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[SP_BLOCK / 32];
+    for (int c = 0; c < S.P; ++c) {
+        for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+            S.d[k] = (k == c) ? 1.0 : 0.0;
+        grid.sync();
+        sp_term_dot(S, S.jv[cur], S.d, nullptr);
+        grid.sync();
+        sp_rowsum(grid, S, S.tmpT, S.workn, false, 0, sm);
+        grid.sync();
+        sp_colsum(grid, S, S.jv[cur], S.workn, S.jtj + (size_t)c * S.P, false);
+        grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+#define SPCK(call)                                                                                    \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e__));            \
+    } while (0)
+
+struct SpBlockHost {
+    const gslnls_model *m = nullptr;
+    Variant *var = nullptr;
+    int k = 0, nvar = 0;
+    long long nterms = 0, term0 = 0, ent0 = 0;
+    int base[NLS_SP_MAXSLOT] = {0};
+    std::vector<std::vector<int>> index; // per slot: empty = scalar parameter
+    std::vector<int> rows;               // empty: identity from row0
+    long long row0 = 0;
+    double *d_vars[NLS_MAX_VARS] = {nullptr};
+    int *d_index[NLS_SP_MAXSLOT] = {nullptr};
+};
+
+template <class T>
+T *sp_upload(const std::vector<T> &v)
+{
+    T *d = nullptr;
+    SPCK(cudaMalloc(&d, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty())
+        SPCK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+double *sp_dalloc(size_t n)
+{
+    double *d = nullptr;
+    SPCK(cudaMalloc(&d, std::max<size_t>(1, n) * sizeof(double)));
+    SPCK(cudaMemset(d, 0, std::max<size_t>(1, n) * sizeof(double)));
+    return d;
+}
+
+// entries sorted by segment (stable), cut into items of <= SP_ITEM
+struct SegBuild {
+    std::vector<int> ent_a, ent_b;
+    std::vector<long long> item_begin;
+    std::vector<int> seg_itemptr;
+};
+void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
+{
+    const size_t nseg = segptr.size() - 1;
+    B.seg_itemptr.assign(nseg + 1, 0);
+    B.item_begin.clear();
+    for (size_t s = 0; s < nseg; ++s) {
+        B.seg_itemptr[s] = (int)B.item_begin.size();
+        for (long long a = segptr[s]; a < segptr[s + 1]; a += SP_ITEM)
+            B.item_begin.push_back(a);
+    }
+    B.seg_itemptr[nseg] = (int)B.item_begin.size();
+    B.item_begin.push_back(segptr[nseg]);
+}
+
+} // namespace
+
+struct gslnls_sparse_problem {
+    int device = 0, P = 0;
+    long long R = 0, T = 0, E = 0;
+    std::vector<SpBlockHost> blocks;
+    std::vector<double> h_y, h_w;
+    bool finalized = false;
+    cudaStream_t stream = nullptr;
+    int grid = 0;
+    SpDev dev{};
+    SpState *h_state = nullptr; // mapped pinned
+    std::vector<void *> owned;  // device allocations
+    template <class T>
+    T *keep(T *p)
+    {
+        owned.push_back((void *)p);
+        return p;
+    }
+    ~gslnls_sparse_problem()
+    {
+        cudaSetDevice(device);
+        for (void *p : owned)
+            cudaFree(p);
+        if (h_state)
+            cudaFreeHost(h_state);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+void sp_finalize(gslnls_sparse_problem *sp)
+{
+    SPCK(cudaSetDevice(sp->device));
+    if (sp->blocks.empty())
+        throw std::runtime_error("sparse problem without blocks");
+    if (!sp->stream)
+        SPCK(cudaStreamCreateWithFlags(&sp->stream, cudaStreamNonBlocking));
+    // global numbering of terms and stored nonzeros
+    long long T = 0, E = 0;
+    bool ident = true;
+    for (auto &b : sp->blocks) {
+        b.term0 = T;
+        b.ent0 = E;
+        T += b.nterms;
+        E += b.nterms * b.k;
+        if (!b.rows.empty() || b.row0 != b.term0)
+            ident = false;
+    }
+    if (T != sp->R)
+        ident = false;
+    if (E >= (1ll << 31) || T >= (1ll << 31))
+        throw std::runtime_error("sparse problem too large: terms and nonzeros are indexed with 32 bits");
+    sp->T = T;
+    sp->E = E;
+    const int P = sp->P;
+    const long long R = sp->R;
+
+    // column of every nonzero, row of every term
+    std::vector<int> ecol((size_t)E), trow((size_t)T);
+    for (auto &b : sp->blocks) {
+        for (long long t = 0; t < b.nterms; ++t) {
+            const long long r = b.rows.empty() ? b.row0 + t : (long long)b.rows[(size_t)t];
+            if (r < 0 || r >= R)
+                throw std::runtime_error("row index out of range");
+            trow[(size_t)(b.term0 + t)] = (int)r;
+        }
+        for (int s = 0; s < b.k; ++s)
+            for (long long t = 0; t < b.nterms; ++t) {
+                const long long c = b.base[s] + (b.index[(size_t)s].empty() ? 0 : (long long)b.index[(size_t)s][(size_t)t]);
+                if (c < 0 || c >= P)
+                    throw std::runtime_error("parameter index out of range");
+                ecol[(size_t)(b.ent0 + (long long)s * b.nterms + t)] = (int)c;
+            }
+    }
+    // rows: terms sorted by row (stable counting sort) unless every row is exactly its own term
+    SegBuild rb, cb;
+    if (!ident) {
+        std::vector<long long> ptr((size_t)R + 1, 0);
+        for (long long t = 0; t < T; ++t)
+            ++ptr[(size_t)trow[(size_t)t] + 1];
+        for (long long r = 0; r < R; ++r)
+            ptr[(size_t)r + 1] += ptr[(size_t)r];
+        rb.ent_a.resize((size_t)T);
+        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+        for (long long t = 0; t < T; ++t)
+            rb.ent_a[(size_t)fill[(size_t)trow[(size_t)t]]++] = (int)t;
+        seg_finish(rb, ptr);
+    }
+    // columns: nonzeros sorted by column, each with its row
+    {
+        std::vector<long long> ptr((size_t)P + 1, 0);
+        for (long long e = 0; e < E; ++e)
+            ++ptr[(size_t)ecol[(size_t)e] + 1];
+        for (int k = 0; k < P; ++k)
+            ptr[(size_t)k + 1] += ptr[(size_t)k];
+        cb.ent_a.resize((size_t)E);
+        cb.ent_b.resize((size_t)E);
+        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
+        for (auto &b : sp->blocks)
+            for (int s = 0; s < b.k; ++s)
+                for (long long t = 0; t < b.nterms; ++t) {
+                    const long long e = b.ent0 + (long long)s * b.nterms + t;
+                    const long long pos = fill[(size_t)ecol[(size_t)e]]++;
+                    cb.ent_a[(size_t)pos] = (int)e;
+                    cb.ent_b[(size_t)pos] = trow[(size_t)(b.term0 + t)];
+                }
+        seg_finish(cb, ptr);
+    }
+
+    SpDev &D = sp->dev;
+    D = SpDev{};
+    D.P = P;
+    D.R = (int)R;
+    D.T = T;
+    D.E = E;
+    D.nblocks = (int)sp->blocks.size();
+    std::vector<SpBlockDev> bd;
+    for (auto &b : sp->blocks)
+        bd.push_back(SpBlockDev{b.term0, b.nterms, b.ent0, b.k, 0});
+    D.blocks = sp->keep(sp_upload(bd));
+    D.ecol = sp->keep(sp_upload(ecol));
+    if (!sp->h_y.empty())
+        D.y = sp->keep(sp_upload(sp->h_y));
+    if (!sp->h_w.empty()) {
+        std::vector<double> sw(sp->h_w.size());
+        for (size_t i = 0; i < sw.size(); ++i)
+            sw[i] = std::sqrt(sp->h_w[i]); // sqrt_wts_i = sqrt(w_i), src/fdf.c:60-64
+        D.sw = sp->keep(sp_upload(sw));
+    }
+    for (int i = 0; i < 2; ++i) {
+        D.tv[i] = sp->keep(sp_dalloc((size_t)T));
+        D.jv[i] = sp->keep(sp_dalloc((size_t)E));
+        D.f[i] = sp->keep(sp_dalloc((size_t)R));
+        unsigned long long *nb = nullptr;
+        SPCK(cudaMalloc(&nb, 2 * sizeof(unsigned long long)));
+        D.nbad[i] = sp->keep(nb);
+    }
+    if (!ident) {
+        D.rows.ent_a = sp->keep(sp_upload(rb.ent_a));
+        D.rows.item_begin = sp->keep(sp_upload(rb.item_begin));
+        D.rows.seg_itemptr = sp->keep(sp_upload(rb.seg_itemptr));
+        D.rows.nitems = (int)rb.item_begin.size() - 1;
+        D.rows.nseg = (int)R;
+        D.rows.ipart = sp->keep(sp_dalloc((size_t)D.rows.nitems));
+    }
+    D.cols.ent_a = sp->keep(sp_upload(cb.ent_a));
+    D.cols.ent_b = sp->keep(sp_upload(cb.ent_b));
+    D.cols.item_begin = sp->keep(sp_upload(cb.item_begin));
+    D.cols.seg_itemptr = sp->keep(sp_upload(cb.seg_itemptr));
+    D.cols.nitems = (int)cb.item_begin.size() - 1;
+    D.cols.nseg = P;
+    D.cols.ipart = sp->keep(sp_dalloc((size_t)D.cols.nitems));
+    D.cols.ipart2 = sp->keep(sp_dalloc((size_t)D.cols.nitems));
+    D.tmpT = sp->keep(sp_dalloc((size_t)T));
+    D.workn = sp->keep(sp_dalloc((size_t)R));
+    double **pv[] = {&D.x, &D.x_trial, &D.dx, &D.g, &D.diag, &D.z, &D.r, &D.d, &D.jjj, &D.wp};
+    for (double **q : pv)
+        *q = sp->keep(sp_dalloc((size_t)P));
+
+    // grid of the cooperative solver kernel: every CTA resident, no more CTAs than the problem can use
+    int dev_sms = 0, occ = 0;
+    SPCK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, sp->device));
+    SPCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sp_step, SP_BLOCK, 0));
+    const long long work = std::max<long long>(std::max<long long>(E, T), std::max<long long>(P, R));
+    const long long want = (work + SP_BLOCK * 4 - 1) / (SP_BLOCK * 4);
+    sp->grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)dev_sms * std::min(occ, 4)));
+    D.red = sp->keep(sp_dalloc((size_t)SP_NRED * (size_t)sp->grid));
+    SpState *st = nullptr;
+    SPCK(cudaMalloc(&st, sizeof(SpState)));
+    D.st = sp->keep(st);
+    if (!sp->h_state)
+        SPCK(cudaHostAlloc(&sp->h_state, sizeof(SpState), cudaHostAllocMapped));
+    SPCK(cudaHostGetDevicePointer((void **)&D.host_st, sp->h_state, 0));
+
+    // block data and kernels
+    for (auto &b : sp->blocks) {
+        const KernelTune t = default_tune(b.k);
+        b.var = &const_cast<gslnls_model *>(b.m)->load(
+            VariantKey{0, 2, 1, t.block, t.unroll, t.minb, t.tiled, t.stages, t.prefetch, t.fexp});
+        if (!b.var->sparse_eval)
+            throw std::runtime_error("the model has no sparse evaluation kernel (symbolic Jacobian, <= 16 parameters)");
+    }
+    sp->finalized = true;
+}
+
+void sp_launch_evals(gslnls_sparse_problem *sp, const double *theta, int buf)
+{
+    const SpDev &D = sp->dev;
+    SPCK(cudaMemsetAsync(D.nbad[buf], 0, 2 * sizeof(unsigned long long), sp->stream));
+    int dev_sms = 0;
+    SPCK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, sp->device));
+    for (auto &b : sp->blocks) {
+        NlsSparseEvalParams prm;
+        std::memset(&prm, 0, sizeof prm);
+        for (int v = 0; v < b.nvar; ++v)
+            prm.vars[v] = b.d_vars[v];
+        for (int s = 0; s < b.k; ++s) {
+            prm.slot_index[s] = b.d_index[s];
+            prm.slot_base[s] = b.base[s];
+        }
+        prm.nterms = b.nterms;
+        prm.theta = theta;
+        prm.tv = D.tv[buf] + b.term0;
+        prm.jv = D.jv[buf] + b.ent0;
+        prm.nbad = D.nbad[buf];
+        const long long blocks = std::max<long long>(1, std::min<long long>((b.nterms + 255) / 256, (long long)dev_sms * 8));
+        void *args[] = {&prm};
+        SPCK(cudaLaunchKernel((const void *)b.var->sparse_eval, dim3((unsigned)blocks), dim3(256), args, 0, sp->stream));
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+GSLNLS_API int gslnls_sparse_create(int device, int p_total, int64_t nrows, gslnls_sparse_problem **out)
+{
+    if (!out || p_total < 1 || nrows < 1 || nrows >= (1ll << 31)) {
+        set_error("invalid argument");
+        return GSLNLS_EINVAL;
+    }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        set_error("no usable CUDA device (this library has no CPU path)");
+        return GSLNLS_ENODEVICE;
+    }
+    auto *sp = new gslnls_sparse_problem();
+    sp->device = device;
+    sp->P = p_total;
+    sp->R = nrows;
+    *out = sp;
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API void gslnls_sparse_free(gslnls_sparse_problem *sp) { delete sp; }
+
+GSLNLS_API int gslnls_sparse_add_block(gslnls_sparse_problem *sp, const gslnls_model *m, int64_t nterms,
+                                       const double *const *vars, const int *slot_base,
+                                       const int *const *slot_index, const int *rows, int64_t row0)
+{
+    if (!sp || !m || nterms < 1 || !slot_base || sp->finalized) {
+        set_error("invalid argument");
+        return GSLNLS_EINVAL;
+    }
+    if (m->p > NLS_SP_MAXSLOT || m->spec.jac_mode != GSLNLS_JAC_SYMBOLIC) {
+        set_error("a sparse block needs a model with a symbolic Jacobian and at most 16 (local) parameters");
+        return GSLNLS_EINVAL;
+    }
+    try {
+        SPCK(cudaSetDevice(sp->device));
+        SpBlockHost b;
+        b.m = m;
+        b.k = m->p;
+        b.nvar = m->nvar;
+        b.nterms = nterms;
+        b.row0 = row0;
+        b.index.resize((size_t)b.k);
+        for (int s = 0; s < b.k; ++s) {
+            b.base[s] = slot_base[s];
+            if (slot_index && slot_index[s]) {
+                b.index[(size_t)s].assign(slot_index[s], slot_index[s] + nterms);
+                b.d_index[s] = sp->keep(sp_upload(b.index[(size_t)s]));
+            }
+        }
+        if (rows)
+            b.rows.assign(rows, rows + nterms);
+        for (int v = 0; v < b.nvar; ++v) {
+            if (!vars || !vars[v])
+                throw std::runtime_error("missing data column");
+            double *d = nullptr;
+            SPCK(cudaMalloc(&d, (size_t)nterms * sizeof(double)));
+            sp->keep(d);
+            SPCK(cudaMemcpy(d, vars[v], (size_t)nterms * sizeof(double), cudaMemcpyHostToDevice));
+            b.d_vars[v] = d;
+        }
+        sp->blocks.push_back(std::move(b));
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return GSLNLS_ECUDA;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_sparse_set_response(gslnls_sparse_problem *sp, const double *y, const double *weights)
+{
+    if (!sp || sp->finalized) {
+        set_error("invalid argument");
+        return GSLNLS_EINVAL;
+    }
+    sp->h_y.clear();
+    sp->h_w.clear();
+    if (y)
+        sp->h_y.assign(y, y + sp->R);
+    if (weights) {
+        for (long long i = 0; i < sp->R; ++i)
+            if (!(weights[i] > 0.0)) {
+                set_error("missing or non-positive weights not allowed");
+                return GSLNLS_EINVAL;
+            }
+        sp->h_w.assign(weights, weights + sp->R);
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int gslnls_sparse_finalize(gslnls_sparse_problem *sp)
+{
+    if (!sp || sp->finalized) {
+        set_error("invalid argument");
+        return GSLNLS_EINVAL;
+    }
+    try {
+        sp_finalize(sp);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return GSLNLS_ECUDA;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+GSLNLS_API int64_t gslnls_sparse_nnz(const gslnls_sparse_problem *sp) { return sp ? sp->E : 0; }
+
+GSLNLS_API void gslnls_sparse_result_free(gslnls_sparse_result *r)
+{
+    if (!r)
+        return;
+    std::free(r->par);
+    std::free(r->ssrtrace);
+    std::free(r->grad_vec);
+    std::free(r->jtj);
+    std::free(r->resid);
+    std::memset(r, 0, sizeof *r);
+}
+
+GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start, const int *control_int,
+                                 const double *control_dbl, int want_jtj, int want_resid, gslnls_sparse_result *out)
+{
+    if (!sp || !start || !control_int || !control_dbl || !out || !sp->finalized) {
+        set_error("invalid argument (finalize the problem first)");
+        return GSLNLS_EINVAL;
+    }
+    std::memset(out, 0, sizeof *out);
+    if (control_int[0] < 1) {
+        set_error("maxiter must be >= 1");
+        return GSLNLS_EINVAL;
+    }
+    if (control_int[2] != 5) {
+        set_error("sparse-row problems run algorithm = \"cgst\" (Steihaug-Toint, matrix-free); the other trust-region "
+                  "methods factor a dense J^T J and are available on the dense path (p <= 64)");
+        return GSLNLS_EINVAL;
+    }
+    if (sp->R < sp->P) {
+        set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
+        return GSLNLS_EINVAL;
+    }
+    try {
+        SPCK(cudaSetDevice(sp->device));
+        SpDev &D = sp->dev;
+        const int P = sp->P;
+        D.maxiter = control_int[0];
+        D.want_trace = control_int[1] ? 1 : 0;
+        D.scale = control_int[3];
+        D.factor_up = control_dbl[0];
+        D.factor_down = control_dbl[1];
+        D.xtol = control_dbl[5];
+        D.gtol = control_dbl[7];
+        D.cg_tol = 1.0e-6;     // GSL default
+        D.cg_maxit = sp->R;    // GSL default: n
+        double *d_trace = nullptr;
+        SPCK(cudaMalloc(&d_trace, ((size_t)D.maxiter + 1) * sizeof(double)));
+        D.ssrtrace = d_trace;
+        struct Free {
+            double *p, *q = nullptr;
+            ~Free()
+            {
+                cudaFree(p);
+                cudaFree(q);
+            }
+        } guard{d_trace};
+        SPCK(cudaMemsetAsync(d_trace, 0, ((size_t)D.maxiter + 1) * sizeof(double), sp->stream));
+        SPCK(cudaMemcpyAsync(D.x, start, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, sp->stream));
+        SpState st{};
+        st.phase = SP_PH_INIT;
+        SPCK(cudaMemcpyAsync(D.st, &st, sizeof st, cudaMemcpyHostToDevice, sp->stream));
+        *sp->h_state = st;
+        sp_launch_evals(sp, D.x, 0);
+        long long launches = 0;
+        for (;;) {
+            void *args[] = {&D};
+            SPCK(cudaLaunchCooperativeKernel((const void *)sp_step, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
+                                             sp->stream));
+            ++launches;
+            SPCK(cudaStreamSynchronize(sp->stream));
+            st = *sp->h_state;
+            if (st.phase == SP_PH_DONE)
+                break;
+            sp_launch_evals(sp, D.x_trial, 1 - st.cur);
+        }
+        out->p = P;
+        out->nrows = sp->R;
+        out->nterms = sp->T;
+        out->nnz = sp->E;
+        out->niter = st.niter;
+        out->conv = st.conv;
+        out->info = st.info;
+        out->status = gslnls_strerror(st.conv);
+        out->ssr = st.chisq1;
+        out->ssrtol = st.chisq0 - st.chisq1;
+        out->chisq_init = st.chisq_init;
+        out->neval[0] = st.nevalf;
+        out->neval[1] = st.nevaldfu;
+        out->neval[2] = st.nevaldf2;
+        out->neval[3] = 0;
+        out->cg_iters = st.cg_iters;
+        out->launches = launches;
+        out->par = (double *)std::malloc((size_t)P * sizeof(double));
+        out->grad_vec = (double *)std::malloc((size_t)P * sizeof(double));
+        SPCK(cudaMemcpy(out->par, D.x, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost));
+        SPCK(cudaMemcpy(out->grad_vec, D.g, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost));
+        if (st.conv != 0 && st.conv != GSLNLS_EMAXITER) // failure: the start values come back (src/nls_large.c:293-302)
+            std::memcpy(out->par, start, (size_t)P * sizeof(double));
+        if (D.want_trace) {
+            out->ntrace = D.maxiter + 1;
+            out->ssrtrace = (double *)std::malloc(((size_t)D.maxiter + 1) * sizeof(double));
+            SPCK(cudaMemcpy(out->ssrtrace, d_trace, ((size_t)D.maxiter + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        if (want_resid) {
+            out->resid = (double *)std::malloc((size_t)sp->R * sizeof(double));
+            SPCK(cudaMemcpy(out->resid, D.f[st.cur], (size_t)sp->R * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        if (want_jtj) {
+            SPCK(cudaMalloc(&guard.q, (size_t)P * P * sizeof(double)));
+            D.jtj = guard.q;
+            int cur = st.cur;
+            void *args[] = {&D, &cur};
+            SPCK(cudaLaunchCooperativeKernel((const void *)sp_jtj, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
+                                             sp->stream));
+            SPCK(cudaStreamSynchronize(sp->stream));
+            out->jtj = (double *)std::malloc((size_t)P * P * sizeof(double));
+            SPCK(cudaMemcpy(out->jtj, D.jtj, (size_t)P * P * sizeof(double), cudaMemcpyDeviceToHost));
+            D.jtj = nullptr;
+        }
+        D.ssrtrace = nullptr;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        gslnls_sparse_result_free(out);
+        return GSLNLS_ECUDA;
+    }
+    return out->conv;
+}
+
+/* J^T f, diag(J^T J), f at theta without fitting: the test hook for the operator kernels.  Any output may be NULL. */
+GSLNLS_API int gslnls_sparse_eval(gslnls_sparse_problem *sp, const double *theta, double *resid, double *grad_vec,
+                                  double *jtj_diag, double *ssr)
+{
+    if (!sp || !theta || !sp->finalized) {
+        set_error("invalid argument (finalize the problem first)");
+        return GSLNLS_EINVAL;
+    }
+    // one INIT launch with maxiter = 1 would also step; run the pieces through a fit that stops at once instead:
+    // xtol = inf makes the first test succeed, but a step is still taken.  So: evaluate with the dedicated path.
+    try {
+        SPCK(cudaSetDevice(sp->device));
+        SpDev &D = sp->dev;
+        SPCK(cudaMemcpyAsync(D.x, theta, (size_t)sp->P * sizeof(double), cudaMemcpyHostToDevice, sp->stream));
+        sp_launch_evals(sp, D.x, 0);
+        SpDev E = D;
+        E.maxiter = 0; // INIT only: sp_step leaves after trust_init when maxiter == 0
+        E.want_trace = 0;
+        E.scale = 0;
+        E.factor_up = 3.0;
+        E.factor_down = 2.0;
+        E.cg_maxit = 0;
+        SpState st{};
+        st.phase = SP_PH_INIT;
+        SPCK(cudaMemcpyAsync(E.st, &st, sizeof st, cudaMemcpyHostToDevice, sp->stream));
+        void *args[] = {&E};
+        SPCK(cudaLaunchCooperativeKernel((const void *)sp_step, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
+                                         sp->stream));
+        SPCK(cudaStreamSynchronize(sp->stream));
+        st = *sp->h_state;
+        if (resid)
+            SPCK(cudaMemcpy(resid, D.f[0], (size_t)sp->R * sizeof(double), cudaMemcpyDeviceToHost));
+        if (grad_vec)
+            SPCK(cudaMemcpy(grad_vec, D.g, (size_t)sp->P * sizeof(double), cudaMemcpyDeviceToHost));
+        if (jtj_diag)
+            SPCK(cudaMemcpy(jtj_diag, D.jjj, (size_t)sp->P * sizeof(double), cudaMemcpyDeviceToHost));
+        if (ssr)
+            *ssr = st.chisq_init;
+        if (st.conv == GSLNLS_EBADFUNC)
+            return GSLNLS_EBADFUNC;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return GSLNLS_ECUDA;
+    }
+    return GSLNLS_SUCCESS;
+}
+
+} // extern "C"

@@ -330,6 +330,54 @@ GSLNLS_API int gslnls_measure_read_bandwidth(int device, size_t bytes, double *g
 /* ---- misc -------------------------------------------------------------------------------------- */
 GSLNLS_API const char *gslnls_strerror(int code);   /* gsl_strerror() strings + library errors */
 GSLNLS_API const char *gslnls_trs_name(int algorithm);
+/* ---- sparse-row problems: gsl_nls_large() with a sparse Jacobian ---------------------------------------
+ * Replaces the dgT/dgC/dgRMatrix branches of gsl_df_large (src/nls_large.c:528-623: triplet rebuild per callback,
+ * :635-648: gsl_spblas_dgemv and densify + dsyrk) for models with many parameters of which a row touches a few
+ * (README Example 4, inst/unit_tests/unit_tests_gslnls.R:302-346).  R closures cannot run on the device, so the
+ * sparsity structure is data:
+ *   - the problem has p_total parameters and nrows residual rows;
+ *   - a BLOCK is a compiled row formula (gslnls_model_compile, symbolic Jacobian, k <= 16 local parameters) over
+ *     nterms terms.  Local parameter s of term t is theta[slot_base[s] + (slot_index[s] ? slot_index[s][t] : 0)];
+ *     vars are the block's data columns (nterms doubles each);
+ *   - term t of the block belongs to row rows[t] (rows == NULL: row0 + t); a row is the sum of its terms minus
+ *     y[row], times sqrt(weights[row]).  A dense row such as sum(theta^2) - 0.25 is p one-parameter terms that
+ *     share a row.
+ * The solver is GSL's multilarge trust region with trs = cgst (Steihaug-Toint; J d and J^T u applied from the
+ * stored nonzeros, never a dense J or J^T J), scaling more / levenberg / marquardt, the convergence tests and
+ * driver of src/nls_fit.c:153-224.  control_int / control_dbl are those of gslnls_fit_large; algorithm must be 5. */
+typedef struct gslnls_sparse_problem gslnls_sparse_problem;
+typedef struct gslnls_sparse_result {
+    int p;
+    int64_t nrows, nterms, nnz; /* nnz: stored nonzeros of J */
+    double *par;        /* [p] */
+    double ssr, ssrtol, chisq_init;
+    int niter, conv, info;
+    const char *status;
+    int64_t neval[4];   /* f, dfu, df2, fvv: logical GSL counts (dfu: every J d / J^T u product) */
+    int64_t cg_iters;   /* Steihaug-Toint iterations over the whole fit */
+    int64_t launches;   /* solver kernel launches (one per trial point) */
+    int ntrace;
+    double *ssrtrace;   /* [maxiter + 1] when control_int[1] */
+    double *grad_vec;   /* [p] J^T f at par */
+    double *jtj;        /* [p*p] column-major J^T J at par when want_jtj (R = chol(jtj) for summary / vcov) */
+    double *resid;      /* [nrows] weighted residuals when want_resid */
+} gslnls_sparse_result;
+GSLNLS_API int gslnls_sparse_create(int device, int p_total, int64_t nrows, gslnls_sparse_problem **out);
+GSLNLS_API void gslnls_sparse_free(gslnls_sparse_problem *sp);
+GSLNLS_API int gslnls_sparse_add_block(gslnls_sparse_problem *sp, const gslnls_model *m, int64_t nterms,
+                                       const double *const *vars, const int *slot_base,
+                                       const int *const *slot_index, const int *rows, int64_t row0);
+GSLNLS_API int gslnls_sparse_set_response(gslnls_sparse_problem *sp, const double *y, const double *weights);
+/* builds the row / column gather lists and the device workspace; no blocks can be added afterwards */
+GSLNLS_API int gslnls_sparse_finalize(gslnls_sparse_problem *sp);
+GSLNLS_API int64_t gslnls_sparse_nnz(const gslnls_sparse_problem *sp);
+GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start, const int *control_int,
+                                 const double *control_dbl, int want_jtj, int want_resid, gslnls_sparse_result *out);
+/* weighted residuals [nrows], J^T f [p], diag(J^T J) [p] and f^T f at theta; any output may be NULL */
+GSLNLS_API int gslnls_sparse_eval(gslnls_sparse_problem *sp, const double *theta, double *resid, double *grad_vec,
+                                  double *jtj_diag, double *ssr);
+GSLNLS_API void gslnls_sparse_result_free(gslnls_sparse_result *r);
+
 GSLNLS_API const char *gslnls_last_error(void);     /* thread-local detail of the last GSLNLS_E* */
 GSLNLS_API int gslnls_device_count(void);
 GSLNLS_API const char *gslnls_version(void);
