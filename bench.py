@@ -197,7 +197,7 @@ def measured_peaks():
 
 def recorded_traffic(name):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any"""
-    fn = {"exp3": "k1_traffic.json", "gaussmix48": "k1b_traffic.json"}.get(name)
+    fn = {"exp3": "k1_traffic.json", "gaussmix48": "k1b_traffic.json", "sparse": "sparse_traffic.json"}.get(name)
     try:
         with open(os.path.join(ROOT, "profiles", fn)) as fh:
             return json.load(fh)
@@ -227,6 +227,8 @@ def run_reference(args):
     O.build()
     if args.config == "mstart8192":
         return run_reference_mstart(args, cores)
+    if args.config == "sparse":
+        return run_reference_sparse(args, cores)
     wl = Workload(args.config, args)
     n_s = args.cpu_sample or wl.n     # the real size unless told otherwise: same_config
     if args.warmup > 0:
@@ -507,6 +509,192 @@ def run_fit_config(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ sparse-row config
+SPARSE_METRIC = "cgst iterations/sec, gsl_nls_large with a sparse Jacobian, grouped exponential n=2e7 p=200001"
+SPARSE_WORKLOAD = ("y ~ A[g]*exp(-lam*x)+b[g], n=%d rows in %d groups of %d consecutive rows, p=%d (3 nonzeros per "
+                   "Jacobian row), cgst, scale=more (SURVEY 8 f3; the reference's sparse-Jacobian path "
+                   "src/nls_large.c:528-648)")
+SPARSE_GROUP = 200
+
+
+def sparse_rows(n, seed=6):
+    """grouped exponential: group g = row // 200; truth A_g in [2, 5], b_g in [0, 1], lam = 1.5, noise 0.05"""
+    ng = max(1, n // SPARSE_GROUP)
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    g = np.minimum(np.arange(n) // SPARSE_GROUP, ng - 1).astype(np.int32)
+    x = 3.0 * rng.random(n)
+    A = 2.0 + 3.0 * rng.random(ng)
+    b = rng.random(ng)
+    y = A[g] * np.exp(-1.5 * x) + b[g] + 0.05 * rng.standard_normal(n)
+    start = np.concatenate([np.full(ng, 3.0), np.full(ng, 0.3), [1.0]])
+    return g, x, y, ng, start
+
+
+def sparse_cpu_fit(n_s):
+    """the reference's sparse data flow (oracle/sparse.py: triplets -> sparse matrix -> spblas products, GSL cgst)"""
+    from oracle import sparse as OS
+    g, x, y, ng, start = sparse_rows(n_s)
+    model = OS.grouped_exp_model(g.astype(np.int64), x, ng)
+    t0 = time.perf_counter()
+    r = OS.nls_large_sparse(model, y, start)
+    return r, time.perf_counter() - t0
+
+
+def run_reference_sparse(args, cores):
+    n = args.n or 20_000_000
+    n_s = args.cpu_sample or 2_000_000
+    iters, elapsed, fits, last = 0, 0.0, 0, None
+    if args.warmup > 0:
+        sparse_cpu_fit(20_000)
+    while iters < args.steps:
+        r, dt = sparse_cpu_fit(n_s)
+        iters += r["niter"]
+        elapsed += dt
+        fits += 1
+        last = r
+    scale = n_s / float(n)
+    value = iters / elapsed * scale
+    line = {
+        "impl": "reference", "metric": SPARSE_METRIC, "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": iters, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": SPARSE_WORKLOAD % (n, n // SPARSE_GROUP, SPARSE_GROUP, 2 * (n // SPARSE_GROUP) + 1),
+                   "note": "reference CPU algorithm (oracle/sparse.py: src/nls_large.c:575-648 data flow with "
+                           "scipy.sparse standing in for gsl_spmatrix / gsl_spblas, GSL multilarge cgst restated), one "
+                           "thread like the reference, on the first %d rows (%d groups) of the same design, scaled "
+                           "x%g: the work per iteration is linear in the nonzeros" % (n_s, n_s // SPARSE_GROUP, scale),
+                   "final": {"ssr": float(last["ssr"]), "niter": int(last["niter"]), "conv": int(last["conv"]),
+                             "lam": float(last["par"][-1])}},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port",
+                         "sample": "%d cgst fit(s) at n=%d (%d iterations in %.1f s), scaled x%g" % (
+                             fits, n_s, iters, elapsed, scale)},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_sparse(args):
+    import torch
+
+    from gslnls_b200 import SparseProblem
+    torch.cuda.set_device(0)
+    n = args.n or 20_000_000
+    g, x, y, ng, start = sparse_rows(n)
+    P = 2 * ng + 1
+
+    def build():
+        sp = SparseProblem(p=P, nrows=n)
+        sp.add_block("A * exp(-lam * x) + b", {"A": (0, g), "lam": 2 * ng, "b": (ng, g)}, {"x": x})
+        sp.set_response(y)
+        return sp.finalize()
+
+    t0 = time.perf_counter()
+    sp = build()
+    setup_s = time.perf_counter() - t0
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        r = sp.fit(start)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    ev_ms = sv_ms = 0.0
+    launches = cg = trials = 0
+    for _ in range(args.steps):
+        r = sp.fit(start)
+        ev_ms += r["eval_ms"]
+        sv_ms += r["solver_ms"]
+        launches += 2 * r["launches"]
+        trials += r["launches"]
+        cg += r["cg_iters"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms_per_step = 1e3 * wall / args.steps
+    niter = int(r["niter"])
+    # e2e: host arrays -> problem (upload + gather lists) -> fit -> result
+    sp.close()
+    t0 = time.perf_counter()
+    sp = build()
+    r2 = sp.fit(start)
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # algorithmic bytes of the solver launches of one fit (DESIGN.md: per nonzero 8 B value + 4 B index per product,
+    # 8 B per row vector element read or written)
+    E, T, R = 3 * n, n, n
+    accepts = niter
+    per_cg = 2 * 12.0 * E + 16.0 * R
+    per_trial = 12.0 * E + 8.0 * T + 24.0 * R
+    per_accept = 12.0 * E + 8.0 * R
+    fit_trials = trials / args.steps
+    fit_bytes = (cg / args.steps) * per_cg + fit_trials * per_trial + accepts * per_accept
+    peak, peak_src = measured_peaks()
+    achieved = fit_bytes / ((sv_ms / args.steps) * 1e-3) / 1e9
+    traffic = recorded_traffic("sparse")
+    line = {
+        "metric": SPARSE_METRIC, "value": niter / (ms_per_step * 1e-3), "unit": "iterations/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": SPARSE_WORKLOAD % (n, ng, SPARSE_GROUP, P),
+                   "step": "one complete fit from the start values (%d outer iterations, %d trial points, %d CG "
+                           "iterations); host wall clock around SparseProblem.fit(), problem resident" % (
+                               niter, int(fit_trials), cg // args.steps),
+                   "device_ms_per_fit": {"term_evaluation": ev_ms / args.steps, "solver": sv_ms / args.steps},
+                   "l2": "nonzeros + index lists (%.2f GB) exceed the 126 MB L2; no flush needed" % (E * 24 / 1e9),
+                   "final": {"ssr": float(r["ssr"]), "niter": niter, "status": r["status"], "lam": float(r["par"][-1]),
+                             "max_abs_grad": float(np.max(np.abs(r["grad_vec"])))}},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "sp_step (cooperative solver launch: J d, J^T u, row / column sums)",
+                     "avg_launch_ms": sv_ms / max(trials, 1), "launches_timed": int(trials),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "algorithmic_bytes_per_launch": fit_bytes / fit_trials, "peak_source": peak_src,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "note": "bytes per fit = CG iterations x (24 E + 16 R) + trial points x (12 E + 8 T + 24 R) + "
+                             "accepted points x (12 E + 8 R), E nonzeros, T terms, R rows; time = CUDA events around "
+                             "every sp_step launch on its stream"},
+        "e2e": {"value": int(r2["niter"]) / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int((20 * n + 8 * P) / niter),
+                "d2h_bytes_per_step": int(16 * P / niter), "ms_per_fit": 1e3 * e2e_s, "setup_s_first": setup_s,
+                "note": "SparseProblem(...) from pageable host arrays (data + index columns up, row / column gather "
+                        "lists built on the host and uploaded) + finalize + fit + result, one call sequence"},
+    }
+    if not args.no_cpu_baseline:
+        n_s = args.cpu_sample or 400_000
+        rc, dt = sparse_cpu_fit(n_s)
+        line["cpu_baseline"] = {"value": rc["niter"] / dt * (n_s / float(n)), "unit": "iterations/s", "cores": 1,
+                                "kind": "port", "sample": "oracle/sparse.py cgst fit of the first %d rows (%d iterations "
+                                                         "in %.1f s), scaled x%g" % (n_s, rc["niter"], dt, n_s / float(n))}
+        # README Example 4 side by side (README.md:1117-1146: "Sparse CGST" 158 ms median on the authors' CPU)
+        import math
+        from oracle import sparse as OS
+        p4 = 500
+        idx = np.arange(p4, dtype=np.int32)
+        s4 = SparseProblem(p=p4, nrows=p4 + 1)
+        s4.add_block("%.17g * (th - 1)" % math.sqrt(1e-5), {"th": (0, idx)}, nterms=p4)
+        s4.add_block("th^2", {"th": (0, idx)}, rows=np.full(p4, p4, dtype=np.int32))
+        y4 = np.zeros(p4 + 1)
+        y4[p4] = 0.25
+        s4.set_response(y4).finalize()
+        st4 = np.arange(1, p4 + 1, dtype=float)
+        s4.fit(st4, control={"maxiter": 500})
+        t0 = time.perf_counter()
+        for _ in range(5):
+            r4 = s4.fit(st4, control={"maxiter": 500})
+        g4 = (time.perf_counter() - t0) / 5
+        m4, yy4 = OS.penalty_model(p4)
+        t0 = time.perf_counter()
+        o4 = OS.nls_large_sparse(m4, yy4, st4, maxiter=500)
+        c4 = time.perf_counter() - t0
+        line["config"]["readme_example4"] = {
+            "workload": "Penalty function I, p=500, start 1:p, cgst (README.md:1088-1146)",
+            "gpu_ms_per_fit": 1e3 * g4, "gpu_ssr": float(r4["ssr"]), "gpu_niter": int(r4["niter"]),
+            "gpu_cg_iters": int(r4["cg_iters"]), "oracle_sparse_ms_per_fit": 1e3 * c4, "oracle_ssr": float(o4["ssr"]),
+            "readme_published_ms": 158.18, "readme_published_ssr": 0.004778845}
+        s4.close()
+    print(json.dumps(line))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ CUDA arm: multistart
 MSTART_METRIC = "multi-start candidate-iterations/sec, 8192 starts x 5 LM iterations, exp mixture n=4096 p=4"
 MSTART_WORKLOAD = ("y ~ A1*exp(-l1*x)+A2*exp(-l2*x), n=4096, p=4, S=%d Sobol starts in [0,10]^4, mstart_p=5 LM "
@@ -581,7 +769,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--config", default="exp3", choices=["exp3", "gaussmix48", "mstart8192"])
+    ap.add_argument("--config", default="exp3", choices=["exp3", "gaussmix48", "mstart8192", "sparse"])
     ap.add_argument("--n", type=int, default=0, help="rows (exp3, gaussmix48) or candidates (mstart8192)")
     ap.add_argument("--algorithm", default=None)
     ap.add_argument("--cpu-sample", type=int, default=0,
@@ -590,7 +778,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 10 if args.config == "mstart8192" else 40
+        args.steps = {"mstart8192": 10, "sparse": 5}.get(args.config, 40)
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -598,6 +786,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     if args.config == "mstart8192":
         return run_mstart(args)
+    if args.config == "sparse":
+        return run_sparse(args)
     return run_fit_config(args)
 
 

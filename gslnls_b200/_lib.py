@@ -42,7 +42,8 @@ class SparseResult(C.Structure):
     _fields_ = [("p", C.c_int), ("nrows", C.c_int64), ("nterms", C.c_int64), ("nnz", C.c_int64), ("par", c_double_p),
                 ("ssr", C.c_double), ("ssrtol", C.c_double), ("chisq_init", C.c_double), ("niter", C.c_int),
                 ("conv", C.c_int), ("info", C.c_int), ("status", C.c_char_p), ("neval", C.c_int64 * 4),
-                ("cg_iters", C.c_int64), ("launches", C.c_int64), ("ntrace", C.c_int), ("ssrtrace", c_double_p),
+                ("cg_iters", C.c_int64), ("launches", C.c_int64), ("eval_ms", C.c_double), ("solver_ms", C.c_double),
+                ("ntrace", C.c_int), ("ssrtrace", c_double_p),
                 ("grad_vec", c_double_p), ("jtj", c_double_p), ("resid", c_double_p)]
 
 

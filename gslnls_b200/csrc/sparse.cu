@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -52,12 +53,15 @@ namespace {
 constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
+constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
+                                   // GSLNLS_SP_MINB overrides (A/B in profiles/r02_summary.md)
 
 enum { SP_PH_INIT = 0, SP_PH_TRIAL = 1, SP_PH_DONE = 2 };
 
 struct SpBlockDev {
     long long term0, nterms, ent0;
     int k, pad;
+    int scalar_col[NLS_SP_MAXSLOT]; // global index of a scalar local parameter, -1: per-term index column
 };
 
 // a family of segmented sums: entries grouped by segment (row or column), cut into items
@@ -65,6 +69,9 @@ struct SpSeg {
     const int *ent_a;            // per entry: gather index (row sums: term id; column sums: position in jv)
     const int *ent_b;            // per entry: row id (column sums) or nullptr
     const long long *item_begin; // [nitems + 1] entry ranges
+    const int *item_a0, *item_b0; // [nitems] first ent_a / ent_b of an item whose entries are CONSECUTIVE in both
+                                 // (a run of terms of one slot: group-sorted data, scalar parameters), else -1:
+                                 // such items are streamed without touching the index lists
     const int *seg_itemptr;      // [nseg + 1] item ranges of each segment
     int nitems, nseg;
     double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
@@ -158,25 +165,64 @@ __device__ double sp_block_max(double v, double *sm)
 #define SP_GTID ((long long)blockIdx.x * SP_BLOCK + threadIdx.x)
 #define SP_GSTRIDE ((long long)gridDim.x * SP_BLOCK)
 
-// u_t = sum_s J[t, s] * vec[col(t, s)] / (dscale ? dscale[col] : 1) for every term -> S.tmpT   (first half of J v)
-__device__ void sp_term_dot(const SpDev &S, const double *jv, const double *vec, const double *dscale)
+// u_t = sum_s J[t, s] * vec[col(t, s)] for every term (first half of J v).  Rows that aggregate terms: u -> S.tmpT
+// and sp_rowsum finishes the product.  One term per row (FUSE): the row value sw_t * u_t goes straight to `out`
+// and its square into the thread's partial of ||J v||^2 (returned) -- no second sweep, no grid.sync.
+// Two terms per thread and trip, written out by hand: two independent load chains in flight.  (A generic
+// `double u[UN]` + `#pragma unroll` form of this loop gave run-to-run different fits on B200 with nvcc 12.9 -- 20 of
+// 20 runs, also when a run-time switch bypassed it -- while this form and the one-term form pass; the A/B builds
+// are recorded in profiles/r02_summary.md.)
+// Vectors that other CTAs rewrite between two grid.sync() of the same launch (wp, workn, tmpT, f, ...) are read
+// with plain loads only: `const __restrict__` / __ldg would allow the non-coherent path (ld.global.nc), which the
+// barrier's fence does not invalidate.
+template <bool FUSE>
+__device__ double sp_term_dot(const SpDev &S, const double *jv, const double *vec, double *out)
 {
+    double acc = 0.0;
     for (int b = 0; b < S.nblocks; ++b) {
-        const SpBlockDev B = S.blocks[b];
-        for (long long t = SP_GTID; t < B.nterms; t += SP_GSTRIDE) {
-            double u = 0.0;
-            for (int s = 0; s < B.k; ++s) {
-                const long long e = B.ent0 + (long long)s * B.nterms + t;
-                const int c = S.ecol[e];
-                const double v = dscale ? vec[c] / dscale[c] : vec[c];
-                u = fma(jv[e], v, u);
+        const SpBlockDev *Bp = S.blocks + b;
+        const long long term0 = Bp->term0, nterms = Bp->nterms;
+        const int k = Bp->k;
+        const double *jb = jv + Bp->ent0;
+        const int *cb = S.ecol + Bp->ent0;
+        for (long long t = SP_GTID; t < nterms; t += 2 * SP_GSTRIDE) {
+            const long long t1 = t + SP_GSTRIDE;
+            const bool two = t1 < nterms;
+            double u0 = 0.0, u1 = 0.0;
+            for (int s = 0; s < k; ++s) {
+                const long long e0 = (long long)s * nterms;
+                const int sc = Bp->scalar_col[s]; // a scalar parameter: no index column to read
+                const double j0 = jb[e0 + t];
+                const double j1 = two ? jb[e0 + t1] : 0.0;
+                const int c0 = sc >= 0 ? sc : cb[e0 + t];
+                const int c1 = sc >= 0 ? sc : (two ? cb[e0 + t1] : c0);
+                u0 = fma(j0, vec[c0], u0);
+                u1 = fma(j1, vec[c1], u1);
             }
-            S.tmpT[B.term0 + t] = u;
+            if (FUSE) {
+                if (S.sw)
+                    u0 *= S.sw[term0 + t];
+                out[term0 + t] = u0;
+                acc = fma(u0, u0, acc);
+                if (two) {
+                    if (S.sw)
+                        u1 *= S.sw[term0 + t1];
+                    out[term0 + t1] = u1;
+                    acc = fma(u1, u1, acc);
+                }
+            } else {
+                S.tmpT[term0 + t] = u0;
+                if (two)
+                    S.tmpT[term0 + t1] = u1;
+            }
         }
     }
+    return acc;
 }
 
-// items of a segmented sum: one warp per item, lanes stride the item's entries, xor tree at the end
+// items of a segmented sum: one warp per item, lanes stride the item's entries (each lane adds its entries in
+// order), xor tree at the end.  Consecutive items skip the index lists; the order of the additions is the same
+// on both paths.
 template <int KIND> // 0: rows (value = src[ent_a]); 1: columns (value = jv[ent_a] * wv[ent_b], and squares)
 __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, const double *sw, bool squares)
 {
@@ -184,17 +230,42 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
     const long long warp = SP_GTID >> 5, nwarp = SP_GSTRIDE >> 5;
     for (long long it = warp; it < G.nitems; it += nwarp) {
         const long long a = G.item_begin[it], b = G.item_begin[it + 1];
+        const int a0 = G.item_a0[it];
         double s = 0.0, s2 = 0.0;
-        for (long long e = a + lane; e < b; e += 32) {
+        if (a0 >= 0) {
+            const int len = (int)(b - a);
+            const double *sp = src + a0;
             if (KIND == 0) {
-                s += src[G.ent_a[e]];
+#pragma unroll 4
+                for (int i = lane; i < len; i += 32)
+                    s += sp[i];
             } else {
-                const int row = G.ent_b[e];
-                const double j = sw ? src[G.ent_a[e]] * sw[row] : src[G.ent_a[e]];
-                if (wv)
-                    s = fma(j, wv[row], s);
-                if (squares)
-                    s2 = fma(j, j, s2);
+                const int b0 = G.item_b0[it];
+                const double *wp = wv ? wv + b0 : nullptr;
+                const double *swp = sw ? sw + b0 : nullptr;
+#pragma unroll 4
+                for (int i = lane; i < len; i += 32) {
+                    const double j = swp ? sp[i] * swp[i] : sp[i];
+                    if (wp)
+                        s = fma(j, wp[i], s);
+                    if (squares)
+                        s2 = fma(j, j, s2);
+                }
+            }
+        } else {
+#pragma unroll 4
+            for (long long e = a + lane; e < b; e += 32) {
+                if (KIND == 0) {
+                    s += src[G.ent_a[e]];
+                } else {
+                    const int row = G.ent_b[e];
+                    const double jj = src[G.ent_a[e]];
+                    const double j = sw ? jj * sw[row] : jj;
+                    if (wv)
+                        s = fma(j, wv[row], s);
+                    if (squares)
+                        s2 = fma(j, j, s2);
+                }
             }
         }
         s = sp_warp_sum(s);
@@ -253,8 +324,24 @@ __device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv
     }
 }
 
+// out = sqrt(W) J vec (a row vector) and its squared norm into reduction slot `slot`; the caller syncs before
+// reading either.  vec is a P-vector in global memory, complete before the call (grid.sync by the caller).
+__device__ void sp_apply_J(cg::grid_group &grid, const SpDev &S, const double *jv, const double *vec, double *out,
+                           int slot, double *sm)
+{
+    if (S.rows.ent_a == nullptr) {
+        sp_put(S, slot, sp_term_dot<true>(S, jv, vec, out), sm);
+    } else {
+        sp_term_dot<false>(S, jv, vec, nullptr);
+        grid.sync();
+        sp_rowsum(grid, S, S.tmpT, out, false, slot, sm);
+    }
+}
+
 // Steihaug-Toint step: GSL multilarge_nlinear/cgst.c, statement order of the restatement in
 // oracle/multilarge.c:994-1060.  Returns 0 with dx and x_trial written, or GSLNLS_EMAXITER.
+// Four grid.sync() per CG iteration when every row is one term: the P-vector updates at the bottom and at the
+// top of the loop use the same element -> thread mapping, so they need no barrier between them.
 __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, double delta, long long &cg_iters,
                        long long &ndfu, double *sm)
 {
@@ -281,14 +368,11 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
             break;
         }
         ++cg_iters;
-        // workn = J D^-1 d
-        sp_term_dot(S, jv, S.d, S.diag);
-        grid.sync();
-        sp_rowsum(grid, S, S.tmpT, S.workn, false, 0, sm);
-        ++ndfu;
+        // wp = D^-1 d, and the three dot products of cgst_calc_tau / the boundary test
         double zz = 0.0, dd = 0.0, zd = 0.0;
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
             const double zk = S.z[k], dk = S.d[k];
+            S.wp[k] = dk / S.diag[k];
             zz = fma(zk, zk, zz);
             dd = fma(dk, dk, dd);
             zd = fma(zk, dk, zd);
@@ -296,6 +380,10 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         sp_put(S, 1, zz, sm);
         sp_put(S, 2, dd, sm);
         sp_put(S, 3, zd, sm);
+        grid.sync();
+        // workn = J D^-1 d
+        sp_apply_J(grid, S, jv, S.wp, S.workn, 0, sm);
+        ++ndfu;
         grid.sync();
         const double normJd2 = sp_total(S, 0, sm);
         zz = sp_total(S, 1, sm);
@@ -309,6 +397,19 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         if (normJd2 == 0.0) {
             exit_kind = 1;
             tau = tau_b;
+            break;
+        }
+        if (normJd2 != normJd2) {
+            // NaN (a non-finite residual with a finite Jacobian): from here on every quantity of GSL's loop is NaN
+            // and every test false, so it runs its cg_maxit = n iterations and returns z = NaN with EMAXITER.
+            // Same outcome and the same evaluation counts, without the n sweeps.
+            const long long rest = S.cg_maxit - it - 1;
+            for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
+                S.z[k] = normJd2;
+            cg_iters += rest;
+            ndfu += 1 + 2 * rest;
+            exit_kind = 0;
+            status = GSLNLS_EMAXITER;
             break;
         }
         const double alpha = norm_r2 / normJd2; // (||r|| / ||J D^-1 d||)^2
@@ -341,7 +442,6 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
             S.d[k] = fma(beta, S.d[k], S.r[k]);
         norm_r2 = norm_rp1_2;
-        grid.sync();
     }
     for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
         const double v = (exit_kind == 1 ? fma(tau, S.d[k], S.z[k]) : S.z[k]) / S.diag[k];
@@ -405,7 +505,8 @@ __device__ void sp_gradient_and_scale(cg::grid_group &grid, const SpDev &S, cons
     grid.sync();
 }
 
-__global__ void __launch_bounds__(SP_BLOCK) sp_step(const SpDev S)
+template <int MINB>
+__global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[SP_BLOCK / 32];
@@ -457,16 +558,14 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_step(const SpDev S)
         sp_rowsum(grid, S, S.tv[tr], S.f[tr], true, 0, sm);
         ++st.nevalf;
         // predicted reduction of the quadratic model: needs g . dx and ||J dx||^2 (J of the accepted point)
-        sp_term_dot(S, S.jv[cur], S.dx, nullptr);
         double gdx = 0.0;
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
             gdx = fma(S.g[k], S.dx[k], gdx);
         sp_put(S, 2, gdx, sm);
+        sp_apply_J(grid, S, S.jv[cur], S.dx, S.workn, 1, sm);
         grid.sync();
         const double ff_trial = sp_total(S, 0, sm);
         gdx = sp_total(S, 2, sm);
-        sp_rowsum(grid, S, S.tmpT, S.workn, false, 1, sm);
-        grid.sync();
         const double jdx2 = sp_total(S, 1, sm);
         const double normf_trial = sqrt(ff_trial);
         double rho;
@@ -572,9 +671,7 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
             S.d[k] = (k == c) ? 1.0 : 0.0;
         grid.sync();
-        sp_term_dot(S, S.jv[cur], S.d, nullptr);
-        grid.sync();
-        sp_rowsum(grid, S, S.tmpT, S.workn, false, 0, sm);
+        sp_apply_J(grid, S, S.jv[cur], S.d, S.workn, 0, sm);
         grid.sync();
         sp_colsum(grid, S, S.jv[cur], S.workn, S.jtj + (size_t)c * S.P, false);
         grid.sync();
@@ -623,7 +720,7 @@ double *sp_dalloc(size_t n)
 struct SegBuild {
     std::vector<int> ent_a, ent_b;
     std::vector<long long> item_begin;
-    std::vector<int> seg_itemptr;
+    std::vector<int> seg_itemptr, item_a0, item_b0;
 };
 void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
 {
@@ -637,6 +734,23 @@ void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
     }
     B.seg_itemptr[nseg] = (int)B.item_begin.size();
     B.item_begin.push_back(segptr[nseg]);
+    // items whose entries are consecutive in ent_a (and ent_b)
+    const size_t nitems = B.item_begin.size() - 1;
+    B.item_a0.assign(nitems, -1);
+    B.item_b0.assign(nitems, -1);
+    for (size_t it = 0; it < nitems; ++it) {
+        const long long a = B.item_begin[it], b = B.item_begin[it + 1];
+        if (b <= a)
+            continue;
+        bool run = true;
+        for (long long e = a + 1; e < b && run; ++e)
+            run = B.ent_a[(size_t)e] == B.ent_a[(size_t)e - 1] + 1 &&
+                  (B.ent_b.empty() || B.ent_b[(size_t)e] == B.ent_b[(size_t)e - 1] + 1);
+        if (run) {
+            B.item_a0[it] = B.ent_a[(size_t)a];
+            B.item_b0[it] = B.ent_b.empty() ? 0 : B.ent_b[(size_t)a];
+        }
+    }
 }
 
 } // namespace
@@ -649,6 +763,7 @@ struct gslnls_sparse_problem {
     bool finalized = false;
     cudaStream_t stream = nullptr;
     int grid = 0;
+    const void *step_fn = nullptr; // sp_step<MINB>
     SpDev dev{};
     SpState *h_state = nullptr; // mapped pinned
     std::vector<void *> owned;  // device allocations
@@ -759,8 +874,16 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.E = E;
     D.nblocks = (int)sp->blocks.size();
     std::vector<SpBlockDev> bd;
-    for (auto &b : sp->blocks)
-        bd.push_back(SpBlockDev{b.term0, b.nterms, b.ent0, b.k, 0});
+    for (auto &b : sp->blocks) {
+        SpBlockDev d{};
+        d.term0 = b.term0;
+        d.nterms = b.nterms;
+        d.ent0 = b.ent0;
+        d.k = b.k;
+        for (int s = 0; s < NLS_SP_MAXSLOT; ++s)
+            d.scalar_col[s] = (s < b.k && b.index[(size_t)s].empty()) ? b.base[s] : -1;
+        bd.push_back(d);
+    }
     D.blocks = sp->keep(sp_upload(bd));
     D.ecol = sp->keep(sp_upload(ecol));
     if (!sp->h_y.empty())
@@ -783,6 +906,8 @@ void sp_finalize(gslnls_sparse_problem *sp)
         D.rows.ent_a = sp->keep(sp_upload(rb.ent_a));
         D.rows.item_begin = sp->keep(sp_upload(rb.item_begin));
         D.rows.seg_itemptr = sp->keep(sp_upload(rb.seg_itemptr));
+        D.rows.item_a0 = sp->keep(sp_upload(rb.item_a0));
+        D.rows.item_b0 = sp->keep(sp_upload(rb.item_b0));
         D.rows.nitems = (int)rb.item_begin.size() - 1;
         D.rows.nseg = (int)R;
         D.rows.ipart = sp->keep(sp_dalloc((size_t)D.rows.nitems));
@@ -791,6 +916,8 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.cols.ent_b = sp->keep(sp_upload(cb.ent_b));
     D.cols.item_begin = sp->keep(sp_upload(cb.item_begin));
     D.cols.seg_itemptr = sp->keep(sp_upload(cb.seg_itemptr));
+    D.cols.item_a0 = sp->keep(sp_upload(cb.item_a0));
+    D.cols.item_b0 = sp->keep(sp_upload(cb.item_b0));
     D.cols.nitems = (int)cb.item_begin.size() - 1;
     D.cols.nseg = P;
     D.cols.ipart = sp->keep(sp_dalloc((size_t)D.cols.nitems));
@@ -804,10 +931,15 @@ void sp_finalize(gslnls_sparse_problem *sp)
     // grid of the cooperative solver kernel: every CTA resident, no more CTAs than the problem can use
     int dev_sms = 0, occ = 0;
     SPCK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, sp->device));
-    SPCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sp_step, SP_BLOCK, 0));
+    int minb = SP_MINB_DEFAULT;
+    if (const char *e = std::getenv("GSLNLS_SP_MINB"))
+        minb = std::atoi(e);
+    minb = minb <= 2 ? 2 : (minb == 3 ? 3 : 4);
+    sp->step_fn = minb == 2 ? (const void *)sp_step<2> : (minb == 3 ? (const void *)sp_step<3> : (const void *)sp_step<4>);
+    SPCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sp->step_fn, SP_BLOCK, 0));
     const long long work = std::max<long long>(std::max<long long>(E, T), std::max<long long>(P, R));
     const long long want = (work + SP_BLOCK * 4 - 1) / (SP_BLOCK * 4);
-    sp->grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)dev_sms * std::min(occ, 4)));
+    sp->grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)dev_sms * std::min(occ, minb)));
     D.red = sp->keep(sp_dalloc((size_t)SP_NRED * (size_t)sp->grid));
     SpState *st = nullptr;
     SPCK(cudaMalloc(&st, sizeof(SpState)));
@@ -824,6 +956,10 @@ void sp_finalize(gslnls_sparse_problem *sp)
         if (!b.var->sparse_eval)
             throw std::runtime_error("the model has no sparse evaluation kernel (symbolic Jacobian, <= 16 parameters)");
     }
+    // cudaMemset / cudaMemcpy above ran on the legacy default stream, and cudaMemset does not wait for the host:
+    // the solver's stream is non-blocking, so without this the zero-fill of a workspace vector could land after
+    // the first kernels that write it
+    SPCK(cudaDeviceSynchronize());
     sp->finalized = true;
 }
 
@@ -1027,19 +1163,43 @@ GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start,
         st.phase = SP_PH_INIT;
         SPCK(cudaMemcpyAsync(D.st, &st, sizeof st, cudaMemcpyHostToDevice, sp->stream));
         *sp->h_state = st;
+        // device times of the two kernels (CUDA events on the launching stream) for bench.py's roofline
+        struct Ev {
+            cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+            ~Ev()
+            {
+                for (cudaEvent_t x : e)
+                    if (x)
+                        cudaEventDestroy(x);
+            }
+        } ev;
+        for (cudaEvent_t &x : ev.e)
+            SPCK(cudaEventCreate(&x));
+        double eval_ms = 0.0, solver_ms = 0.0;
+        SPCK(cudaEventRecord(ev.e[0], sp->stream));
         sp_launch_evals(sp, D.x, 0);
         long long launches = 0;
         for (;;) {
             void *args[] = {&D};
-            SPCK(cudaLaunchCooperativeKernel((const void *)sp_step, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
+            SPCK(cudaEventRecord(ev.e[1], sp->stream));
+            SPCK(cudaLaunchCooperativeKernel(sp->step_fn, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
                                              sp->stream));
+            SPCK(cudaEventRecord(ev.e[2], sp->stream));
             ++launches;
             SPCK(cudaStreamSynchronize(sp->stream));
+            float ms = 0.f;
+            SPCK(cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]));
+            eval_ms += ms;
+            SPCK(cudaEventElapsedTime(&ms, ev.e[1], ev.e[2]));
+            solver_ms += ms;
             st = *sp->h_state;
             if (st.phase == SP_PH_DONE)
                 break;
+            SPCK(cudaEventRecord(ev.e[0], sp->stream));
             sp_launch_evals(sp, D.x_trial, 1 - st.cur);
         }
+        out->eval_ms = eval_ms;
+        out->solver_ms = solver_ms;
         out->p = P;
         out->nrows = sp->R;
         out->nterms = sp->T;
@@ -1119,7 +1279,7 @@ GSLNLS_API int gslnls_sparse_eval(gslnls_sparse_problem *sp, const double *theta
         st.phase = SP_PH_INIT;
         SPCK(cudaMemcpyAsync(E.st, &st, sizeof st, cudaMemcpyHostToDevice, sp->stream));
         void *args[] = {&E};
-        SPCK(cudaLaunchCooperativeKernel((const void *)sp_step, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
+        SPCK(cudaLaunchCooperativeKernel(sp->step_fn, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
                                          sp->stream));
         SPCK(cudaStreamSynchronize(sp->stream));
         st = *sp->h_state;

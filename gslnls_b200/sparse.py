@@ -119,7 +119,7 @@ class SparseProblem:
             "ssr": res.ssr, "ssrtol": res.ssrtol, "chisq_init": res.chisq_init, "niter": res.niter,
             "conv": res.conv, "info": res.info, "status": res.status.decode(),
             "neval": {"f": res.neval[0], "dfu": res.neval[1], "df2": res.neval[2], "fvv": res.neval[3]},
-            "cg_iters": res.cg_iters, "launches": res.launches, "nnz": res.nnz, "nterms": res.nterms,
+            "cg_iters": res.cg_iters, "launches": res.launches, "eval_ms": res.eval_ms, "solver_ms": res.solver_ms, "nnz": res.nnz, "nterms": res.nterms,
             "algorithm": algorithm,
         }
         if trace:

@@ -356,6 +356,7 @@ typedef struct gslnls_sparse_result {
     int64_t neval[4];   /* f, dfu, df2, fvv: logical GSL counts (dfu: every J d / J^T u product) */
     int64_t cg_iters;   /* Steihaug-Toint iterations over the whole fit */
     int64_t launches;   /* solver kernel launches (one per trial point) */
+    double eval_ms, solver_ms; /* device time (CUDA events) of the term-evaluation and of the solver launches */
     int ntrace;
     double *ssrtrace;   /* [maxiter + 1] when control_int[1] */
     double *grad_vec;   /* [p] J^T f at par */

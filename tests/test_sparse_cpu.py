@@ -63,3 +63,51 @@ def test_oracle_side_of_the_sparse_parity_tests():
     assert np.allclose(a["par"], b["par"], rtol=1e-5) and abs(a["ssr"] - b["ssr"]) < 1e-9
     # More', Garbow, Hillstrom (1981) problem 23, n = 10: f* = 7.08765e-5
     assert abs(a["ssr"] - 7.08765e-5) < 1e-9
+
+
+# ------------------------------------------------------------------- oracle/sparse.py pinned on the dense oracle
+def _dense_rows_from(model, n, p):
+    def rows(th, v, wf, wJ, wh):
+        f, trip = model(th, wJ)
+        J = None
+        if wJ:
+            J = np.zeros((n, p))
+            np.add.at(J, (trip[0], trip[1]), trip[2])
+        return f, J, None
+    return rows
+
+
+@pytest.mark.parametrize("p,scale,weighted", [(10, "more", False), (10, "levenberg", False), (10, "marquardt", False),
+                                               (40, "more", True), (500, "more", False)])
+def test_sparse_oracle_matches_dense_oracle_penalty(p, scale, weighted):
+    from oracle import sparse as OS
+    model, y = OS.penalty_model(p)
+    start = np.full(p, 0.15) if p < 500 else np.arange(1, p + 1, dtype=float)
+    w = (0.5 + (np.arange(p + 1) % 5) / 2.0) if weighted else None
+    a = OS.nls_large_sparse(model, y, start, weights=w, scale=scale, maxiter=500, trace=True)
+    b = O.nls_large(_dense_rows_from(model, p + 1, p), y, start, weights=w, algorithm="cgst", scale=scale,
+                    maxiter=500, trace=True)
+    assert a["conv"] == b["conv"] == 0 and a["niter"] == b["niter"] and a["info"] == b["info"]
+    assert a["neval"] == b["neval"]
+    assert abs(a["ssr"] - b["ssr"]) <= 1e-10 * b["ssr"]
+    assert np.max(np.abs(a["ssrtrace"] - b["ssrtrace"]) / b["ssrtrace"]) < 1e-9
+    # p = 500: flat minimum, coefficients defined to ~1e-6 only (see tests/test_gpu_sparse.py)
+    assert np.max(np.abs(a["par"] - b["par"]) / np.abs(b["par"])) < (1e-8 if p < 500 else 1e-5)
+    if p == 500:
+        assert float("%.7g" % a["ssr"]) == 0.004778845  # README.md:1100
+
+
+def test_sparse_oracle_matches_dense_oracle_grouped():
+    from oracle import sparse as OS
+    n, ng = 3000, 12
+    rng = np.random.default_rng(5)
+    g = (np.arange(n) * ng // n).astype(np.int64)
+    x = 3.0 * rng.random(n)
+    y = (2.0 + g % 3)[...] * np.exp(-1.5 * x) + 0.1 * g + 0.05 * rng.standard_normal(n)
+    model = OS.grouped_exp_model(g, x, ng)
+    start = np.concatenate([np.full(ng, 3.0), np.full(ng, 0.3), [1.0]])
+    a = OS.nls_large_sparse(model, y, start)
+    b = O.nls_large(_dense_rows_from(model, n, 2 * ng + 1), y, start, algorithm="cgst")
+    assert a["conv"] == b["conv"] == 0 and a["niter"] == b["niter"] and a["neval"] == b["neval"]
+    assert np.max(np.abs(a["par"] - b["par"]) / np.abs(b["par"])) < 1e-9
+    assert abs(a["ssr"] - b["ssr"]) <= 1e-11 * b["ssr"]
