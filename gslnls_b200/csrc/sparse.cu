@@ -53,6 +53,7 @@ namespace {
 constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
+constexpr int SP_LONG = 64;   // items per segment above which a CTA adds them
 constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
                                    // GSLNLS_SP_MINB overrides (A/B in profiles/r02_summary.md)
 
@@ -73,6 +74,8 @@ struct SpSeg {
                                  // (a run of terms of one slot: group-sorted data, scalar parameters), else -1:
                                  // such items are streamed without touching the index lists
     const int *seg_itemptr;      // [nseg + 1] item ranges of each segment
+    const int *long_seg;         // [nlong] segments of more than SP_LONG items (a parameter every row depends on, a
+    int nlong;                   // dense row): their item sums are added by a whole CTA instead of one thread
     int nitems, nseg;
     double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
 };
@@ -175,46 +178,61 @@ __device__ double sp_block_max(double v, double *sm)
 // Vectors that other CTAs rewrite between two grid.sync() of the same launch (wp, workn, tmpT, f, ...) are read
 // with plain loads only: `const __restrict__` / __ldg would allow the non-coherent path (ld.global.nc), which the
 // barrier's fence does not invalidate.
+template <bool FUSE, int K> // K > 0: the block's parameter count at compile time (loads of all slots in flight)
+__device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBlockDev *Bp, const double *jv,
+                                                    const double *vec, double *out)
+{
+    double acc = 0.0;
+    const long long term0 = Bp->term0, nterms = Bp->nterms;
+    const int k = K > 0 ? K : Bp->k;
+    const double *jb = jv + Bp->ent0;
+    const int *cb = S.ecol + Bp->ent0;
+    for (long long t = SP_GTID; t < nterms; t += 2 * SP_GSTRIDE) {
+        const long long t1 = t + SP_GSTRIDE;
+        const bool two = t1 < nterms;
+        double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < k; ++s) {
+            const long long e0 = (long long)s * nterms;
+            const int sc = Bp->scalar_col[s]; // a scalar parameter: no index column to read
+            const double j0 = jb[e0 + t];
+            const double j1 = two ? jb[e0 + t1] : 0.0;
+            const int c0 = sc >= 0 ? sc : cb[e0 + t];
+            const int c1 = sc >= 0 ? sc : (two ? cb[e0 + t1] : c0);
+            u0 = fma(j0, vec[c0], u0);
+            u1 = fma(j1, vec[c1], u1);
+        }
+        if (FUSE) {
+            if (S.sw)
+                u0 *= S.sw[term0 + t];
+            out[term0 + t] = u0;
+            acc = fma(u0, u0, acc);
+            if (two) {
+                if (S.sw)
+                    u1 *= S.sw[term0 + t1];
+                out[term0 + t1] = u1;
+                acc = fma(u1, u1, acc);
+            }
+        } else {
+            S.tmpT[term0 + t] = u0;
+            if (two)
+                S.tmpT[term0 + t1] = u1;
+        }
+    }
+    return acc;
+}
 template <bool FUSE>
 __device__ double sp_term_dot(const SpDev &S, const double *jv, const double *vec, double *out)
 {
     double acc = 0.0;
     for (int b = 0; b < S.nblocks; ++b) {
         const SpBlockDev *Bp = S.blocks + b;
-        const long long term0 = Bp->term0, nterms = Bp->nterms;
-        const int k = Bp->k;
-        const double *jb = jv + Bp->ent0;
-        const int *cb = S.ecol + Bp->ent0;
-        for (long long t = SP_GTID; t < nterms; t += 2 * SP_GSTRIDE) {
-            const long long t1 = t + SP_GSTRIDE;
-            const bool two = t1 < nterms;
-            double u0 = 0.0, u1 = 0.0;
-            for (int s = 0; s < k; ++s) {
-                const long long e0 = (long long)s * nterms;
-                const int sc = Bp->scalar_col[s]; // a scalar parameter: no index column to read
-                const double j0 = jb[e0 + t];
-                const double j1 = two ? jb[e0 + t1] : 0.0;
-                const int c0 = sc >= 0 ? sc : cb[e0 + t];
-                const int c1 = sc >= 0 ? sc : (two ? cb[e0 + t1] : c0);
-                u0 = fma(j0, vec[c0], u0);
-                u1 = fma(j1, vec[c1], u1);
-            }
-            if (FUSE) {
-                if (S.sw)
-                    u0 *= S.sw[term0 + t];
-                out[term0 + t] = u0;
-                acc = fma(u0, u0, acc);
-                if (two) {
-                    if (S.sw)
-                        u1 *= S.sw[term0 + t1];
-                    out[term0 + t1] = u1;
-                    acc = fma(u1, u1, acc);
-                }
-            } else {
-                S.tmpT[term0 + t] = u0;
-                if (two)
-                    S.tmpT[term0 + t1] = u1;
-            }
+        switch (Bp->k) { // same arithmetic in every case; the additions of a thread happen in block order
+        case 1: acc += sp_term_dot_block<FUSE, 1>(S, Bp, jv, vec, out); break;
+        case 2: acc += sp_term_dot_block<FUSE, 2>(S, Bp, jv, vec, out); break;
+        case 3: acc += sp_term_dot_block<FUSE, 3>(S, Bp, jv, vec, out); break;
+        case 4: acc += sp_term_dot_block<FUSE, 4>(S, Bp, jv, vec, out); break;
+        default: acc += sp_term_dot_block<FUSE, 0>(S, Bp, jv, vec, out); break;
         }
     }
     return acc;
@@ -285,6 +303,20 @@ __device__ __forceinline__ double sp_seg_total(const SpSeg &G, const double *ipa
         s += ipart[i];
     return s;
 }
+__device__ __forceinline__ bool sp_seg_is_long(const SpSeg &G, int seg)
+{
+    return G.nlong && G.seg_itemptr[seg + 1] - G.seg_itemptr[seg] > SP_LONG;
+}
+// a long segment's total by one CTA: threads stride its items (each thread adds its items in order), then the
+// fixed-order CTA sum.  Every thread of the CTA must call it.
+__device__ __forceinline__ double sp_seg_total_cta(const SpSeg &G, const double *ipart, int seg, double *sm)
+{
+    double s = 0.0;
+#pragma unroll 4
+    for (int i = G.seg_itemptr[seg] + (int)threadIdx.x; i < G.seg_itemptr[seg + 1]; i += SP_BLOCK)
+        s += ipart[i];
+    return sp_block_sum(s, sm);
+}
 
 // out_r = sw_r * (sum of the row's terms - y_r); sum of squares -> reduction slot.  Contains one grid.sync()
 // when rows aggregate terms.
@@ -298,6 +330,8 @@ __device__ void sp_rowsum(cg::grid_group &grid, const SpDev &S, const double *ts
     }
     double acc = 0.0;
     for (long long r = SP_GTID; r < S.R; r += SP_GSTRIDE) {
+        if (!ident && sp_seg_is_long(S.rows, (int)r))
+            continue;
         double v = ident ? tsrc[r] : sp_seg_total(S.rows, S.rows.ipart, (int)r);
         if (sub_y && S.y)
             v -= S.y[r];
@@ -306,21 +340,53 @@ __device__ void sp_rowsum(cg::grid_group &grid, const SpDev &S, const double *ts
         out[r] = v;
         acc = fma(v, v, acc);
     }
+    if (!ident && S.rows.nlong) {
+        for (int j = blockIdx.x; j < S.rows.nlong; j += gridDim.x) {
+            const int r = S.rows.long_seg[j];
+            double v = sp_seg_total_cta(S.rows, S.rows.ipart, r, sm);
+            if (sub_y && S.y)
+                v -= S.y[r];
+            if (S.sw)
+                v *= S.sw[r];
+            if (threadIdx.x == 0) {
+                out[r] = v;
+                acc = fma(v, v, acc);
+            }
+        }
+    }
     sp_put(S, slot, acc, sm);
 }
 
 // g = J^T u (and jjj = diag(J^T J) when squares) from the nonzeros jv; u is a weighted row vector.  grid.sync()
 // inside; the caller syncs before using g.
 __device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv, const double *u, double *gout,
-                          bool squares)
+                          bool squares, double *sm)
 {
     sp_items<1>(S.cols, jv, u, S.sw, squares);
     grid.sync();
     for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
+        if (sp_seg_is_long(S.cols, (int)k))
+            continue;
         if (gout)
             gout[k] = sp_seg_total(S.cols, S.cols.ipart, (int)k);
         if (squares)
             S.jjj[k] = sp_seg_total(S.cols, S.cols.ipart2, (int)k);
+    }
+    if (S.cols.nlong) {
+        // e.g. the decay rate every row depends on: 1e4 item sums, added by a CTA instead of by the one thread
+        // that owns the column.  The owner reads the result next, hence the barrier.
+        for (int j = blockIdx.x; j < S.cols.nlong; j += gridDim.x) {
+            const int k = S.cols.long_seg[j];
+            const double a = gout ? sp_seg_total_cta(S.cols, S.cols.ipart, k, sm) : 0.0;
+            const double b = squares ? sp_seg_total_cta(S.cols, S.cols.ipart2, k, sm) : 0.0;
+            if (threadIdx.x == 0) {
+                if (gout)
+                    gout[k] = a;
+                if (squares)
+                    S.jjj[k] = b;
+            }
+        }
+        grid.sync();
     }
 }
 
@@ -422,7 +488,7 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
             S.z[k] = fma(alpha, S.d[k], S.z[k]);
         // r -= alpha D^-1 J^T workn
-        sp_colsum(grid, S, jv, S.workn, S.wp, false);
+        sp_colsum(grid, S, jv, S.workn, S.wp, false, sm);
         ++ndfu;
         // (same threads wrote wp[k] and read it: the k loops of colsum and this one use the same mapping)
         acc = 0.0;
@@ -487,9 +553,10 @@ __device__ int sp_test(cg::grid_group &grid, const SpDev &S, double normf, doubl
 }
 
 // J^T f and diag(J^T J) at the accepted point, scaling update (GSL scaling.c)
-__device__ void sp_gradient_and_scale(cg::grid_group &grid, const SpDev &S, const double *jv, const double *f, bool init)
+__device__ void sp_gradient_and_scale(cg::grid_group &grid, const SpDev &S, const double *jv, const double *f, bool init,
+                                      double *sm)
 {
-    sp_colsum(grid, S, jv, f, S.g, true);
+    sp_colsum(grid, S, jv, f, S.g, true, sm);
     for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
         const double Jjj = S.jjj[k];
         const double norm = (Jjj <= 0.0) ? 1.0 : sqrt(Jjj);
@@ -531,7 +598,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
             st.conv = st.info = GSLNLS_EBADFUNC;
             done = true;
         } else {
-            sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], true);
+            sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], true, sm);
             ++st.nevaldfu;
             ++st.nevaldf2;
             double acc = 0.0;
@@ -592,7 +659,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
             if (S.nbad[cur][1] != 0) {
                 iterate_status = GSLNLS_EBADFUNC;
             } else {
-                sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], false);
+                sp_gradient_and_scale(grid, S, S.jv[cur], S.f[cur], false, sm);
                 ++st.nevaldfu;
                 ++st.nevaldf2;
             }
@@ -673,7 +740,7 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
         grid.sync();
         sp_apply_J(grid, S, S.jv[cur], S.d, S.workn, 0, sm);
         grid.sync();
-        sp_colsum(grid, S, S.jv[cur], S.workn, S.jtj + (size_t)c * S.P, false);
+        sp_colsum(grid, S, S.jv[cur], S.workn, S.jtj + (size_t)c * S.P, false, sm);
         grid.sync();
     }
 }
@@ -720,7 +787,7 @@ double *sp_dalloc(size_t n)
 struct SegBuild {
     std::vector<int> ent_a, ent_b;
     std::vector<long long> item_begin;
-    std::vector<int> seg_itemptr, item_a0, item_b0;
+    std::vector<int> seg_itemptr, item_a0, item_b0, long_seg;
 };
 void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
 {
@@ -734,6 +801,10 @@ void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
     }
     B.seg_itemptr[nseg] = (int)B.item_begin.size();
     B.item_begin.push_back(segptr[nseg]);
+    B.long_seg.clear();
+    for (size_t sg = 0; sg < nseg; ++sg)
+        if (B.seg_itemptr[sg + 1] - B.seg_itemptr[sg] > SP_LONG)
+            B.long_seg.push_back((int)sg);
     // items whose entries are consecutive in ent_a (and ent_b)
     const size_t nitems = B.item_begin.size() - 1;
     B.item_a0.assign(nitems, -1);
@@ -908,6 +979,8 @@ void sp_finalize(gslnls_sparse_problem *sp)
         D.rows.seg_itemptr = sp->keep(sp_upload(rb.seg_itemptr));
         D.rows.item_a0 = sp->keep(sp_upload(rb.item_a0));
         D.rows.item_b0 = sp->keep(sp_upload(rb.item_b0));
+        D.rows.long_seg = sp->keep(sp_upload(rb.long_seg));
+        D.rows.nlong = (int)rb.long_seg.size();
         D.rows.nitems = (int)rb.item_begin.size() - 1;
         D.rows.nseg = (int)R;
         D.rows.ipart = sp->keep(sp_dalloc((size_t)D.rows.nitems));
@@ -918,6 +991,8 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.cols.seg_itemptr = sp->keep(sp_upload(cb.seg_itemptr));
     D.cols.item_a0 = sp->keep(sp_upload(cb.item_a0));
     D.cols.item_b0 = sp->keep(sp_upload(cb.item_b0));
+    D.cols.long_seg = sp->keep(sp_upload(cb.long_seg));
+    D.cols.nlong = (int)cb.long_seg.size();
     D.cols.nitems = (int)cb.item_begin.size() - 1;
     D.cols.nseg = P;
     D.cols.ipart = sp->keep(sp_dalloc((size_t)D.cols.nitems));
