@@ -7,11 +7,13 @@
 extern SEXP C_nls_large_cuda(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 extern SEXP C_nls_large_cuda_eval(SEXP, SEXP, SEXP);
 extern SEXP C_nls_large_cuda_free(SEXP);
+extern SEXP C_nls_large_cuda_sparse(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 static const R_CallMethodDef CallEntries[] = {
     {"C_nls_large_cuda", (DL_FUNC)&C_nls_large_cuda, 11},
     {"C_nls_large_cuda_eval", (DL_FUNC)&C_nls_large_cuda_eval, 3},
     {"C_nls_large_cuda_free", (DL_FUNC)&C_nls_large_cuda_free, 1},
+    {"C_nls_large_cuda_sparse", (DL_FUNC)&C_nls_large_cuda_sparse, 8},
     {NULL, NULL, 0}};
 
 void R_init_gslnlscuda(DllInfo *dll)

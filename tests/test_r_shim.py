@@ -57,6 +57,12 @@ def test_r_front_end_packs_control_like_the_reference():
     assert "useDynLib(gslnlscuda, .registration = TRUE)" in ns
     init = open(os.path.join(ROOT, "r-package", "src", "init.c")).read()
     assert '{"C_nls_large_cuda", (DL_FUNC)&C_nls_large_cuda, 11}' in init
+    assert '{"C_nls_large_cuda_sparse", (DL_FUNC)&C_nls_large_cuda_sparse, 8}' in init
+    sp = open(os.path.join(ROOT, "r-package", "R", "nls_large_cuda_sparse.R")).read()
+    for piece in ("C_nls_large_cuda_sparse", '.cuda_pack_control(control, "cgst", trace)', "negative residual degrees of freedom",
+                  'class(out) <- c("gsl_nls", "nls")'):
+        assert piece in sp, piece
+    assert "export(gsl_nls_large_cuda_sparse)" in ns and "export(nls_block)" in ns
 
 
 @pytest.mark.gpu
@@ -88,3 +94,49 @@ def test_shim_fits_example1_on_gpu(tmp_path, readme_examples, alg, wmode):
     assert d["grad_last"] == pytest.approx(ref["grad"][-1, 2], rel=1e-7)
     assert d["released"] == 1
     assert d["algorithm"] == ["levenberg-marquardt", "levenberg-marquardt+accel", "dogleg"][alg]
+
+
+SPARSE_DRIVER = os.path.join(STUB, "_build", "sparse_driver")
+
+
+def test_sparse_shim_is_small_and_refuses_without_a_gpu():
+    """r-package/src/nls_large_cuda_sparse.c: the .Call shim of the sparse-Jacobian path"""
+    src = os.path.join(ROOT, "r-package", "src", "nls_large_cuda_sparse.c")
+    assert sum(1 for _ in open(src)) < 150 and "oracle" not in open(src).read()
+    _build()
+    import gslnls_b200._lib as L
+    if L.lib().gslnls_device_count() > 0:
+        pytest.skip("a GPU is present: covered by the gpu test below")
+    r = subprocess.run([SPARSE_DRIVER, "10", "0", "100"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p,start,maxiter", [(10, 0, 100), (500, 1, 500)])
+def test_sparse_shim_fits_penalty_on_gpu(p, start, maxiter, readme_examples):
+    """inst/unit_tests/unit_tests_gslnls.R:316-346 (p = 10) and README Example 4 (p = 500) through the R shim"""
+    import math
+    from oracle import oracle as O
+    _build()
+    r = subprocess.run([SPARSE_DRIVER, str(p), str(start), str(maxiter)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["names"] == ["par", "niter", "status", "conv", "ssr", "ssrtol", "neval", "ssrtrace", "grad_vec", "jtj",
+                            "resid", "cg_iters", "nnz"]
+    assert out["conv"] == 0 and out["status"] == "success" and out["nnz"] == 2 * p
+    assert out["ntrace"] == out["niter"] + 1 and abs(out["resid_ss"] - out["ssr"]) <= 1e-12 * out["ssr"]
+    assert out["jtj_is_null"] == (p > 64)
+    sa = math.sqrt(1e-5)
+    eye = np.eye(p) * sa
+
+    def rows(th, v, wf, wJ, wh):
+        return (np.concatenate([sa * (th - 1), [np.sum(th ** 2)]]), np.vstack([eye, 2 * th[None, :]]) if wJ else None, None)
+    y = np.zeros(p + 1)
+    y[p] = 0.25
+    st = np.arange(1, p + 1, dtype=float) if start else np.full(p, 0.15)
+    ref = O.nls_large(rows, y, st, algorithm="cgst", maxiter=maxiter)
+    assert out["niter"] == ref["niter"] and abs(out["ssr"] - ref["ssr"]) <= 1e-8 * ref["ssr"]
+    if p == 500:
+        assert float("%.7g" % out["ssr"]) == readme_examples["example4_penalty"]["ssr_print"]
+    else:
+        assert np.max(np.abs(np.array(out["par"]) - ref["par"]) / np.abs(ref["par"])) < 1e-8
