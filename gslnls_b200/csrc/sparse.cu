@@ -30,6 +30,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -53,6 +54,7 @@ namespace {
 constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
+constexpr int SP_VAR_DEFAULT = 3;
 constexpr int SP_LONG = 64;   // items per segment above which a CTA adds them
 constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
                                    // GSLNLS_SP_MINB overrides (A/B in profiles/r02_summary.md)
@@ -76,7 +78,7 @@ struct SpSeg {
     const int *seg_itemptr;      // [nseg + 1] item ranges of each segment
     const int *long_seg;         // [nlong] segments of more than SP_LONG items (a parameter every row depends on, a
     int nlong;                   // dense row): their item sums are added by a whole CTA instead of one thread
-    int nitems, nseg;
+    int nitems, nseg, var;
     double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
 };
 
@@ -93,6 +95,8 @@ struct SpState {
 
 struct SpDev {
     int P, R, nblocks, maxiter, scale, want_trace;
+    int var; // loop variants (GSLNLS_SP_VAR bits): 1 = adjacent term pairs with 128-bit loads in J v, 2 = 8-deep item loads,
+             // 4 = four adjacent terms per thread
     long long T, E;
     long long cg_maxit;
     double factor_up, factor_down, xtol, gtol, cg_tol;
@@ -110,6 +114,7 @@ struct SpDev {
     SpState *host_st;  // mapped host copy written at the end of every launch
     double *ssrtrace;  // [maxiter + 1]
     double *jtj;       // [P * P] column-major, filled by sp_jtj on request
+    unsigned long long *trace; // [SP_NSTAMP] count + (globaltimer << 4 | phase code) stamps, or nullptr
 };
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -165,6 +170,20 @@ __device__ double sp_block_max(double v, double *sm)
     return s;
 }
 
+// phase stamps of the first CG iterations of a launch (GSLNLS_SP_TRACE=file; tools/trace_sparse.py reads them)
+#define SP_NSTAMP 256
+#define SP_STAMP(S, code)                                                                  \
+    do {                                                                                   \
+        if ((S).trace && blockIdx.x == 0 && threadIdx.x == 0) {                            \
+            const unsigned long long n__ = (S).trace[0];                                   \
+            if (n__ + 1 < SP_NSTAMP) {                                                     \
+                unsigned long long t__;                                                    \
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                    \
+                (S).trace[1 + n__] = (t__ << 4) | (unsigned long long)(code);              \
+                (S).trace[0] = n__ + 1;                                                    \
+            }                                                                              \
+        }                                                                                  \
+    } while (0)
 #define SP_GTID ((long long)blockIdx.x * SP_BLOCK + threadIdx.x)
 #define SP_GSTRIDE ((long long)gridDim.x * SP_BLOCK)
 
@@ -187,6 +206,87 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
     const int k = K > 0 ? K : Bp->k;
     const double *jb = jv + Bp->ent0;
     const int *cb = S.ecol + Bp->ent0;
+    if (K > 0 && (S.var & 4) && ((nterms | Bp->ent0 | term0) & 3) == 0) {
+        // four adjacent terms per thread: 1 KB (values) / 512 B (indices) contiguous per warp and load
+        const long long nquad = nterms >> 2;
+        for (long long i = SP_GTID; i < nquad; i += SP_GSTRIDE) {
+            double2 ja[K > 0 ? K : 1], jb2[K > 0 ? K : 1];
+            int4 c[K > 0 ? K : 1];
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const long long e0 = (long long)s * nterms + 4 * i;
+                const int sc = Bp->scalar_col[s];
+                ja[s] = *reinterpret_cast<const double2 *>(jb + e0);
+                jb2[s] = *reinterpret_cast<const double2 *>(jb + e0 + 2);
+                c[s] = make_int4(sc, sc, sc, sc);
+                if (sc < 0)
+                    c[s] = *reinterpret_cast<const int4 *>(cb + e0);
+            }
+            double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                u0 = fma(ja[s].x, vec[c[s].x], u0);
+                u1 = fma(ja[s].y, vec[c[s].y], u1);
+                u2 = fma(jb2[s].x, vec[c[s].z], u2);
+                u3 = fma(jb2[s].y, vec[c[s].w], u3);
+            }
+            const long long r = term0 + 4 * i;
+            if (FUSE) {
+                if (S.sw) {
+                    u0 *= S.sw[r];
+                    u1 *= S.sw[r + 1];
+                    u2 *= S.sw[r + 2];
+                    u3 *= S.sw[r + 3];
+                }
+                *reinterpret_cast<double2 *>(out + r) = make_double2(u0, u1);
+                *reinterpret_cast<double2 *>(out + r + 2) = make_double2(u2, u3);
+                acc = fma(u0, u0, acc);
+                acc = fma(u1, u1, acc);
+                acc = fma(u2, u2, acc);
+                acc = fma(u3, u3, acc);
+            } else {
+                *reinterpret_cast<double2 *>(S.tmpT + r) = make_double2(u0, u1);
+                *reinterpret_cast<double2 *>(S.tmpT + r + 2) = make_double2(u2, u3);
+            }
+        }
+        return acc;
+    }
+    if (K > 0 && (S.var & 1) && ((nterms | Bp->ent0 | term0) & 1) == 0) {
+        // adjacent term pairs: every load of a warp is one contiguous 512-byte (values) / 256-byte (indices) piece
+        const long long npair = nterms >> 1;
+        for (long long i = SP_GTID; i < npair; i += SP_GSTRIDE) {
+            double2 j[K > 0 ? K : 1];
+            int2 c[K > 0 ? K : 1];
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const long long e0 = (long long)s * nterms + 2 * i;
+                const int sc = Bp->scalar_col[s];
+                j[s] = *reinterpret_cast<const double2 *>(jb + e0);
+                c[s] = make_int2(sc, sc);
+                if (sc < 0)
+                    c[s] = *reinterpret_cast<const int2 *>(cb + e0);
+            }
+            double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                u0 = fma(j[s].x, vec[c[s].x], u0);
+                u1 = fma(j[s].y, vec[c[s].y], u1);
+            }
+            const long long r = term0 + 2 * i;
+            if (FUSE) {
+                if (S.sw) {
+                    u0 *= S.sw[r];
+                    u1 *= S.sw[r + 1];
+                }
+                *reinterpret_cast<double2 *>(out + r) = make_double2(u0, u1);
+                acc = fma(u0, u0, acc);
+                acc = fma(u1, u1, acc);
+            } else {
+                *reinterpret_cast<double2 *>(S.tmpT + r) = make_double2(u0, u1);
+            }
+        }
+        return acc;
+    }
     for (long long t = SP_GTID; t < nterms; t += 2 * SP_GSTRIDE) {
         const long long t1 = t + SP_GSTRIDE;
         const bool two = t1 < nterms;
@@ -261,6 +361,23 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
                 const int b0 = G.item_b0[it];
                 const double *wp = wv ? wv + b0 : nullptr;
                 const double *swp = sw ? sw + b0 : nullptr;
+                if ((G.var & 2) && wp && !swp && !squares) {
+                    // the CG iteration's case, 8 x 32 entries per trip: all loads of a trip in flight, the additions
+                    // of a lane in the same order as below
+                    for (int base = lane; base < len; base += 256) {
+                        double jq[8], wq[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = base + 32 * q;
+                            jq[q] = i < len ? sp[i] : 0.0;
+                            wq[q] = i < len ? wp[i] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (base + 32 * q < len)
+                                s = fma(jq[q], wq[q], s);
+                    }
+                } else
 #pragma unroll 4
                 for (int i = lane; i < len; i += 32) {
                     const double j = swp ? sp[i] * swp[i] : sp[i];
@@ -364,6 +481,7 @@ __device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv
 {
     sp_items<1>(S.cols, jv, u, S.sw, squares);
     grid.sync();
+    SP_STAMP(S, 3); // column items done
     for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
         if (sp_seg_is_long(S.cols, (int)k))
             continue;
@@ -447,10 +565,12 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         sp_put(S, 2, dd, sm);
         sp_put(S, 3, zd, sm);
         grid.sync();
+        SP_STAMP(S, 1); // P-vector prologue done
         // workn = J D^-1 d
         sp_apply_J(grid, S, jv, S.wp, S.workn, 0, sm);
         ++ndfu;
         grid.sync();
+        SP_STAMP(S, 2); // J d done
         const double normJd2 = sp_total(S, 0, sm);
         zz = sp_total(S, 1, sm);
         dd = sp_total(S, 2, sm);
@@ -499,6 +619,7 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         }
         sp_put(S, 0, acc, sm);
         grid.sync();
+        SP_STAMP(S, 4); // J^T u totals + r update done
         const double norm_rp1_2 = sp_total(S, 0, sm);
         if (sqrt(norm_rp1_2) / cg_norm_g < S.cg_tol) {
             exit_kind = 0;
@@ -579,6 +700,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
     __shared__ double sm[SP_BLOCK / 32];
     SpState st = *S.st;
     grid.sync(); // every thread holds its copy before thread 0 rewrites the state at the end
+    SP_STAMP(S, 0);
     int cur = st.cur;
     bool done = false, need_step = false;
     int iterate_status = 0;
@@ -944,6 +1066,7 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.T = T;
     D.E = E;
     D.nblocks = (int)sp->blocks.size();
+    D.var = std::getenv("GSLNLS_SP_VAR") ? std::atoi(std::getenv("GSLNLS_SP_VAR")) : SP_VAR_DEFAULT;
     std::vector<SpBlockDev> bd;
     for (auto &b : sp->blocks) {
         SpBlockDev d{};
@@ -995,6 +1118,7 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.cols.nlong = (int)cb.long_seg.size();
     D.cols.nitems = (int)cb.item_begin.size() - 1;
     D.cols.nseg = P;
+    D.cols.var = D.var;
     D.cols.ipart = sp->keep(sp_dalloc((size_t)D.cols.nitems));
     D.cols.ipart2 = sp->keep(sp_dalloc((size_t)D.cols.nitems));
     D.tmpT = sp->keep(sp_dalloc((size_t)T));
@@ -1254,8 +1378,18 @@ GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start,
         SPCK(cudaEventRecord(ev.e[0], sp->stream));
         sp_launch_evals(sp, D.x, 0);
         long long launches = 0;
+        const char *trace_path = std::getenv("GSLNLS_SP_TRACE");
+        struct TraceBuf {
+            unsigned long long *d = nullptr;
+            ~TraceBuf() { cudaFree(d); }
+        } tb;
+        if (trace_path)
+            SPCK(cudaMalloc(&tb.d, SP_NSTAMP * sizeof(unsigned long long)));
+        D.trace = tb.d;
         for (;;) {
             void *args[] = {&D};
+            if (tb.d)
+                SPCK(cudaMemsetAsync(tb.d, 0, SP_NSTAMP * sizeof(unsigned long long), sp->stream));
             SPCK(cudaEventRecord(ev.e[1], sp->stream));
             SPCK(cudaLaunchCooperativeKernel(sp->step_fn, dim3((unsigned)sp->grid), dim3(SP_BLOCK), args, 0,
                                              sp->stream));
@@ -1268,11 +1402,22 @@ GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start,
             SPCK(cudaEventElapsedTime(&ms, ev.e[1], ev.e[2]));
             solver_ms += ms;
             st = *sp->h_state;
+            if (tb.d) {
+                unsigned long long h[SP_NSTAMP];
+                SPCK(cudaMemcpy(h, tb.d, sizeof h, cudaMemcpyDeviceToHost));
+                if (FILE *fh = std::fopen(trace_path, "a")) {
+                    std::fprintf(fh, "launch %lld ms %.4f n %llu\n", launches, (double)ms, h[0]);
+                    for (unsigned long long i = 0; i < h[0]; ++i)
+                        std::fprintf(fh, "%llu %llu\n", h[1 + i] & 15ull, h[1 + i] >> 4);
+                    std::fclose(fh);
+                }
+            }
             if (st.phase == SP_PH_DONE)
                 break;
             SPCK(cudaEventRecord(ev.e[0], sp->stream));
             sp_launch_evals(sp, D.x_trial, 1 - st.cur);
         }
+        D.trace = nullptr;
         out->eval_ms = eval_ms;
         out->solver_ms = solver_ms;
         out->p = P;
