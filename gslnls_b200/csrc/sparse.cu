@@ -54,7 +54,7 @@ namespace {
 constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
-constexpr int SP_VAR_DEFAULT = 3;
+constexpr int SP_VAR_DEFAULT = 7;
 constexpr int SP_LONG = 64;   // items per segment above which a CTA adds them
 constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
                                    // GSLNLS_SP_MINB overrides (A/B in profiles/r02_summary.md)

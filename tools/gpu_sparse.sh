@@ -7,7 +7,7 @@ timeout 400 python bench.py --config sparse > gpurun_out/r02_bench_sparse.json 2
 echo "bench rc=$?"; cat gpurun_out/r02_bench_sparse.json; tail -5 gpurun_out/r02_bench_sparse.err
 fi
 if [ "$1" = "ncu" ] || [ "$2" = "ncu" ]; then
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_sparse_launches.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_sparse_launches.csv \
     python bench.py --config sparse --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2> gpurun_out/r02_sparse_launches.err
 echo "launch list rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:sp_step -s 2 -c 2 -o /tmp/r02_sparse_full -f \
