@@ -55,6 +55,7 @@ constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
 constexpr int SP_VAR_DEFAULT = 7;
+constexpr int SP_SHORT = 8;   // entries per item up to which one thread adds them
 constexpr int SP_LONG = 64;   // items per segment above which a CTA adds them
 constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
                                    // GSLNLS_SP_MINB overrides (A/B in profiles/r02_summary.md)
@@ -79,6 +80,8 @@ struct SpSeg {
     const int *long_seg;         // [nlong] segments of more than SP_LONG items (a parameter every row depends on, a
     int nlong;                   // dense row): their item sums are added by a whole CTA instead of one thread
     int nitems, nseg, var;
+    const int *wide_item;        // [nwide] items of more than SP_SHORT entries (one warp each), or nullptr = all of them;
+    int nwide, nshort;           // the others (a column with a handful of nonzeros) take one thread each
     double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
 };
 
@@ -184,6 +187,15 @@ __device__ double sp_block_max(double v, double *sm)
             }                                                                              \
         }                                                                                  \
     } while (0)
+// the grid barrier; a one-CTA grid (a problem of a few thousand nonzeros) needs only the CTA barrier, which also
+// orders the CTA's global-memory accesses -- 0.3 us instead of the 2-3 us of the atomic + fences of grid.sync()
+__device__ __forceinline__ void sp_sync(cg::grid_group &grid)
+{
+    if (gridDim.x == 1)
+        __syncthreads();
+    else
+        grid.sync();
+}
 #define SP_GTID ((long long)blockIdx.x * SP_BLOCK + threadIdx.x)
 #define SP_GSTRIDE ((long long)gridDim.x * SP_BLOCK)
 
@@ -346,7 +358,34 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
 {
     const int lane = threadIdx.x & 31;
     const long long warp = SP_GTID >> 5, nwarp = SP_GSTRIDE >> 5;
-    for (long long it = warp; it < G.nitems; it += nwarp) {
+    if (G.nshort) {
+        // short items, one thread each, entries added in order (a warp per 2-entry column would idle 30 lanes and
+        // serialise ~60 dependent load chains per warp on a small problem)
+        for (long long it = SP_GTID; it < G.nitems; it += SP_GSTRIDE) {
+            const long long a = G.item_begin[it], b = G.item_begin[it + 1];
+            if (b - a > SP_SHORT)
+                continue;
+            double s = 0.0, s2 = 0.0;
+            for (long long e = a; e < b; ++e) {
+                if (KIND == 0) {
+                    s += src[G.ent_a[e]];
+                } else {
+                    const int row = G.ent_b[e];
+                    const double jj = src[G.ent_a[e]];
+                    const double j = sw ? jj * sw[row] : jj;
+                    if (wv)
+                        s = fma(j, wv[row], s);
+                    if (squares)
+                        s2 = fma(j, j, s2);
+                }
+            }
+            G.ipart[it] = s;
+            if (squares)
+                G.ipart2[it] = s2;
+        }
+    }
+    for (long long jw = warp; jw < G.nwide; jw += nwarp) {
+        const long long it = G.wide_item ? G.wide_item[jw] : jw;
         const long long a = G.item_begin[it], b = G.item_begin[it + 1];
         const int a0 = G.item_a0[it];
         double s = 0.0, s2 = 0.0;
@@ -443,7 +482,7 @@ __device__ void sp_rowsum(cg::grid_group &grid, const SpDev &S, const double *ts
     const bool ident = S.rows.ent_a == nullptr;
     if (!ident) {
         sp_items<0>(S.rows, tsrc, nullptr, nullptr, false);
-        grid.sync();
+        sp_sync(grid);
     }
     double acc = 0.0;
     for (long long r = SP_GTID; r < S.R; r += SP_GSTRIDE) {
@@ -480,7 +519,7 @@ __device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv
                           bool squares, double *sm)
 {
     sp_items<1>(S.cols, jv, u, S.sw, squares);
-    grid.sync();
+    sp_sync(grid);
     SP_STAMP(S, 3); // column items done
     for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE) {
         if (sp_seg_is_long(S.cols, (int)k))
@@ -504,7 +543,7 @@ __device__ void sp_colsum(cg::grid_group &grid, const SpDev &S, const double *jv
                     S.jjj[k] = b;
             }
         }
-        grid.sync();
+        sp_sync(grid);
     }
 }
 
@@ -517,7 +556,7 @@ __device__ void sp_apply_J(cg::grid_group &grid, const SpDev &S, const double *j
         sp_put(S, slot, sp_term_dot<true>(S, jv, vec, out), sm);
     } else {
         sp_term_dot<false>(S, jv, vec, nullptr);
-        grid.sync();
+        sp_sync(grid);
         sp_rowsum(grid, S, S.tmpT, out, false, slot, sm);
     }
 }
@@ -539,7 +578,7 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         acc = fma(v, v, acc);
     }
     sp_put(S, 0, acc, sm);
-    grid.sync();
+    sp_sync(grid);
     double norm_r2 = sp_total(S, 0, sm);
     const double cg_norm_g = sqrt(norm_r2);
     int exit_kind = -1; // 0: z / D, 1: (z + tau d) / D
@@ -564,12 +603,12 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         sp_put(S, 1, zz, sm);
         sp_put(S, 2, dd, sm);
         sp_put(S, 3, zd, sm);
-        grid.sync();
+        sp_sync(grid);
         SP_STAMP(S, 1); // P-vector prologue done
         // workn = J D^-1 d
         sp_apply_J(grid, S, jv, S.wp, S.workn, 0, sm);
         ++ndfu;
-        grid.sync();
+        sp_sync(grid);
         SP_STAMP(S, 2); // J d done
         const double normJd2 = sp_total(S, 0, sm);
         zz = sp_total(S, 1, sm);
@@ -618,7 +657,7 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
             acc = fma(rk, rk, acc);
         }
         sp_put(S, 0, acc, sm);
-        grid.sync();
+        sp_sync(grid);
         SP_STAMP(S, 4); // J^T u totals + r update done
         const double norm_rp1_2 = sp_total(S, 0, sm);
         if (sqrt(norm_rp1_2) / cg_norm_g < S.cg_tol) {
@@ -635,7 +674,7 @@ __device__ int sp_cgst(cg::grid_group &grid, const SpDev &S, const double *jv, d
         S.dx[k] = v;
         S.x_trial[k] = S.x[k] + v;
     }
-    grid.sync();
+    sp_sync(grid);
     return status;
 }
 
@@ -656,7 +695,7 @@ __device__ int sp_test(cg::grid_group &grid, const SpDev &S, double normf, doubl
         S.red[(size_t)4 * gridDim.x + blockIdx.x] = viol;
         S.red[(size_t)5 * gridDim.x + blockIdx.x] = gmax;
     }
-    grid.sync();
+    sp_sync(grid);
     viol = 0.0;
     gmax = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += SP_BLOCK) {
@@ -690,7 +729,7 @@ __device__ void sp_gradient_and_scale(cg::grid_group &grid, const SpDev &S, cons
             dk = init ? fmax(0.0, norm) : fmax(S.diag[k], norm);
         S.diag[k] = dk;
     }
-    grid.sync();
+    sp_sync(grid);
 }
 
 template <int MINB>
@@ -699,7 +738,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[SP_BLOCK / 32];
     SpState st = *S.st;
-    grid.sync(); // every thread holds its copy before thread 0 rewrites the state at the end
+    sp_sync(grid); // every thread holds its copy before thread 0 rewrites the state at the end
     SP_STAMP(S, 0);
     int cur = st.cur;
     bool done = false, need_step = false;
@@ -710,7 +749,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
         // trust_init (oracle/multilarge.c:1104-1140): f, g = J^T f, J^T J (its diagonal), D, delta
         sp_rowsum(grid, S, S.tv[cur], S.f[cur], true, 0, sm);
         ++st.nevalf;
-        grid.sync();
+        sp_sync(grid);
         const double ff = sp_total(S, 0, sm);
         st.normf = sqrt(ff);
         st.chisq_init = st.chisq1 = ff;
@@ -730,7 +769,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
                 S.dx[k] = 0.0;
             }
             sp_put(S, 0, acc, sm);
-            grid.sync();
+            sp_sync(grid);
             st.delta = 0.3 * fmax(1.0, sqrt(sp_total(S, 0, sm)));
             st.chisq0 = st.chisq1; // driver2: first iterate call
             st.bad_steps = 0;
@@ -752,7 +791,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
             gdx = fma(S.g[k], S.dx[k], gdx);
         sp_put(S, 2, gdx, sm);
         sp_apply_J(grid, S, S.jv[cur], S.dx, S.workn, 1, sm);
-        grid.sync();
+        sp_sync(grid);
         const double ff_trial = sp_total(S, 0, sm);
         gdx = sp_total(S, 2, sm);
         const double jdx2 = sp_total(S, 1, sm);
@@ -808,7 +847,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
             ++st.iter;
             if (S.want_trace && SP_GTID == 0)
                 S.ssrtrace[st.iter] = st.chisq1;
-            grid.sync(); // x, g complete
+            sp_sync(grid); // x, g complete
             const int info = sp_test(grid, S, st.normf, sm);
             if (info) {
                 st.conv = 0;
@@ -829,7 +868,7 @@ __global__ void __launch_bounds__(SP_BLOCK, MINB) sp_step(const SpDev S)
         }
         if (need_step) {
             need_step = false;
-            grid.sync();
+            sp_sync(grid);
             const int s = sp_cgst(grid, S, S.jv[cur], st.delta, st.cg_iters, st.nevaldfu, sm);
             if (s == 0)
                 break; // x_trial is ready: the host evaluates it
@@ -859,11 +898,11 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
     for (int c = 0; c < S.P; ++c) {
         for (long long k = SP_GTID; k < S.P; k += SP_GSTRIDE)
             S.d[k] = (k == c) ? 1.0 : 0.0;
-        grid.sync();
+        sp_sync(grid);
         sp_apply_J(grid, S, S.jv[cur], S.d, S.workn, 0, sm);
-        grid.sync();
+        sp_sync(grid);
         sp_colsum(grid, S, S.jv[cur], S.workn, S.jtj + (size_t)c * S.P, false, sm);
-        grid.sync();
+        sp_sync(grid);
     }
 }
 
@@ -909,7 +948,8 @@ double *sp_dalloc(size_t n)
 struct SegBuild {
     std::vector<int> ent_a, ent_b;
     std::vector<long long> item_begin;
-    std::vector<int> seg_itemptr, item_a0, item_b0, long_seg;
+    std::vector<int> seg_itemptr, item_a0, item_b0, long_seg, wide_item;
+    int nshort = 0;
 };
 void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
 {
@@ -929,6 +969,11 @@ void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
             B.long_seg.push_back((int)sg);
     // items whose entries are consecutive in ent_a (and ent_b)
     const size_t nitems = B.item_begin.size() - 1;
+    B.wide_item.clear();
+    for (size_t it = 0; it < nitems; ++it)
+        if (B.item_begin[it + 1] - B.item_begin[it] > SP_SHORT)
+            B.wide_item.push_back((int)it);
+    B.nshort = (int)(nitems - B.wide_item.size());
     B.item_a0.assign(nitems, -1);
     B.item_b0.assign(nitems, -1);
     for (size_t it = 0; it < nitems; ++it) {
@@ -1104,6 +1149,9 @@ void sp_finalize(gslnls_sparse_problem *sp)
         D.rows.item_b0 = sp->keep(sp_upload(rb.item_b0));
         D.rows.long_seg = sp->keep(sp_upload(rb.long_seg));
         D.rows.nlong = (int)rb.long_seg.size();
+        D.rows.nshort = rb.nshort;
+        D.rows.nwide = (int)rb.wide_item.size();
+        D.rows.wide_item = rb.nshort ? sp->keep(sp_upload(rb.wide_item)) : nullptr;
         D.rows.nitems = (int)rb.item_begin.size() - 1;
         D.rows.nseg = (int)R;
         D.rows.ipart = sp->keep(sp_dalloc((size_t)D.rows.nitems));
@@ -1116,6 +1164,9 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.cols.item_b0 = sp->keep(sp_upload(cb.item_b0));
     D.cols.long_seg = sp->keep(sp_upload(cb.long_seg));
     D.cols.nlong = (int)cb.long_seg.size();
+    D.cols.nshort = cb.nshort;
+    D.cols.nwide = (int)cb.wide_item.size();
+    D.cols.wide_item = cb.nshort ? sp->keep(sp_upload(cb.wide_item)) : nullptr;
     D.cols.nitems = (int)cb.item_begin.size() - 1;
     D.cols.nseg = P;
     D.cols.var = D.var;
