@@ -165,3 +165,21 @@ def test_nvrtc_compiles_every_k1_load_path_for_sm100a(monkeypatch, tune):
     assert "nls_model_fj" in m.source
     m2 = Model("A * exp(-lam * x) + b", ["A", "lam", "b"], ["x"], jac="center", fvv="fd")
     assert "nls_model_f" in m2.source
+
+
+def test_compiled_modules_are_cached_per_process(monkeypatch):
+    """the host language compiles 'the same formula' on every .Call: the second NVRTC compile of an identical
+    module (generated source + options) is served from the process-wide cache; a different module is not"""
+    import time
+    rhs = "A * exp(-lam * x) + b + 0.125"
+    t0 = time.perf_counter()
+    Model(rhs, ["A", "lam", "b"], ["x"], jac=True)
+    first = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m2 = Model(rhs, ["A", "lam", "b"], ["x"], jac=True)
+    second = time.perf_counter() - t0
+    assert second < 0.25 * first and "nls_model_fj" in m2.source
+    monkeypatch.setenv("GSLNLS_TUNE", "tiled=0,block=128,unroll=2,minb=2,prefetch=0,fexp=0")  # other options: a miss
+    t0 = time.perf_counter()
+    Model(rhs, ["A", "lam", "b"], ["x"], jac=True)
+    assert time.perf_counter() - t0 > 4 * second
