@@ -195,9 +195,12 @@ def test_nist_fits(G, nist_problems, name):
         got = np.array(list(fit.coef().values()))
         assert fit.convInfo["stopCode"] == ref["conv"], (name, alg)
         if ref["conv"] == 0 and name != "BoxBOD":
+            # Thurber: the oracle against itself (rows permuted / long-double accumulators) differs by up to 3
+            # iterations and 5.4e-8 in the coefficients -- tests/test_oracle_pins.py::
+            # test_thurber_iteration_count_is_not_pinned_by_the_algorithm; the gate is 10 x that sensitivity
             hard = name in ("Thurber",)
             assert abs(fit.convInfo["finIter"] - ref["niter"]) <= (3 if hard else 0), (name, alg)
-            assert np.allclose(got, ref["par"], rtol=5e-6 if hard else 1e-8), (name, alg)
+            assert np.allclose(got, ref["par"], rtol=5e-7 if hard else 1e-8), (name, alg)
             assert fit.deviance() == pytest.approx(ref["ssr"], rel=1e-8)
             assert np.max(np.abs(got - np.array(pr["target"])) / np.abs(pr["target"])) < 1e-6, (name, alg)
 

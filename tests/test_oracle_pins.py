@@ -190,3 +190,30 @@ def test_longdouble_accumulation_agrees(readme_examples):
     b = O.eval_packet("exp3", y, [1.0, 1.0, 0.0], x=x, longdouble=True)
     assert np.allclose(a, b, rtol=1e-14)
     assert a.size == 10
+
+
+def test_thurber_iteration_count_is_not_pinned_by_the_algorithm(nist_problems):
+    """Why tests/test_gpu_parity.py::test_nist_fits holds Thurber (NIST "higher difficulty", 7 parameters, start 1) to
+    niter +- 3 and 5e-7 on the coefficients instead of equality and 1e-8: the oracle itself, with nothing changed
+    but the order in which the 37 observations are added (rows permuted) or the width of the accumulators (long
+    double), moves by up to three iterations and ~5e-8 in the coefficients, while SSR agrees to 1e-12 -- the
+    trust-region path through this problem's flat valley is decided by roundings.  A CUDA kernel with yet another
+    (fixed) summation order cannot be asked to reproduce one particular of these paths."""
+    pr = nist_problems["Thurber"]
+    x, y = np.array(pr["data"]["x"]), np.array(pr["data"]["y"])
+    rhs = O.split_formula(pr["formula"])[1]
+    perm = np.random.default_rng(1).permutation(y.size)
+    spread_iter, spread_par = 0, 0.0
+    for alg in ("lm", "lmaccel", "dogleg", "ddogleg", "subspace2D", "cgst"):
+        runs = []
+        for xx, yy, ld in ((x, y, False), (x, y, True), (x[perm], y[perm], False)):
+            r = O.nls_large(O.sympy_rows(rhs, pr["param_names"], {"x": xx}), yy, pr["start"], algorithm=alg, longdouble=ld)
+            assert r["conv"] == 0
+            runs.append(r)
+        base = runs[0]
+        for r in runs[1:]:
+            assert abs(r["ssr"] - base["ssr"]) <= 1e-12 * base["ssr"]
+            spread_iter = max(spread_iter, abs(r["niter"] - base["niter"]))
+            spread_par = max(spread_par, float(np.max(np.abs(r["par"] - base["par"]) / np.abs(base["par"]))))
+    assert 1 <= spread_iter <= 3          # observed: up to 3 (subspace2D 43 / 42 / 40)
+    assert 1e-8 < spread_par < 5e-7       # observed: 5.4e-8
