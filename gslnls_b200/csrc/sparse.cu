@@ -40,6 +40,7 @@
 #include "../../include/gslnls_b200.h"
 #include "model.hpp"
 #include "nls_abi.h"
+#include "trs_launch.hpp"
 
 namespace cg = cooperative_groups;
 
@@ -906,6 +907,40 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
     }
 }
 
+// Dense normal-equation packet [J^T J lower packed, row-major | J^T f | f^T f | non-finite residual count] of a
+// sparse-row problem at the point evaluated into buffer `buf`: what K3 (csrc/trs_core.h, the dense trust-region
+// state machine: lm, dogleg, ddogleg, subspace2D) consumes.  J^T J column c is J^T (J e_c) from the stored
+// nonzeros, P <= 100 columns -- the reference densifies J for the same purpose (src/nls_large.c:641-648).
+__global__ void __launch_bounds__(SP_BLOCK) sp_packet(const SpDev S, double *packet, int buf)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[SP_BLOCK / 32];
+    const int P = S.P, npk = P * (P + 1) / 2;
+    sp_rowsum(grid, S, S.tv[buf], S.f[buf], true, 0, sm);
+    sp_sync(grid);
+    const double ff = sp_total(S, 0, sm);
+    sp_colsum(grid, S, S.jv[buf], S.f[buf], S.g, false, sm);
+    sp_sync(grid);
+    for (int c = 0; c < P; ++c) {
+        for (long long k = SP_GTID; k < P; k += SP_GSTRIDE)
+            S.d[k] = (k == c) ? 1.0 : 0.0;
+        sp_sync(grid);
+        sp_apply_J(grid, S, S.jv[buf], S.d, S.workn, 1, sm);
+        sp_sync(grid);
+        sp_colsum(grid, S, S.jv[buf], S.workn, S.wp, false, sm);
+        sp_sync(grid);
+        for (long long k = SP_GTID; k < P; k += SP_GSTRIDE)
+            if (k >= c)
+                packet[k * (k + 1) / 2 + c] = S.wp[k];
+    }
+    for (long long k = SP_GTID; k < P; k += SP_GSTRIDE)
+        packet[npk + k] = S.g[k];
+    if (SP_GTID == 0) {
+        packet[npk + P] = ff;
+        packet[npk + P + 1] = (double)S.nbad[buf][0];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 #define SPCK(call)                                                                                    \
     do {                                                                                              \
@@ -1002,6 +1037,7 @@ struct gslnls_sparse_problem {
     cudaStream_t stream = nullptr;
     int grid = 0;
     const void *step_fn = nullptr; // sp_step<MINB>
+    int grid_packet = 1;           // cooperative grid of sp_packet
     SpDev dev{};
     SpState *h_state = nullptr; // mapped pinned
     std::vector<void *> owned;  // device allocations
@@ -1190,6 +1226,11 @@ void sp_finalize(gslnls_sparse_problem *sp)
     const long long work = std::max<long long>(std::max<long long>(E, T), std::max<long long>(P, R));
     const long long want = (work + SP_BLOCK * 4 - 1) / (SP_BLOCK * 4);
     sp->grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)dev_sms * std::min(occ, minb)));
+    {
+        int occ2 = 0;
+        SPCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, sp_packet, SP_BLOCK, 0));
+        sp->grid_packet = (int)std::max<long long>(1, std::min<long long>(sp->grid, (long long)dev_sms * std::max(occ2, 1)));
+    }
     D.red = sp->keep(sp_dalloc((size_t)SP_NRED * (size_t)sp->grid));
     SpState *st = nullptr;
     SPCK(cudaMalloc(&st, sizeof(SpState)));
@@ -1240,6 +1281,115 @@ void sp_launch_evals(gslnls_sparse_problem *sp, const double *theta, int buf)
 }
 
 } // namespace
+
+// lm / dogleg / ddogleg / subspace2D on a sparse-row problem with P <= trs_max_p(): the launch-ordered dense
+// trust-region step kernel (K3) driven by packets assembled from the stored nonzeros.  These are the methods the
+// reference's own sparse-Jacobian unit tests run (default "lm", inst/unit_tests/unit_tests_gslnls.R:302-346).
+static int sp_fit_dense(gslnls_sparse_problem *sp, const double *start, const int *ci, const double *cd, int want_jtj,
+                        int want_resid, gslnls_sparse_result *out)
+{
+    const int p = sp->P;
+    SpDev &D = sp->dev;
+    trs::Params P{};
+    P.p = p;
+    P.maxiter = ci[0];
+    P.trace = ci[1] ? 1 : 0;
+    P.trs = ci[2];
+    P.scale = (ci[3] == 1 || ci[3] == 2) ? ci[3] : 0;
+    P.batch_iters = 0;
+    P.cg_maxit = std::max<long long>(sp->R, 1);
+    P.factor_up = cd[0]; P.factor_down = cd[1]; P.avmax = cd[2]; P.h_df = cd[3]; P.h_fvv = cd[4];
+    P.xtol = cd[5]; P.ftol = cd[6]; P.gtol = cd[7];
+    P.cg_tol = 1.0e-6;
+    const int ns = trs::state_doubles(p), nr = trs::request_doubles(p), npk = trs::packet_doubles(p) + 1;
+    const int nt = P.maxiter + 1;
+    struct Bufs {
+        double *state = nullptr, *req = nullptr, *packet = nullptr, *start = nullptr, *ptr = nullptr, *str = nullptr,
+               *ctr = nullptr;
+        int *ndone = nullptr;
+        ~Bufs()
+        {
+            cudaFree(state); cudaFree(req); cudaFree(packet); cudaFree(start); cudaFree(ptr); cudaFree(str);
+            cudaFree(ctr); cudaFree(ndone);
+        }
+    } b;
+    SPCK(cudaMalloc(&b.state, sizeof(double) * ns));
+    SPCK(cudaMalloc(&b.req, sizeof(double) * nr));
+    SPCK(cudaMalloc(&b.packet, sizeof(double) * npk));
+    SPCK(cudaMalloc(&b.start, sizeof(double) * p));
+    SPCK(cudaMalloc(&b.ndone, sizeof(int)));
+    if (P.trace) {
+        SPCK(cudaMalloc(&b.ptr, sizeof(double) * (size_t)nt * p));
+        SPCK(cudaMalloc(&b.str, sizeof(double) * nt));
+        SPCK(cudaMalloc(&b.ctr, sizeof(double) * nt));
+        SPCK(cudaMemsetAsync(b.str, 0, sizeof(double) * nt, sp->stream));
+    }
+    SPCK(cudaMemcpyAsync(b.start, start, sizeof(double) * p, cudaMemcpyHostToDevice, sp->stream));
+    SPCK(trs_launch_reset(b.state, ns, b.req, nr, b.start, p, 1, b.ndone, sp->stream));
+    const long long cap = (long long)P.maxiter * 34 + 8; // every trial step is one packet
+    long long launches = 0;
+    int hdone = 0, buf = 0;
+    for (; launches < cap && hdone < 1; ++launches) {
+        sp_launch_evals(sp, b.req + 1, buf); // the request's trial point, read on the device
+        void *args[] = {&D, &b.packet, &buf};
+        SPCK(cudaLaunchCooperativeKernel((const void *)sp_packet, dim3((unsigned)sp->grid_packet), dim3(SP_BLOCK), args, 0,
+                                         sp->stream));
+        SPCK(trs_launch_step(P, b.state, b.packet, b.req, b.ptr, b.str, b.ctr, b.ndone, sp->stream));
+        SPCK(cudaMemcpyAsync(&hdone, b.ndone, sizeof(int), cudaMemcpyDeviceToHost, sp->stream));
+        SPCK(cudaStreamSynchronize(sp->stream));
+    }
+    std::vector<double> S((size_t)ns);
+    SPCK(cudaMemcpy(S.data(), b.state, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+    int status = (int)S[trs::S_STATUS];
+    if ((int)S[trs::S_PHASE] != trs::PH_DONE)
+        status = GSLNLS_EMAXITER;
+    const bool ok = status == GSLNLS_SUCCESS || status == GSLNLS_EMAXITER;
+    const double *v = S.data() + trs::S_COUNT;
+    out->p = p;
+    out->nrows = sp->R;
+    out->nterms = sp->T;
+    out->nnz = sp->E;
+    out->par = (double *)std::malloc(sizeof(double) * p);
+    out->grad_vec = (double *)std::malloc(sizeof(double) * p);
+    std::memcpy(out->par, ok ? v : start, sizeof(double) * p); // src/nls_large.c:293-302
+    std::memcpy(out->grad_vec, v + 2 * p, sizeof(double) * p);
+    out->ssr = S[trs::S_CHISQ1];
+    out->ssrtol = S[trs::S_CHISQ0] - S[trs::S_CHISQ1];
+    out->chisq_init = S[trs::S_CHISQ_INIT];
+    out->niter = (int)S[trs::S_NITER];
+    out->conv = status;
+    out->info = (int)S[trs::S_INFO];
+    out->status = gslnls_strerror(status);
+    out->neval[0] = (int64_t)S[trs::S_NEVAL_F];
+    out->neval[1] = (int64_t)S[trs::S_NEVAL_DFU];
+    out->neval[2] = (int64_t)S[trs::S_NEVAL_DF2];
+    out->neval[3] = 0;
+    out->launches = launches;
+    if (P.trace) {
+        out->ntrace = nt;
+        out->ssrtrace = (double *)std::malloc(sizeof(double) * nt);
+        SPCK(cudaMemcpy(out->ssrtrace, b.str, sizeof(double) * nt, cudaMemcpyDeviceToHost));
+    }
+    if (want_jtj) {
+        out->jtj = (double *)std::malloc(sizeof(double) * (size_t)p * p);
+        const double *M = v + 6 * p; // the state keeps the lower triangle
+        for (int i = 0; i < p; ++i)
+            for (int j = 0; j < p; ++j)
+                out->jtj[i * p + j] = i >= j ? M[i * p + j] : M[j * p + i];
+    }
+    if (want_resid) {
+        out->resid = (double *)std::malloc(sizeof(double) * (size_t)sp->R);
+        if (ok) {
+            const int rc = gslnls_sparse_eval(sp, out->par, out->resid, nullptr, nullptr, nullptr);
+            if (rc >= 1000)
+                return rc;
+        } else {
+            for (long long i = 0; i < sp->R; ++i)
+                out->resid[i] = NAN;
+        }
+    }
+    return status;
+}
 
 extern "C" {
 
@@ -1374,14 +1524,29 @@ GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start,
         set_error("maxiter must be >= 1");
         return GSLNLS_EINVAL;
     }
-    if (control_int[2] != 5) {
-        set_error("sparse-row problems run algorithm = \"cgst\" (Steihaug-Toint, matrix-free); the other trust-region "
-                  "methods factor a dense J^T J and are available on the dense path (p <= 64)");
-        return GSLNLS_EINVAL;
-    }
     if (sp->R < sp->P) {
         set_error("negative residual degrees of freedom, cannot fit a model with less observations than parameters");
         return GSLNLS_EINVAL;
+    }
+    if (control_int[2] != 5) {
+        if (control_int[2] == 1) {
+            set_error("algorithm = \"lmaccel\" needs the second directional derivative 'fvv', which sparse-row blocks "
+                      "do not carry");
+            return GSLNLS_EINVAL;
+        }
+        if (control_int[2] < 0 || control_int[2] > 5 || sp->P > trs_max_p()) {
+            set_error("sparse-row problems with more than 100 parameters run algorithm = \"cgst\" (Steihaug-Toint, "
+                      "matrix-free); lm, dogleg, ddogleg and subspace2D factor a dense J^T J");
+            return GSLNLS_EINVAL;
+        }
+        try {
+            SPCK(cudaSetDevice(sp->device));
+            return sp_fit_dense(sp, start, control_int, control_dbl, want_jtj, want_resid, out);
+        } catch (const std::exception &e) {
+            set_error(e.what());
+            gslnls_sparse_result_free(out);
+            return GSLNLS_ECUDA;
+        }
     }
     try {
         SPCK(cudaSetDevice(sp->device));

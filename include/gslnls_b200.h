@@ -342,9 +342,12 @@ GSLNLS_API const char *gslnls_trs_name(int algorithm);
  *   - term t of the block belongs to row rows[t] (rows == NULL: row0 + t); a row is the sum of its terms minus
  *     y[row], times sqrt(weights[row]).  A dense row such as sum(theta^2) - 0.25 is p one-parameter terms that
  *     share a row.
- * The solver is GSL's multilarge trust region with trs = cgst (Steihaug-Toint; J d and J^T u applied from the
- * stored nonzeros, never a dense J or J^T J), scaling more / levenberg / marquardt, the convergence tests and
- * driver of src/nls_fit.c:153-224.  control_int / control_dbl are those of gslnls_fit_large; algorithm must be 5. */
+ * The solver is GSL's multilarge trust region, driver and convergence tests of src/nls_fit.c:153-224.  algorithm 5
+ * (cgst, Steihaug-Toint) applies J d and J^T u from the stored nonzeros, never a dense J or J^T J, scaling more /
+ * levenberg / marquardt, any number of parameters.  Algorithms 0, 2, 3, 4 (lm, dogleg, ddogleg, subspace2D) factor
+ * a dense J^T J: for p_total <= 100 the library assembles the dense packet from the nonzeros and runs the dense
+ * trust-region kernel (the reference densifies J for the same purpose, src/nls_large.c:641-648); algorithm 1
+ * (lmaccel) is refused (blocks carry no fvv).  control_int / control_dbl are those of gslnls_fit_large. */
 typedef struct gslnls_sparse_problem gslnls_sparse_problem;
 typedef struct gslnls_sparse_result {
     int p;

@@ -12,15 +12,17 @@
 ##     blocks = list(
 ##       nls_block(~ sqrt(1e-5) * (th - 1), params = list(th = seq_len(p))),                   # rows 1..p
 ##       nls_block(~ th^2, params = list(th = seq_len(p)), rows = rep(p + 1L, p))),             # summed into row p+1
-##     y = c(rep(0, p), 0.25), start = 1:p, control = list(maxiter = 500))
+##     y = c(rep(0, p), 0.25), start = 1:p, algorithm = "cgst", control = list(maxiter = 500))
 ##
 ##   ## a grouped model, three nonzeros per Jacobian row: y ~ A[g] * exp(-lam * x) + b[g]
 ##   nls_block(~ A * exp(-lam * x) + b, params = list(A = g, lam = 2L * G + 1L, b = G + g), data = list(x = x))
 ##
 ## A parameter binding is one index (the same parameter for every term) or an integer vector with one (1-based)
 ## index per term.  Rows default to one row per term, blocks stacked in order; `rows` assigns terms to rows
-## explicitly and a row is the SUM of its terms minus y.  The solver is the reference's algorithm = "cgst"
-## (Steihaug-Toint, matrix-free): the other trust-region methods factor a dense J^T J.
+## explicitly and a row is the SUM of its terms minus y.  algorithm = "cgst" (Steihaug-Toint) is matrix-free and
+## has no size limit; "lm" (the reference's default), "dogleg", "ddogleg" and "subspace2D" factor a dense J^T J,
+## which the library assembles from the nonzeros for up to 100 parameters (the reference densifies J for the same
+## purpose, src/nls_large.c:641-648).
 
 nls_block <- function(formula, params, data = list(), rows = NULL) {
   rhs <- formula[[length(formula)]]
@@ -50,8 +52,13 @@ nls_block <- function(formula, params, data = list(), rows = NULL) {
     rows = if (is.null(rows)) NULL else as.integer(rows) - 1L, row0 = 0L, nterms = nterms), class = "nls_block")
 }
 
-gsl_nls_large_cuda_sparse <- function(blocks, y, start, weights = NULL, control = gsl_nls_control(),
+gsl_nls_large_cuda_sparse <- function(blocks, y, start,
+                                      algorithm = c("lm", "dogleg", "ddogleg", "subspace2D", "cgst"),
+                                      weights = NULL, control = gsl_nls_control(),
                                       trace = FALSE, want_jtj = length(start) <= 1000L, device = 0L) {
+  algorithm <- match.arg(algorithm)
+  if (algorithm != "cgst" && length(start) > 100L)
+    stop("more than 100 parameters: use algorithm = \"cgst\" (matrix-free); ", algorithm, " factors a dense J^T J")
   if (inherits(blocks, "nls_block")) blocks <- list(blocks)
   stopifnot(is.list(blocks), all(vapply(blocks, inherits, NA, "nls_block")))
   if (!is.numeric(start) || !length(start) || any(!is.finite(start)))
@@ -68,13 +75,15 @@ gsl_nls_large_cuda_sparse <- function(blocks, y, start, weights = NULL, control 
     if (any(unlist(blocks[[b]]$index) >= length(start)) || any(blocks[[b]]$base >= length(start)))
       stop("parameter index out of range in block ", b)
   }
-  ctl <- .cuda_pack_control(control, "cgst", trace)
+  ctl <- .cuda_pack_control(control, algorithm, trace)
   cFit <- .Call(C_nls_large_cuda_sparse, blocks, as.double(y), as.double(start),
                 if (is.null(weights)) NULL else as.double(weights), ctl$int, ctl$dbl,
                 c(as.integer(isTRUE(want_jtj)), 1L), as.integer(device))
   names(cFit$par) <- names(start)
   convInfo <- list(isConv = as.logical(!cFit$conv), finIter = cFit$niter, finTol = cFit$ssrtol,
-                   nEval = cFit$neval, trsName = "multilarge/steihaug-toint",
+                   nEval = cFit$neval,
+                   trsName = paste("multilarge", c(lm = "levenberg-marquardt", dogleg = "dogleg", ddogleg = "double-dogleg",
+                                                   subspace2D = "2D-subspace", cgst = "steihaug-toint")[[algorithm]], sep = "/"),
                    stopCode = cFit$conv, stopMessage = cFit$status)
   m <- list(
     getPars = function() cFit$par, resid = function() cFit$resid, deviance = function() cFit$ssr,

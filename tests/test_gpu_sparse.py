@@ -96,6 +96,36 @@ def test_penalty_p10_unit_test_fixture(G, scale):
     sp.close()
 
 
+@pytest.mark.parametrize("alg", ["lm", "dogleg", "ddogleg", "subspace2D"])
+def test_reference_sparse_unit_tests_with_dense_methods(G, alg, nist_problems):
+    """inst/unit_tests/unit_tests_gslnls.R:302-346 run their sparse-Jacobian fits with the DEFAULT algorithm (lm):
+    penalty_fit_dgC / dgR / dgT (p = 10, start 0.15) and Misra1a with a sparse Jacobian (6.2.1).  For p <= 100 the
+    sparse path assembles the dense packet from its nonzeros and runs the dense trust-region kernel; vs the oracle"""
+    p = 10
+    sp = penalty_problem(G, p)
+    start = np.full(p, 0.15)
+    got = sp.fit(start, algorithm=alg, trace=True, want_jtj=True, want_resid=True)
+    rows, y = penalty_rows(p)
+    ref = O.nls_large(rows, y, start, algorithm=alg, trace=True, want_resid_grad=True)
+    assert got["conv"] == ref["conv"] == 0 and got["niter"] == ref["niter"] and got["info"] == ref["info"]
+    assert rel(got["par"], ref["par"]) < 1e-8 and abs(got["ssr"] - ref["ssr"]) <= 1e-8 * ref["ssr"]
+    assert rel(got["ssrtrace"], ref["ssrtrace"]) < 1e-8
+    assert got["neval"]["f"] == ref["neval"]["f"] and got["neval"]["df2"] == ref["neval"]["df2"]
+    assert np.max(np.abs(np.tril(got["jtj"]) - ref["jtj"])) <= 1e-10 * np.max(np.abs(ref["jtj"]))
+    assert np.max(np.abs(got["resid"] - ref["resid"])) <= 1e-10 * np.max(np.abs(ref["resid"]))
+    sp.close()
+    pr = nist_problems["Misra1a"]
+    x, y = np.array(pr["data"]["x"]), np.array(pr["data"]["y"])
+    sp = G.SparseProblem(p=2, nrows=y.size)
+    sp.add_block("b1 * (1 - exp(-b2 * x))", {"b1": 0, "b2": 1}, {"x": x})
+    sp.set_response(y)
+    got = sp.fit(np.array(pr["start"], dtype=float), algorithm=alg)
+    ref = O.nls_large(O.sympy_rows("b1 * (1 - exp(-b2 * x))", ["b1", "b2"], {"x": x}), y, pr["start"], algorithm=alg)
+    assert got["conv"] == 0 and got["niter"] == ref["niter"] and rel(got["par"], ref["par"]) < 1e-8
+    assert np.max(np.abs(got["par"] - np.array(pr["target"]))) < 1.22e-4   # dotest_tol("6.2.1", ...)
+    sp.close()
+
+
 def test_readme_example4_penalty_p500(G, readme_examples):
     """README.md:1088-1146: p = 500, start 1:p, cgst -> SSR 0.004778845 as printed; coefficients vs the oracle"""
     e = readme_examples["example4_penalty"]
@@ -260,9 +290,13 @@ def test_grouped_exponential_large_properties(G):
 
 
 def test_sparse_error_paths(G):
-    sp = penalty_problem(G, 4)
+    sp = penalty_problem(G, 101)                     # the dense trust-region kernel stops at p = 100
     with pytest.raises(Exception, match="cgst"):
-        sp.fit(np.full(4, 0.15), algorithm="lm")
+        sp.fit(np.full(101, 0.15), algorithm="lm")
+    sp.close()
+    sp = penalty_problem(G, 4)
+    with pytest.raises(Exception, match="fvv"):
+        sp.fit(np.full(4, 0.15), algorithm="lmaccel")
     sp.close()
     # fewer rows than parameters (R/nls_large.R: negative residual degrees of freedom)
     sp = G.SparseProblem(p=3, nrows=2)

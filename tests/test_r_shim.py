@@ -59,7 +59,7 @@ def test_r_front_end_packs_control_like_the_reference():
     assert '{"C_nls_large_cuda", (DL_FUNC)&C_nls_large_cuda, 11}' in init
     assert '{"C_nls_large_cuda_sparse", (DL_FUNC)&C_nls_large_cuda_sparse, 8}' in init
     sp = open(os.path.join(ROOT, "r-package", "R", "nls_large_cuda_sparse.R")).read()
-    for piece in ("C_nls_large_cuda_sparse", '.cuda_pack_control(control, "cgst", trace)', "negative residual degrees of freedom",
+    for piece in ("C_nls_large_cuda_sparse", '.cuda_pack_control(control, algorithm, trace)', "negative residual degrees of freedom",
                   'class(out) <- c("gsl_nls", "nls")'):
         assert piece in sp, piece
     assert "export(gsl_nls_large_cuda_sparse)" in ns and "export(nls_block)" in ns
