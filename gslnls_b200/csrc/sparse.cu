@@ -29,6 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -40,7 +41,9 @@
 #include "../../include/gslnls_b200.h"
 #include "model.hpp"
 #include "nls_abi.h"
+#include "seg_build.hpp"
 #include "trs_launch.hpp"
+#include "upload.hpp"
 
 namespace cg = cooperative_groups;
 
@@ -979,51 +982,21 @@ double *sp_dalloc(size_t n)
     return d;
 }
 
-// entries sorted by segment (stable), cut into items of <= SP_ITEM
-struct SegBuild {
-    std::vector<int> ent_a, ent_b;
-    std::vector<long long> item_begin;
-    std::vector<int> seg_itemptr, item_a0, item_b0, long_seg, wide_item;
-    int nshort = 0;
-};
-void seg_finish(SegBuild &B, const std::vector<long long> &segptr)
+// big host lists go up through the pinned multi-threaded staging ring (csrc/upload.cpp), small ones directly
+template <class T>
+T *sp_upload_big(int device, const std::vector<T> &v, cudaStream_t stream)
 {
-    const size_t nseg = segptr.size() - 1;
-    B.seg_itemptr.assign(nseg + 1, 0);
-    B.item_begin.clear();
-    for (size_t s = 0; s < nseg; ++s) {
-        B.seg_itemptr[s] = (int)B.item_begin.size();
-        for (long long a = segptr[s]; a < segptr[s + 1]; a += SP_ITEM)
-            B.item_begin.push_back(a);
+    if (v.size() * sizeof(T) < (8u << 20))
+        return sp_upload(v);
+    T *d = nullptr;
+    SPCK(cudaMalloc(&d, v.size() * sizeof(T)));
+    const void *src[1] = {v.data()};
+    void *dst[1] = {d};
+    if (staged_upload(device, src, dst, 1, v.size() * sizeof(T), stream, upload_threads_default(1)) != 0) {
+        cudaFree(d);
+        throw std::runtime_error("staged upload of a gather list failed");
     }
-    B.seg_itemptr[nseg] = (int)B.item_begin.size();
-    B.item_begin.push_back(segptr[nseg]);
-    B.long_seg.clear();
-    for (size_t sg = 0; sg < nseg; ++sg)
-        if (B.seg_itemptr[sg + 1] - B.seg_itemptr[sg] > SP_LONG)
-            B.long_seg.push_back((int)sg);
-    // items whose entries are consecutive in ent_a (and ent_b)
-    const size_t nitems = B.item_begin.size() - 1;
-    B.wide_item.clear();
-    for (size_t it = 0; it < nitems; ++it)
-        if (B.item_begin[it + 1] - B.item_begin[it] > SP_SHORT)
-            B.wide_item.push_back((int)it);
-    B.nshort = (int)(nitems - B.wide_item.size());
-    B.item_a0.assign(nitems, -1);
-    B.item_b0.assign(nitems, -1);
-    for (size_t it = 0; it < nitems; ++it) {
-        const long long a = B.item_begin[it], b = B.item_begin[it + 1];
-        if (b <= a)
-            continue;
-        bool run = true;
-        for (long long e = a + 1; e < b && run; ++e)
-            run = B.ent_a[(size_t)e] == B.ent_a[(size_t)e - 1] + 1 &&
-                  (B.ent_b.empty() || B.ent_b[(size_t)e] == B.ent_b[(size_t)e - 1] + 1);
-        if (run) {
-            B.item_a0[it] = B.ent_a[(size_t)a];
-            B.item_b0[it] = B.ent_b.empty() ? 0 : B.ent_b[(size_t)a];
-        }
-    }
+    return d;
 }
 
 } // namespace
@@ -1088,56 +1061,65 @@ void sp_finalize(gslnls_sparse_problem *sp)
     const int P = sp->P;
     const long long R = sp->R;
 
-    // column of every nonzero, row of every term
+    // column of every nonzero, row of every term (threaded: these are sweeps over up to 2^31 entries)
+    const int nth = seg_threads(E);
     std::vector<int> ecol((size_t)E), trow((size_t)T);
+    std::atomic<int> bad_row{0}, bad_col{0};
     for (auto &b : sp->blocks) {
-        for (long long t = 0; t < b.nterms; ++t) {
-            const long long r = b.rows.empty() ? b.row0 + t : (long long)b.rows[(size_t)t];
-            if (r < 0 || r >= R)
-                throw std::runtime_error("row index out of range");
-            trow[(size_t)(b.term0 + t)] = (int)r;
-        }
-        for (int s = 0; s < b.k; ++s)
-            for (long long t = 0; t < b.nterms; ++t) {
-                const long long c = b.base[s] + (b.index[(size_t)s].empty() ? 0 : (long long)b.index[(size_t)s][(size_t)t]);
-                if (c < 0 || c >= P)
-                    throw std::runtime_error("parameter index out of range");
-                ecol[(size_t)(b.ent0 + (long long)s * b.nterms + t)] = (int)c;
-            }
-    }
-    // rows: terms sorted by row (stable counting sort) unless every row is exactly its own term
-    SegBuild rb, cb;
-    if (!ident) {
-        std::vector<long long> ptr((size_t)R + 1, 0);
-        for (long long t = 0; t < T; ++t)
-            ++ptr[(size_t)trow[(size_t)t] + 1];
-        for (long long r = 0; r < R; ++r)
-            ptr[(size_t)r + 1] += ptr[(size_t)r];
-        rb.ent_a.resize((size_t)T);
-        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
-        for (long long t = 0; t < T; ++t)
-            rb.ent_a[(size_t)fill[(size_t)trow[(size_t)t]]++] = (int)t;
-        seg_finish(rb, ptr);
-    }
-    // columns: nonzeros sorted by column, each with its row
-    {
-        std::vector<long long> ptr((size_t)P + 1, 0);
-        for (long long e = 0; e < E; ++e)
-            ++ptr[(size_t)ecol[(size_t)e] + 1];
-        for (int k = 0; k < P; ++k)
-            ptr[(size_t)k + 1] += ptr[(size_t)k];
-        cb.ent_a.resize((size_t)E);
-        cb.ent_b.resize((size_t)E);
-        std::vector<long long> fill(ptr.begin(), ptr.end() - 1);
-        for (auto &b : sp->blocks)
-            for (int s = 0; s < b.k; ++s)
-                for (long long t = 0; t < b.nterms; ++t) {
-                    const long long e = b.ent0 + (long long)s * b.nterms + t;
-                    const long long pos = fill[(size_t)ecol[(size_t)e]]++;
-                    cb.ent_a[(size_t)pos] = (int)e;
-                    cb.ent_b[(size_t)pos] = trow[(size_t)(b.term0 + t)];
+        seg_parallel(b.nterms, nth, [&](long long t0, long long t1, int) {
+            for (long long t = t0; t < t1; ++t) {
+                const long long r = b.rows.empty() ? b.row0 + t : (long long)b.rows[(size_t)t];
+                if (r < 0 || r >= R) {
+                    bad_row = 1;
+                    trow[(size_t)(b.term0 + t)] = 0;
+                } else {
+                    trow[(size_t)(b.term0 + t)] = (int)r;
                 }
-        seg_finish(cb, ptr);
+            }
+            for (int s = 0; s < b.k; ++s) {
+                const int *ix = b.index[(size_t)s].empty() ? nullptr : b.index[(size_t)s].data();
+                int *dst = ecol.data() + (size_t)(b.ent0 + (long long)s * b.nterms);
+                for (long long t = t0; t < t1; ++t) {
+                    const long long c = b.base[s] + (ix ? (long long)ix[t] : 0);
+                    if (c < 0 || c >= P) {
+                        bad_col = 1;
+                        dst[t] = 0;
+                    } else {
+                        dst[t] = (int)c;
+                    }
+                }
+            }
+        });
+    }
+    if (bad_row)
+        throw std::runtime_error("row index out of range");
+    if (bad_col)
+        throw std::runtime_error("parameter index out of range");
+    // rows: terms grouped by row (stable) unless every row is exactly its own term
+    SegLists rb, cb;
+    if (!ident) {
+        std::vector<long long> ptr;
+        rb.ent_a.resize((size_t)T);
+        seg_group(trow.data(), T, R, ptr, rb.ent_a.data(), nth);
+        seg_items(rb, ptr, SP_ITEM, SP_LONG, SP_SHORT, nth);
+    }
+    // columns: nonzeros grouped by column (stable: block, slot, term order inside a column), each with its row
+    {
+        std::vector<long long> ptr;
+        cb.ent_a.resize((size_t)E);
+        seg_group(ecol.data(), E, P, ptr, cb.ent_a.data(), nth);
+        cb.ent_b.resize((size_t)E);
+        seg_parallel(E, nth, [&](long long p0, long long p1, int) {
+            size_t bi = 0;
+            for (long long pos = p0; pos < p1; ++pos) {
+                const long long e = cb.ent_a[(size_t)pos];
+                while (!(e >= sp->blocks[bi].ent0 && e < sp->blocks[bi].ent0 + sp->blocks[bi].nterms * sp->blocks[bi].k))
+                    bi = (bi + 1) % sp->blocks.size();
+                const auto &b = sp->blocks[bi];
+                cb.ent_b[(size_t)pos] = trow[(size_t)(b.term0 + (e - b.ent0) % b.nterms)];
+            }
+        });
+        seg_items(cb, ptr, SP_ITEM, SP_LONG, SP_SHORT, nth);
     }
 
     SpDev &D = sp->dev;
@@ -1160,7 +1142,7 @@ void sp_finalize(gslnls_sparse_problem *sp)
         bd.push_back(d);
     }
     D.blocks = sp->keep(sp_upload(bd));
-    D.ecol = sp->keep(sp_upload(ecol));
+    D.ecol = sp->keep(sp_upload_big(sp->device, ecol, sp->stream));
     if (!sp->h_y.empty())
         D.y = sp->keep(sp_upload(sp->h_y));
     if (!sp->h_w.empty()) {
@@ -1178,7 +1160,7 @@ void sp_finalize(gslnls_sparse_problem *sp)
         D.nbad[i] = sp->keep(nb);
     }
     if (!ident) {
-        D.rows.ent_a = sp->keep(sp_upload(rb.ent_a));
+        D.rows.ent_a = sp->keep(sp_upload_big(sp->device, rb.ent_a, sp->stream));
         D.rows.item_begin = sp->keep(sp_upload(rb.item_begin));
         D.rows.seg_itemptr = sp->keep(sp_upload(rb.seg_itemptr));
         D.rows.item_a0 = sp->keep(sp_upload(rb.item_a0));
@@ -1192,8 +1174,8 @@ void sp_finalize(gslnls_sparse_problem *sp)
         D.rows.nseg = (int)R;
         D.rows.ipart = sp->keep(sp_dalloc((size_t)D.rows.nitems));
     }
-    D.cols.ent_a = sp->keep(sp_upload(cb.ent_a));
-    D.cols.ent_b = sp->keep(sp_upload(cb.ent_b));
+    D.cols.ent_a = sp->keep(sp_upload_big(sp->device, cb.ent_a, sp->stream));
+    D.cols.ent_b = sp->keep(sp_upload_big(sp->device, cb.ent_b, sp->stream));
     D.cols.item_begin = sp->keep(sp_upload(cb.item_begin));
     D.cols.seg_itemptr = sp->keep(sp_upload(cb.seg_itemptr));
     D.cols.item_a0 = sp->keep(sp_upload(cb.item_a0));
@@ -1440,7 +1422,7 @@ GSLNLS_API int gslnls_sparse_add_block(gslnls_sparse_problem *sp, const gslnls_m
             b.base[s] = slot_base[s];
             if (slot_index && slot_index[s]) {
                 b.index[(size_t)s].assign(slot_index[s], slot_index[s] + nterms);
-                b.d_index[s] = sp->keep(sp_upload(b.index[(size_t)s]));
+                b.d_index[s] = sp->keep(sp_upload_big(sp->device, b.index[(size_t)s], nullptr));
             }
         }
         if (rows)
@@ -1451,7 +1433,15 @@ GSLNLS_API int gslnls_sparse_add_block(gslnls_sparse_problem *sp, const gslnls_m
             double *d = nullptr;
             SPCK(cudaMalloc(&d, (size_t)nterms * sizeof(double)));
             sp->keep(d);
-            SPCK(cudaMemcpy(d, vars[v], (size_t)nterms * sizeof(double), cudaMemcpyHostToDevice));
+            const size_t bytes = (size_t)nterms * sizeof(double);
+            if (bytes < (8u << 20)) {
+                SPCK(cudaMemcpy(d, vars[v], bytes, cudaMemcpyHostToDevice));
+            } else { // pageable caller memory through the pinned staging ring; finalize waits for the copies
+                const void *src[1] = {vars[v]};
+                void *dst[1] = {d};
+                if (staged_upload(sp->device, src, dst, 1, bytes, nullptr, upload_threads_default(1)) != 0)
+                    throw std::runtime_error("staged upload of a data column failed");
+            }
             b.d_vars[v] = d;
         }
         sp->blocks.push_back(std::move(b));

@@ -111,3 +111,15 @@ def test_sparse_oracle_matches_dense_oracle_grouped():
     assert a["conv"] == b["conv"] == 0 and a["niter"] == b["niter"] and a["neval"] == b["neval"]
     assert np.max(np.abs(a["par"] - b["par"]) / np.abs(b["par"])) < 1e-9
     assert abs(a["ssr"] - b["ssr"]) <= 1e-11 * b["ssr"]
+
+
+def test_threaded_gather_list_builder_matches_the_serial_one():
+    """gslnls_b200/csrc/seg_build.hpp (host side of sp_finalize): the threaded stable grouping reproduces the serial
+    counting sort entry for entry on random / sorted / interleaved keys, items and their classes follow their
+    definitions -- compiled and run on the host by tests/host_harness/seg_main.cpp"""
+    d = os.path.join(ROOT, "tests", "host_harness")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    subprocess.check_call(["make", "-C", d, "-s", "_build/seg_main"], env=env)
+    r = subprocess.run([os.path.join(d, "_build", "seg_main")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "seg_build: ok" in r.stdout, r.stdout + r.stderr
