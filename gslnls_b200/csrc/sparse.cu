@@ -1673,6 +1673,8 @@ GSLNLS_API int gslnls_sparse_fit(gslnls_sparse_problem *sp, const double *start,
         D.ssrtrace = nullptr;
     } catch (const std::exception &e) {
         set_error(e.what());
+        sp->dev.trace = nullptr;
+        sp->dev.ssrtrace = nullptr;
         gslnls_sparse_result_free(out);
         return GSLNLS_ECUDA;
     }
