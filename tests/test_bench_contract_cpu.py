@@ -49,3 +49,18 @@ def test_synthetic_rows_are_shard_independent():
             xs.append(a)
             ys.append(b)
         assert np.array_equal(np.concatenate(xs), x) and np.array_equal(np.concatenate(ys), y)
+
+
+def test_reference_arm_of_the_sparse_configurations():
+    """--config sparse / penalty500: the CPU arm is oracle/sparse.py, one JSON line each"""
+    for cfg, extra, unit in (("sparse", ["--cpu-sample", "40000"], "iterations/s"), ("penalty500", ["--n", "60"], "fits/s")):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg,
+                              "--steps", "2", "--warmup", "1"] + extra, capture_output=True, text=True, timeout=600,
+                             cwd=ROOT)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1, lines
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0 and d["gpu_launches"] == 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+        assert d["e2e"]["value"] == d["value"] and d["config"]["final"]["ssr"] > 0
