@@ -642,11 +642,13 @@ def run_sparse(args):
     clocks = sampler.stop()
     # algorithmic bytes of the solver launches of one fit (per nonzero 8 B value + 4 B index per product,
     # 8 B per row vector element read or written)
-    E, T, R = 3 * n, n, n
+    # one of the three partials (d/db = 1) is a literal constant: no value is stored or streamed for it
+    E, Enc, T, R = 3 * n, 2 * n, n, n
     accepts = niter
-    per_cg = 2 * 12.0 * E + 16.0 * R
-    per_trial = 12.0 * E + 8.0 * T + 24.0 * R
-    per_accept = 12.0 * E + 8.0 * R
+    prod = 8.0 * Enc + 4.0 * E          # one application of J or J^T: 8 B per stored value + 4 B per index
+    per_cg = 2 * prod + 16.0 * R
+    per_trial = prod + 8.0 * T + 24.0 * R
+    per_accept = prod + 8.0 * R
     fit_trials = trials / args.steps
     fit_bytes = (cg / args.steps) * per_cg + fit_trials * per_trial + accepts * per_accept
     peak, peak_src = measured_peaks()
@@ -670,9 +672,10 @@ def run_sparse(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "algorithmic_bytes_per_launch": fit_bytes / fit_trials, "peak_source": peak_src,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                     "note": "bytes per fit = CG iterations x (24 E + 16 R) + trial points x (12 E + 8 T + 24 R) + "
-                             "accepted points x (12 E + 8 R), E nonzeros, T terms, R rows; time = CUDA events around "
-                             "every sp_step launch on its stream"},
+                     "note": "bytes per fit = CG iterations x (2 A + 16 R) + trial points x (A + 8 T + 24 R) + "
+                             "accepted points x (A + 8 R), A = 8 B x stored (non-constant) nonzeros + 4 B x all "
+                             "nonzeros = one application of J, T terms, R rows; time = CUDA events around every "
+                             "sp_step launch on its stream"},
         "e2e": {"value": int(r2["niter"]) / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int((20 * n + 8 * P) / niter),
                 "d2h_bytes_per_step": int(16 * P / niter), "ms_per_fit": 1e3 * e2e_s, "setup_s_first": setup_s,
                 "note": "SparseProblem(...) from pageable host arrays (data + index columns up, row / column gather "

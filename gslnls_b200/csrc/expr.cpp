@@ -804,6 +804,21 @@ std::string generate_model_source(const ModelSpec &spec)
         for (int j = 0; j < p; ++j)
             os << "    J[" << j << "] = " << names[j + 1] << ";\n";
         os << "}\n\n";
+        // partial derivatives that are literal constants (an additive or linear parameter): the sparse-row path
+        // stores and streams no column for them (csrc/sparse.cu)
+        if (p <= 30) {
+            unsigned mask = 0;
+            for (int j = 0; j < p; ++j)
+                if (g.is_const(roots[(size_t)j + 1]))
+                    mask |= 1u << j;
+            os << "#define GSLNLS_JCONST_MASK " << mask << "\n";
+            for (int j = 0; j < p; ++j)
+                if (mask >> j & 1u) {
+                    char buf[64];
+                    std::snprintf(buf, sizeof buf, "%a", g.at(roots[(size_t)j + 1]).c);
+                    os << "#define GSLNLS_JCONST_" << j << " " << buf << "\n";
+                }
+        }
         // two-stage form for the tiled kernel: invariants once per launch, rows from th[], c[], x[]
         const SplitCode sc = emit_split(g, roots, "    ", true);
         os << "#define GSLNLS_NC_FJ " << sc.nconst << "\n";

@@ -1534,6 +1534,11 @@ extern "C" __global__ void __launch_bounds__(256) nls_irls_scale(const NlsIrlsPa
 // ---------------------------------------------------------------- sparse-row problems: term evaluation
 // (csrc/sparse.cu holds the model-independent part: row sums, J d, J^T u, the matrix-free cgst solver)
 #if GSLNLS_JAC_MODE == 0 && GSLNLS_P <= NLS_SP_MAXSLOT
+#ifdef GSLNLS_JCONST_MASK
+#define NLS_JCONST_MASK ((unsigned)GSLNLS_JCONST_MASK)
+#else
+#define NLS_JCONST_MASK 0u
+#endif
 extern "C" __global__ void __launch_bounds__(256) nls_sparse_eval(const NlsSparseEvalParams prm)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1556,7 +1561,8 @@ extern "C" __global__ void __launch_bounds__(256) nls_sparse_eval(const NlsSpars
 #pragma unroll
         for (int s = 0; s < NLS_P; ++s) {
             okj = okj && nls_finite(J[s]);
-            prm.jv[(long long)s * prm.nterms + t] = J[s];
+            if (!(NLS_JCONST_MASK >> s & 1u)) // constant partials were written once when the problem was built
+                prm.jv[(long long)s * prm.nterms + t] = J[s];
         }
         badf += okf ? 0u : 1u;
         badj += okj ? 0u : 1u; // -> GSL_EBADFUNC when this Jacobian is adopted, src/nls_large.c:560-566

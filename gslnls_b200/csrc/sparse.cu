@@ -70,6 +70,8 @@ struct SpBlockDev {
     long long term0, nterms, ent0;
     int k, pad;
     int scalar_col[NLS_SP_MAXSLOT]; // global index of a scalar local parameter, -1: per-term index column
+    unsigned jconst_mask, pad2;     // local parameters whose partial derivative is a literal constant (additive /
+    double jconst[NLS_SP_MAXSLOT];  // linear parameters): their column of jv is written once and never streamed
 };
 
 // a family of segmented sums: entries grouped by segment (row or column), cut into items
@@ -84,6 +86,8 @@ struct SpSeg {
     const int *long_seg;         // [nlong] segments of more than SP_LONG items (a parameter every row depends on, a
     int nlong;                   // dense row): their item sums are added by a whole CTA instead of one thread
     int nitems, nseg, var;
+    const double *item_jc;       // [nitems] the constant value of a consecutive item inside a constant-partial
+                                 // column, NaN otherwise; nullptr when no block has constant partials
     const int *wide_item;        // [nwide] items of more than SP_SHORT entries (one warp each), or nullptr = all of them;
     int nwide, nshort;           // the others (a column with a handful of nonzeros) take one thread each
     double *ipart, *ipart2; // [nitems] item sums (second one: squares, for diag(J^T J))
@@ -222,6 +226,7 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
     const int k = K > 0 ? K : Bp->k;
     const double *jb = jv + Bp->ent0;
     const int *cb = S.ecol + Bp->ent0;
+    const unsigned cmask = Bp->jconst_mask;
     if (K > 0 && (S.var & 4) && ((nterms | Bp->ent0 | term0) & 3) == 0) {
         // four adjacent terms per thread: 1 KB (values) / 512 B (indices) contiguous per warp and load
         const long long nquad = nterms >> 2;
@@ -232,8 +237,12 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
             for (int s = 0; s < K; ++s) {
                 const long long e0 = (long long)s * nterms + 4 * i;
                 const int sc = Bp->scalar_col[s];
-                ja[s] = *reinterpret_cast<const double2 *>(jb + e0);
-                jb2[s] = *reinterpret_cast<const double2 *>(jb + e0 + 2);
+                if (cmask >> s & 1u) {
+                    ja[s] = jb2[s] = make_double2(Bp->jconst[s], Bp->jconst[s]);
+                } else {
+                    ja[s] = *reinterpret_cast<const double2 *>(jb + e0);
+                    jb2[s] = *reinterpret_cast<const double2 *>(jb + e0 + 2);
+                }
                 c[s] = make_int4(sc, sc, sc, sc);
                 if (sc < 0)
                     c[s] = *reinterpret_cast<const int4 *>(cb + e0);
@@ -277,7 +286,8 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
             for (int s = 0; s < K; ++s) {
                 const long long e0 = (long long)s * nterms + 2 * i;
                 const int sc = Bp->scalar_col[s];
-                j[s] = *reinterpret_cast<const double2 *>(jb + e0);
+                j[s] = (cmask >> s & 1u) ? make_double2(Bp->jconst[s], Bp->jconst[s])
+                                         : *reinterpret_cast<const double2 *>(jb + e0);
                 c[s] = make_int2(sc, sc);
                 if (sc < 0)
                     c[s] = *reinterpret_cast<const int2 *>(cb + e0);
@@ -311,8 +321,9 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
         for (int s = 0; s < k; ++s) {
             const long long e0 = (long long)s * nterms;
             const int sc = Bp->scalar_col[s]; // a scalar parameter: no index column to read
-            const double j0 = jb[e0 + t];
-            const double j1 = two ? jb[e0 + t1] : 0.0;
+            const bool jc = cmask >> s & 1u;  // a constant partial: no value to read
+            const double j0 = jc ? Bp->jconst[s] : jb[e0 + t];
+            const double j1 = two ? (jc ? Bp->jconst[s] : jb[e0 + t1]) : 0.0;
             const int c0 = sc >= 0 ? sc : cb[e0 + t];
             const int c1 = sc >= 0 ? sc : (two ? cb[e0 + t1] : c0);
             u0 = fma(j0, vec[c0], u0);
@@ -404,6 +415,9 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
                 const int b0 = G.item_b0[it];
                 const double *wp = wv ? wv + b0 : nullptr;
                 const double *swp = sw ? sw + b0 : nullptr;
+                // a run inside a constant-partial column: the value is known, only u (and sqrt(W)) stream
+                const double jcv = G.item_jc ? G.item_jc[it] : NAN;
+                const bool isc = jcv == jcv;
                 if ((G.var & 2) && wp && !swp && !squares) {
                     // the CG iteration's case, 8 x 32 entries per trip: all loads of a trip in flight, the additions
                     // of a lane in the same order as below
@@ -412,7 +426,7 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const int i = base + 32 * q;
-                            jq[q] = i < len ? sp[i] : 0.0;
+                            jq[q] = i < len ? (isc ? jcv : sp[i]) : 0.0;
                             wq[q] = i < len ? wp[i] : 0.0;
                         }
 #pragma unroll
@@ -423,7 +437,8 @@ __device__ void sp_items(const SpSeg &G, const double *src, const double *wv, co
                 } else
 #pragma unroll 4
                 for (int i = lane; i < len; i += 32) {
-                    const double j = swp ? sp[i] * swp[i] : sp[i];
+                    const double j0 = isc ? jcv : sp[i];
+                    const double j = swp ? j0 * swp[i] : j0;
                     if (wp)
                         s = fma(j, wp[i], s);
                     if (squares)
@@ -910,6 +925,12 @@ __global__ void __launch_bounds__(SP_BLOCK) sp_jtj(const SpDev S, int cur)
     }
 }
 
+__global__ void sp_fill(double *dst, long long n, double v)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = v;
+}
+
 // Dense normal-equation packet [J^T J lower packed, row-major | J^T f | f^T f | non-finite residual count] of a
 // sparse-row problem at the point evaluated into buffer `buf`: what K3 (csrc/trs_core.h, the dense trust-region
 // state machine: lm, dogleg, ddogleg, subspace2D) consumes.  J^T J column c is J^T (J e_c) from the stored
@@ -958,6 +979,8 @@ struct SpBlockHost {
     int k = 0, nvar = 0;
     long long nterms = 0, term0 = 0, ent0 = 0;
     int base[NLS_SP_MAXSLOT] = {0};
+    unsigned jconst_mask = 0;             // from the model source (GSLNLS_JCONST_MASK / GSLNLS_JCONST_<j>, csrc/expr.cpp)
+    double jconst[NLS_SP_MAXSLOT] = {0};
     std::vector<std::vector<int>> index; // per slot: empty = scalar parameter
     std::vector<int> rows;               // empty: identity from row0
     long long row0 = 0;
@@ -1139,6 +1162,9 @@ void sp_finalize(gslnls_sparse_problem *sp)
         d.k = b.k;
         for (int s = 0; s < NLS_SP_MAXSLOT; ++s)
             d.scalar_col[s] = (s < b.k && b.index[(size_t)s].empty()) ? b.base[s] : -1;
+        d.jconst_mask = b.jconst_mask;
+        for (int s = 0; s < b.k; ++s)
+            d.jconst[s] = b.jconst[s];
         bd.push_back(d);
     }
     D.blocks = sp->keep(sp_upload(bd));
@@ -1185,6 +1211,35 @@ void sp_finalize(gslnls_sparse_problem *sp)
     D.cols.nshort = cb.nshort;
     D.cols.nwide = (int)cb.wide_item.size();
     D.cols.wide_item = cb.nshort ? sp->keep(sp_upload(cb.wide_item)) : nullptr;
+    // constant partials: their columns of jv are written here, once, in both buffers (the term-evaluation kernel
+    // skips them); consecutive items inside such a column carry the value and stream no jv at all
+    bool any_const = false;
+    for (auto &b : sp->blocks)
+        any_const = any_const || b.jconst_mask != 0;
+    if (any_const) {
+        std::vector<double> jc(cb.item_a0.size(), std::nan(""));
+        for (size_t it = 0; it < jc.size(); ++it) {
+            if (cb.item_a0[it] < 0)
+                continue;
+            const long long e0 = cb.item_a0[it], e1 = e0 + (cb.item_begin[it + 1] - cb.item_begin[it]) - 1;
+            for (auto &b : sp->blocks)
+                if (e0 >= b.ent0 && e1 < b.ent0 + b.nterms * b.k) {
+                    const long long s0 = (e0 - b.ent0) / b.nterms, s1 = (e1 - b.ent0) / b.nterms;
+                    if (s0 == s1 && (b.jconst_mask >> s0 & 1u))
+                        jc[it] = b.jconst[s0];
+                }
+        }
+        D.cols.item_jc = sp->keep(sp_upload(jc));
+        for (auto &b : sp->blocks)
+            for (int sl = 0; sl < b.k; ++sl)
+                if (b.jconst_mask >> sl & 1u)
+                    for (int i = 0; i < 2; ++i) {
+                        const long long cnt = b.nterms;
+                        sp_fill<<<(unsigned)std::min<long long>((cnt + 255) / 256, 4096), 256>>>(  // legacy stream: after the zero-fill
+                            D.jv[i] + b.ent0 + (long long)sl * b.nterms, cnt, b.jconst[sl]);
+                        SPCK(cudaGetLastError());
+                    }
+    }
     D.cols.nitems = (int)cb.item_begin.size() - 1;
     D.cols.nseg = P;
     D.cols.var = D.var;
@@ -1418,6 +1473,20 @@ GSLNLS_API int gslnls_sparse_add_block(gslnls_sparse_problem *sp, const gslnls_m
         b.nterms = nterms;
         b.row0 = row0;
         b.index.resize((size_t)b.k);
+        {
+            const size_t pos = m->source.find("#define GSLNLS_JCONST_MASK ");
+            if (pos != std::string::npos)
+                b.jconst_mask = (unsigned)std::strtoul(m->source.c_str() + pos + 27, nullptr, 10);
+            for (int s = 0; s < b.k; ++s)
+                if (b.jconst_mask >> s & 1u) {
+                    const std::string key = "#define GSLNLS_JCONST_" + std::to_string(s) + " ";
+                    const size_t q = m->source.find(key);
+                    if (q == std::string::npos)
+                        b.jconst_mask &= ~(1u << s);
+                    else
+                        b.jconst[s] = std::strtod(m->source.c_str() + q + key.size(), nullptr);
+                }
+        }
         for (int s = 0; s < b.k; ++s) {
             b.base[s] = slot_base[s];
             if (slot_index && slot_index[s]) {
