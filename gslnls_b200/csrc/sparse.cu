@@ -58,7 +58,7 @@ namespace {
 constexpr int SP_BLOCK = 256;
 constexpr int SP_ITEM = 2048; // entries per segmented-sum item (one warp: 64 per lane)
 constexpr int SP_NRED = 6;    // scalar reduction slots
-constexpr int SP_VAR_DEFAULT = 7;
+constexpr int SP_VAR_DEFAULT = 15;
 constexpr int SP_SHORT = 8;   // entries per item up to which one thread adds them
 constexpr int SP_LONG = 64;   // items per segment above which a CTA adds them
 constexpr int SP_MINB_DEFAULT = 4; // resident CTAs per SM of the solver kernel: 4 (64 registers), 3 (80) or 2 (128);
@@ -106,8 +106,9 @@ struct SpState {
 
 struct SpDev {
     int P, R, nblocks, maxiter, scale, want_trace;
+    int zero; // always 0, but only the host knows (see sp_term_dot_block)
     int var; // loop variants (GSLNLS_SP_VAR bits): 1 = adjacent term pairs with 128-bit loads in J v, 2 = 8-deep item loads,
-             // 4 = four adjacent terms per thread
+             // 4 = four adjacent terms per thread, 8 = that loop with pinned load order
     long long T, E;
     long long cg_maxit;
     double factor_up, factor_down, xtol, gtol, cg_tol;
@@ -227,6 +228,73 @@ __device__ __forceinline__ double sp_term_dot_block(const SpDev &S, const SpBloc
     const double *jb = jv + Bp->ent0;
     const int *cb = S.ecol + Bp->ent0;
     const unsigned cmask = Bp->jconst_mask;
+    if (K > 0 && (S.var & 8) && ((nterms | Bp->ent0 | term0) & 3) == 0) {
+        // The quad loop below with its issue order pinned.  ptxas schedules the plain form slot by slot -- value and
+        // index loads of slot s, its gathers, its FMAs (which wait for the gathers), only then the loads of slot
+        // s + 1 -- so a trip is K serial DRAM round trips (SASS in profiles/r02_summary.md: 5.5 us per trip).
+        // Here every streaming load of the trip is a volatile ld.global issued before the first gather.
+        const long long nquad = nterms >> 2;
+        int scs[K > 0 ? K : 1];
+        double jcs[K > 0 ? K : 1];
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+            scs[s] = Bp->scalar_col[s];
+            jcs[s] = Bp->jconst[s];
+        }
+        for (long long i = SP_GTID; i < nquad; i += SP_GSTRIDE) {
+            double2 ja[K > 0 ? K : 1], jb2[K > 0 ? K : 1];
+            int4 c[K > 0 ? K : 1];
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                const long long e0 = (long long)s * nterms + 4 * i;
+                ja[s] = jb2[s] = make_double2(jcs[s], jcs[s]);
+                if (!(cmask >> s & 1u)) {
+                    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(ja[s].x), "=d"(ja[s].y) : "l"(jb + e0));
+                    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(jb2[s].x), "=d"(jb2[s].y) : "l"(jb + e0 + 2));
+                }
+                c[s] = make_int4(scs[s], scs[s], scs[s], scs[s]);
+                if (scs[s] < 0)
+                    asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(c[s].x), "=r"(c[s].y), "=r"(c[s].z), "=r"(c[s].w)
+                                 : "l"(cb + e0));
+            }
+            // an opaque zero that depends on every index load: no gather can be scheduled before the last
+            // streaming load of the trip has been issued
+            int all = 0, dep;
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                all ^= c[s].x;
+            dep = all & S.zero; // S.zero is a kernel argument (0): ptxas cannot fold it the way it folds "x & 0"
+            const double *vd = vec + dep;
+            double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                u0 = fma(ja[s].x, vd[c[s].x], u0);
+                u1 = fma(ja[s].y, vd[c[s].y], u1);
+                u2 = fma(jb2[s].x, vd[c[s].z], u2);
+                u3 = fma(jb2[s].y, vd[c[s].w], u3);
+            }
+            const long long r = term0 + 4 * i;
+            if (FUSE) {
+                if (S.sw) {
+                    u0 *= S.sw[r];
+                    u1 *= S.sw[r + 1];
+                    u2 *= S.sw[r + 2];
+                    u3 *= S.sw[r + 3];
+                }
+                *reinterpret_cast<double2 *>(out + r) = make_double2(u0, u1);
+                *reinterpret_cast<double2 *>(out + r + 2) = make_double2(u2, u3);
+                acc = fma(u0, u0, acc);
+                acc = fma(u1, u1, acc);
+                acc = fma(u2, u2, acc);
+                acc = fma(u3, u3, acc);
+            } else {
+                *reinterpret_cast<double2 *>(S.tmpT + r) = make_double2(u0, u1);
+                *reinterpret_cast<double2 *>(S.tmpT + r + 2) = make_double2(u2, u3);
+            }
+        }
+        return acc;
+    }
     if (K > 0 && (S.var & 4) && ((nterms | Bp->ent0 | term0) & 3) == 0) {
         // four adjacent terms per thread: 1 KB (values) / 512 B (indices) contiguous per warp and load
         const long long nquad = nterms >> 2;
