@@ -742,7 +742,6 @@ def run_penalty(args):
     nonzeros, one CTA), so this line measures launch and barrier latency, not bandwidth"""
     import torch
 
-    from oracle import sparse as OS
     torch.cuda.set_device(0)
     p = args.n or 500
     sp, start = penalty_problem_gpu(p)
@@ -798,6 +797,7 @@ def run_penalty(args):
                 "d2h_bytes_per_step": int(16 * p), "note": "problem construction (two NVRTC models, gather lists) + fit"},
     }
     if not args.no_cpu_baseline:
+        from oracle import sparse as OS  # the checker's restatement, timed as the CPU baseline only
         m4, yy4 = OS.penalty_model(p)
         OS.nls_large_sparse(m4, yy4, start, maxiter=500)
         t0 = time.perf_counter()
